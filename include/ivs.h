@@ -1,0 +1,248 @@
+/* ivs.h -- C ABI of the B200-native Vlasov-Fokker-Planck step ("Inovesa hot path").
+ *
+ * This is the drop-in boundary: a thin CUDA handler that takes the place of the reference's
+ * OpenCL handler (OCLH, /root/reference/inc/CL/OpenCLHandler.hpp:63-314) and of its clFFT/FFTW
+ * wrappers (/root/reference/inc/FFTWWrapper.hpp:24-107).  Every entry point names the reference
+ * interface it replaces.  Plain pointers and sizes only; no C++ types, no exceptions, no torch.
+ *
+ * Conventions
+ *  - every function returns an ivs_status (0 = ok); ivs_last_error() gives the message
+ *  - `void* d_*` arguments are DEVICE pointers obtained from ivs_malloc()
+ *  - grids are fp32, laid out f[x][y] with y (energy) contiguous, exactly like
+ *    PhaseSpace::_data (/root/reference/inc/PS/PhaseSpace.hpp:445-447); one bunch per grid
+ *  - all work is asynchronous on the context's stream (the reference's single in-order
+ *    queue, /root/reference/src/CL/OpenCLHandler.cpp:56-60); ivs_sync() == OCLH::finish()
+ *  - arithmetic is fp32 and follows the reference's CPU path operation by operation
+ *    (see DESIGN.md "Arithmetic contract"); IVS_ARITH_FMA contracts a*b+c exactly where
+ *    GCC contracts the reference's loops when built with its own flags (-O3 -march=native),
+ *    IVS_ARITH_STRICT rounds every product (a reference build with -ffp-contract=off).
+ */
+#ifndef IVS_H
+#define IVS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int ivs_status;
+enum {
+    IVS_OK = 0,
+    IVS_ERR_INVALID_ARGUMENT = 1, /* mirrors std::invalid_argument of the reference */
+    IVS_ERR_CUDA = 2,             /* mirrors cl::Error */
+    IVS_ERR_UNSUPPORTED = 3,
+    IVS_ERR_HALO = 4,             /* a displacement exceeded what the fused kernel staged */
+    IVS_ERR_NO_DEVICE = 5
+};
+
+enum { IVS_ARITH_FMA = 0, IVS_ARITH_STRICT = 1 };
+
+typedef struct ivs_ctx ivs_ctx; /* replaces oclhptr_t (inc/CL/OpenCLHandler.hpp:36-41) */
+
+/* ------------------------------------------------------------------ context / memory */
+
+/* OCLH::OCLH(device,...) src/CL/OpenCLHandler.cpp:23-92.  `device` is the CUDA ordinal. */
+ivs_status ivs_ctx_create(int device, int arith, ivs_ctx** out);
+/* OCLH::~OCLH src/CL/OpenCLHandler.cpp:163-169 (finish, then release) */
+ivs_status ivs_ctx_destroy(ivs_ctx* ctx);
+/* message of the last failing call on this context ("" if none); ctx may be NULL for
+ * errors of ivs_ctx_create */
+const char* ivs_last_error(const ivs_ctx* ctx);
+/* OCLH::listCLDevices src/CL/OpenCLHandler.cpp:171-200: number of CUDA devices (0 if none) */
+int ivs_device_count(void);
+/* library version string and the CUDA arch it was built for */
+const char* ivs_version(void);
+/* the raw cudaStream_t of the context (for callers that interleave their own work) */
+void* ivs_ctx_stream(ivs_ctx* ctx);
+/* number of kernels this library launched on the context since creation */
+uint64_t ivs_ctx_launch_count(const ivs_ctx* ctx);
+
+/* cl::Buffer(context, CL_MEM_READ_WRITE, bytes) */
+ivs_status ivs_malloc(ivs_ctx* ctx, size_t bytes, void** d_ptr);
+ivs_status ivs_free(ivs_ctx* ctx, void* d_ptr);
+/* OCLH::enqueueWriteBuffer inc/CL/OpenCLHandler.hpp:236-262 (blocking=CL_TRUE semantics
+ * for pageable memory; asynchronous if `host` is pinned via ivs_host_alloc) */
+ivs_status ivs_upload(ivs_ctx* ctx, void* d_dst, const void* host, size_t bytes);
+/* OCLH::enqueueReadBuffer inc/CL/OpenCLHandler.hpp:209-234 (always blocking, as CL_TRUE) */
+ivs_status ivs_download(ivs_ctx* ctx, void* host, const void* d_src, size_t bytes);
+/* OCLH::enqueueCopyBuffer inc/CL/OpenCLHandler.hpp:190-207 */
+ivs_status ivs_copy(ivs_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+ivs_status ivs_memset_zero(ivs_ctx* ctx, void* d_dst, size_t bytes);
+/* pinned host staging memory for the asynchronous transfers of the e2e path */
+ivs_status ivs_host_alloc(ivs_ctx* ctx, size_t bytes, void** host_ptr);
+ivs_status ivs_host_free(ivs_ctx* ctx, void* host_ptr);
+/* OCLH::flush / OCLH::finish inc/CL/OpenCLHandler.hpp:283-288 */
+ivs_status ivs_flush(ivs_ctx* ctx);
+ivs_status ivs_sync(ivs_ctx* ctx);
+
+/* ------------------------------------------------------------------ source maps (unfused ops)
+ * 1:1 replacements of the reference's per-map kernels; results follow the CPU loops.   */
+
+/* KickMap::apply(), Axis::y  (CPU src/SM/KickMap.cpp:243-266; OpenCL kernel apply_yKick
+ * :113-163).  out[x][y] = sum_j w_j(x) in[x][y+first(x)+j], taps outside the grid dropped.
+ * d_offset holds n floats: KickMap::_offset (what swapOffset()/getForce() exchange,
+ * inc/SM/KickMap.hpp:47-55); the tap table of KickMap::updateSM() (src/SM/KickMap.cpp:339-389)
+ * is rebuilt on the fly with the reference's fp32 arithmetic.  it = InterpolationType 1..4. */
+ivs_status ivs_kick_y(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n,
+                      const void* d_offset, uint32_t it);
+/* KickMap::apply(), Axis::x  (CPU src/SM/KickMap.cpp:221-242; kernel apply_xKick :63-110) */
+ivs_status ivs_kick_x(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n,
+                      const void* d_offset, uint32_t it);
+/* FokkerPlanckMap::apply() (CPU src/SM/FokkerPlanckMap.cpp:170-213; kernel applySM_Y :122-141).
+ * d_weights: n rows of 5 floats = stencil weights on y-2..y+2 (built by
+ * ivs_fokker_planck_weights from the constructor arithmetic, src/SM/FokkerPlanckMap.cpp:31-118). */
+ivs_status ivs_fokker_planck(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n,
+                             const void* d_weights);
+/* host helper: fills weights[n*5] like the FokkerPlanckMap constructor
+ * (fptype 0..3 = FPType, derivation 3|4 = DerivationType; e1 = damping decrement;
+ * pmin/pmax describe the energy axis Ruler).  Pure host arithmetic, no GPU needed. */
+ivs_status ivs_fokker_planck_weights(uint32_t n, float pmin, float pmax, float e1,
+                                     uint32_t fptype, uint32_t derivation, float* weights);
+/* RotationMap::apply() (CPU src/SM/RotationMap.cpp:97-176 with genHInfo :190-260; kernels
+ * applyRotation :321-438 / applySM4sat :264-319).  Axis rulers are given by (min,max) per
+ * axis; clamp != 0 requires it == 4 (std::invalid_argument otherwise, :83-87) */
+ivs_status ivs_rotate(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, float angle,
+                      float qmin, float qmax, float pmin, float pmax, uint32_t it, int clamp);
+/* SourceMap::apply() generic gather (CPU src/SM/SourceMap.cpp:75-109; kernel applySM1D
+ * :121-139): out[i] = sum_{j<ip} in[index[i*ip+j]]*weight[i*ip+j]; table = array of
+ * {uint32 index; float weight} (the reference's `hi`, inc/SM/SourceMap.hpp:37-40) */
+ivs_status ivs_apply_source_map(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t ncells,
+                                const void* d_hinfo, uint32_t ip);
+/* Identity::apply() inc/SM/Identity.hpp:36-55 */
+ivs_status ivs_identity(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n);
+
+/* ------------------------------------------------------------------ phase-space reductions */
+
+/* PhaseSpace::simpsonWeights src/PS/PhaseSpace.cpp:486-501 (host arithmetic) */
+ivs_status ivs_simpson_weights(uint32_t n, float delta, float* ws);
+/* PhaseSpace::updateXProjection (CPU src/PS/PhaseSpace.cpp:313-321; kernel projectionX :538-550) */
+ivs_status ivs_project_x(ivs_ctx* ctx, const void* d_grid, uint32_t n, const void* d_ws,
+                         void* d_proj);
+/* PhaseSpace::updateYProjection src/PS/PhaseSpace.cpp:325-340 (host loop in the reference) */
+ivs_status ivs_project_y(ivs_ctx* ctx, const void* d_grid, uint32_t n, const void* d_ws,
+                         void* d_proj);
+/* PhaseSpace::integrate (CPU src/PS/PhaseSpace.cpp:229-238; kernels integral/integralSum
+ * :509-532): *d_integral = sum_x proj[x]*ws[x] */
+ivs_status ivs_integrate(ivs_ctx* ctx, const void* d_proj, uint32_t n, const void* d_ws,
+                         void* d_integral);
+/* PhaseSpace::normalize src/PS/PhaseSpace.cpp:342-372: grid *= filling_set / *d_integral */
+ivs_status ivs_normalize(ivs_ctx* ctx, void* d_grid, uint32_t n, float filling_set,
+                         const void* d_integral);
+/* PhaseSpace::average + variance src/PS/PhaseSpace.cpp:241-289 on one projection:
+ * d_out[0] = mean, d_out[1] = variance, d_out[2] = rms; axis values = amin + i*delta */
+ivs_status ivs_moments(ivs_ctx* ctx, const void* d_proj, uint32_t n, float amin, float delta,
+                       const void* d_integral, void* d_out3);
+
+/* ------------------------------------------------------------------ electric field */
+
+/* ElectricField::wakePotential (CPU src/PS/ElectricField.cpp:186-253; OpenCL chain
+ * copy -> clFFT r2c -> wakeloss -> clFFT c2r -> scalewp :188-205): zero-pad the bunch
+ * profile (n floats) to nmax, r2c FFT, multiply bins < nmax/2 by the impedance
+ * (nmax complex<float>, upper half unused, Nyquist = 0), c2r FFT, scale by `wakescaling`
+ * (already divided by nmax like ElectricField::_wakescaling :58) and keep the first n
+ * samples.  One CTA, hand-written shared-memory FFT; nmax a power of two, n <= nmax <= 16384.
+ * d_formfactor (nmax/2+1 complex, may be NULL) receives the spectrum of the profile. */
+ivs_status ivs_wake_potential(ivs_ctx* ctx, const void* d_profile, uint32_t n,
+                              const void* d_impedance, uint32_t nmax, float wakescaling,
+                              void* d_wake, void* d_formfactor);
+/* The wake FUNCTION of the same operator, w[m], m = -(n-1)..(n-1) (2n-1 floats, w[0] at
+ * index n-1), such that wakePotential()[x] == sum_x' profile[x'] * w[x - x'] exactly in
+ * real arithmetic (the zero padding nmax >= 2n removes every circular wrap).  Used by the
+ * fused step, which applies the kick from a direct Toeplitz product per row block. */
+ivs_status ivs_wake_function(ivs_ctx* ctx, const void* d_impedance, uint32_t nmax,
+                             float wakescaling, uint32_t n, void* d_wakefunction);
+/* ElectricField::updateCSR src/PS/ElectricField.cpp:133-184: spectrum[i] (nmax floats) and
+ * *d_power = sum_i delta_f * spectrum[i]; dq = grid spacing, f_scale = c/sigma_z ("Hertz"
+ * scale of the frequency ruler), cutoff <= 0 disables the shielding factor */
+ivs_status ivs_csr_power(ivs_ctx* ctx, const void* d_profile, uint32_t n,
+                         const void* d_impedance, uint32_t nmax, float dq, float f_scale,
+                         float cutoff, void* d_spectrum, void* d_power);
+
+/* ------------------------------------------------------------------ passive particles */
+
+/* SourceMap::applyToAll with KickMap::applyTo (src/SM/SourceMap.cpp:111-117,
+ * src/SM/KickMap.cpp:280-303): particles = np pairs {x,y} in grid units
+ * (PhaseSpace::Position); axis 0 = x-kick (drift), 1 = y-kick (RF, wake) */
+ivs_status ivs_track_kick(ivs_ctx* ctx, void* d_particles, uint32_t np, const void* d_offset,
+                          uint32_t n, int axis);
+/* FokkerPlanckMap::applyTo src/SM/FokkerPlanckMap.cpp:214-268.  fptrack 0..3; mode 3
+ * (stochastic) draws from a counter-based generator keyed by (seed, step, particle) --
+ * the reference's unseeded mt19937 (:22-24) cannot be reproduced */
+ivs_status ivs_track_fokker_planck(ivs_ctx* ctx, void* d_particles, uint32_t np,
+                                   const void* d_grid, uint32_t n, const void* d_weights,
+                                   uint32_t fptrack, float e1, float dp, uint64_t seed,
+                                   uint64_t step);
+/* RotationMap::applyTo src/SM/RotationMap.cpp:178-188 */
+ivs_status ivs_track_rotate(ivs_ctx* ctx, void* d_particles, uint32_t np, float angle,
+                            float zerobin_x, float zerobin_y);
+
+/* ------------------------------------------------------------------ whole simulation step
+ * The loop body of main() (src/main.cpp:948-1053) for one bunch:
+ *   wake potential -> wake kick -> RF kick -> drift -> Fokker-Planck -> X projection
+ * as ONE fused kernel per step (plus nothing else), captured in a CUDA graph.            */
+
+typedef struct ivs_sim ivs_sim;
+
+typedef struct ivs_sim_desc {
+    uint32_t n;            /* GridSize (nx = ny) */
+    uint32_t members;      /* independent simulations advanced in lock-step (ensemble); >= 1 */
+    uint32_t it;           /* InterpolationPoints 1..4 */
+    uint32_t nmax;         /* padded FFT length (power of two, >= 2n), 0 = no wake map */
+    uint32_t n_particles;  /* tracked particles per member (0 = none) */
+    uint32_t fptrack;      /* FPTracking for the particles */
+    uint32_t flags;        /* IVS_SIM_* */
+    uint32_t reserved;
+    float dq;              /* axis 0 delta (Simpson weights are built from it, as the reference) */
+    float dp;              /* axis 1 delta */
+    float e1;              /* damping decrement (tracking only; the stencil is in fp_weights) */
+    float reserved_f;
+    const float* rf_offset;     /* host, n floats: RFKickMap::_offset (getForce()) */
+    const float* drift_offset;  /* host, n floats: DriftMap::_offset */
+    const float* fp_weights;    /* host, n*5 floats (ivs_fokker_planck_weights) or NULL = Identity */
+    const float* impedance;     /* host, nmax complex<float> (wake impedance) or NULL */
+    const float* wakescaling;   /* host, `members` floats: ElectricField::_wakescaling per member */
+    const float* grid;          /* host, members*n*n floats: initial density (grid_t1) */
+    const float* particles;     /* host, members*n_particles*2 floats or NULL */
+    uint64_t seed;
+} ivs_sim_desc;
+
+enum {
+    IVS_SIM_WAKE_FFT = 1u,      /* per-step wake potential through the FFT kernel instead of the
+                                   Toeplitz product (same operator) */
+    IVS_SIM_UNFUSED = 2u,       /* run the step as the reference's kernel sequence (debug / parity) */
+    IVS_SIM_NO_GRAPH = 4u       /* launch kernels directly instead of replaying a CUDA graph */
+};
+
+ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* desc, ivs_sim** out);
+ivs_status ivs_sim_destroy(ivs_sim* sim);
+/* advance every member by nsteps (asynchronous) */
+ivs_status ivs_sim_step(ivs_sim* sim, uint32_t nsteps);
+/* steps taken so far */
+uint64_t ivs_sim_steps_done(const ivs_sim* sim);
+/* device pointers to the current state (valid until the next ivs_sim_step):
+ * grid [members][n][n], x-projection [members][n], wake potential [members][n]
+ * (the offsets the last step applied), particles [members][np][2] */
+ivs_status ivs_sim_state(ivs_sim* sim, void** d_grid, void** d_profile, void** d_wake,
+                         void** d_particles);
+/* PhaseSpace::syncCLMem(dev2cpu) src/PS/PhaseSpace.cpp:395-412: blocking copies to host
+ * (any pointer may be NULL) */
+ivs_status ivs_sim_download(ivs_sim* sim, float* grid, float* profile, float* wake,
+                            float* particles);
+/* replace the density of all members (PhaseSpace::syncCLMem(cpu2dev)); recomputes the
+ * X projection on the device */
+ivs_status ivs_sim_upload_grid(ivs_sim* sim, const float* grid);
+/* out-step observables of main.cpp:961-1033 for every member, computed on the device:
+ * obs[m*8 + {0: integral, 1: mean_q, 2: var_q, 3: sigma_q, 4: mean_p, 5: var_p, 6: sigma_p,
+ * 7: csr_power}]; csr needs `rad_impedance` given to ivs_sim_set_radiation */
+ivs_status ivs_sim_observe(ivs_sim* sim, float* obs);
+ivs_status ivs_sim_set_radiation(ivs_sim* sim, const float* rad_impedance, float f_scale,
+                                 float cutoff);
+/* PhaseSpace::integrateAndNormalize (main.cpp:953-956) on every member */
+ivs_status ivs_sim_renormalize(ivs_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVS_H */

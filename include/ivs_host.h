@@ -1,0 +1,100 @@
+/* ivs_host.h -- host-side (CPU, one-time) helpers of the B200 VFP step library.
+ *
+ * These restate the set-up arithmetic the reference performs in main() and in the map /
+ * impedance constructors, so that a caller can go from ring parameters to the tables the
+ * device path consumes (ivs_sim_desc in ivs.h).  They run on the CPU, need no GPU, and are
+ * deterministic.  Citations are into /root/reference/.
+ */
+#ifndef IVS_HOST_H
+#define IVS_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* The subset of the reference's program options (src/IO/ProgramOptions.cpp:22-305) that
+ * reaches the hot path, with the reference's member types (inc/IO/ProgramOptions.hpp:239-290:
+ * float for meshaxis_t/frequency_t options, double for the others). */
+typedef struct ivs_ring_params {
+    uint32_t grid_size;        /* GridSize            (256)   */
+    uint32_t steps_per_Ts;     /* StepsPerTsync       (1000)  */
+    uint32_t interpolation;    /* InterpolationPoints (4)     */
+    uint32_t derivation;       /* DerivationType      (4)     */
+    uint32_t fp_type;          /* FPType              (3)     */
+    uint32_t fp_track;         /* FPTrack             (3)     */
+    uint32_t linear_rf;        /* LinearRF            (1)     */
+    uint32_t round_padding;    /* RoundPadding        (1)     */
+    uint32_t use_csr;          /* UseCSR              (1)     */
+    uint32_t reserved;
+    float pq_size;             /* PhaseSpaceSize      (12)    */
+    float shift_x, shift_y;    /* PhaseSpaceShiftX/Y  (0)     */
+    float alpha0, alpha1, alpha2; /* AlphaZero/One/Two        */
+    float f_s;                 /* SynchrotronFrequency (0 = derive from alpha0) */
+    float f_rev;               /* RevolutionFrequency (9e6)   */
+    float harmonic;            /* HarmonicNumber      (50)    */
+    float f_cutoff;            /* CutoffFrequency     (23e9)  */
+    double padding;            /* padding             (8)     */
+    double steps_per_Trev;     /* StepsPerTrev        (0)     */
+    double E0;                 /* BeamEnergy          (1.3e9) */
+    double sE;                 /* BeamEnergySpread    (4.7e-4)*/
+    double V_RF;               /* AcceleratingVoltage (1e6)   */
+    double R_bend;             /* BendingRadius       (-1)    */
+    double t_damp;             /* DampingTime         (-1)    */
+    double gap;                /* VacuumGap           (0.03)  */
+    double collimator;         /* CollimatorRadius    (0)     */
+    double wall_conductivity;  /* WallConductivity    (0)     */
+    double wall_susceptibility;/* WallSusceptibility  (0)     */
+    double zoom;               /* InitialDistZoom     (1)     */
+    float bunch_current;       /* BunchCurrent (single bunch) */
+    float reserved_f;
+} ivs_ring_params;
+
+/* Scalars main() derives before building its objects (src/main.cpp:163-355,663-664,682). */
+typedef struct ivs_derived {
+    float qmin, qmax, pmin, pmax;   /* :179-187 */
+    float dq, dp;                   /* Ruler delta (inc/PS/Ruler.hpp:38) */
+    float zerobin_x, zerobin_y;     /* Ruler zerobin (inc/PS/Ruler.hpp:40) */
+    float angle;                    /* :353 */
+    float fmax;                     /* :309 */
+    float e1;                       /* :682 */
+    float slip[3];                  /* :663-664 */
+    float wakescaling;              /* ElectricField::_wakescaling (hpp:99-100, cpp:58) */
+    float bl_f, dE_f;               /* axis scales as stored (float map values) */
+    double dE, R_bend, f_rev, f_RF, V0, V_eff, fs, alpha0, bl, Ib, Qb, steps, t_damp, dt,
+        revolutionpart;
+    uint32_t padded_bins;           /* :311-316 */
+    uint32_t spacing_bins;          /* :304-307 */
+    uint32_t laststep_per_Ts;       /* ceil(steps) */
+    uint32_t reserved;
+} ivs_derived;
+
+/* fills `p` with the reference's defaults (the values in the comments above) */
+void ivs_default_params(ivs_ring_params* p);
+/* src/main.cpp:163-355,663-664,682 */
+int ivs_derive(const ivs_ring_params* p, ivs_derived* d);
+/* RFKickMap::_calcKick (src/SM/RFKickMap.cpp:59-83) at the synchronous phase: n floats */
+int ivs_rf_kick_offsets(const ivs_ring_params* p, const ivs_derived* d, float* offset);
+/* DriftMap::DriftMap (src/SM/DriftMap.cpp:21-30): n floats */
+int ivs_drift_offsets(const ivs_ring_params* p, const ivs_derived* d, float* offset);
+/* makeImpedance (src/Z/ImpedanceFactory.cpp:21-84) without the file contribution:
+ * z = nfreqs complex<float> (interleaved re,im); *nonzero = 0 if "no impedance is used" */
+int ivs_make_impedance(size_t nfreqs, float fmax, double R_bend, double f_rev, double gap,
+                       int use_csr, double s, double xi, double collimator, float* z,
+                       int* nonzero);
+/* the wake impedance (src/main.cpp:717-721) and the radiation impedance (:724-727) */
+int ivs_wake_impedance(const ivs_ring_params* p, const ivs_derived* d, float* z, int* nonzero);
+int ivs_radiation_impedance(const ivs_ring_params* p, const ivs_derived* d, float* z);
+/* PhaseSpace::PhaseSpace with data == nullptr followed by main()'s initial
+ * renormalisation (src/PS/PhaseSpace.cpp:52-65,457-484; src/main.cpp:528-532): n*n floats */
+int ivs_initial_grid(const ivs_derived* d, uint32_t n, double zoom, float* grid);
+/* Airy functions used by the parallel-plates impedance (src/Z/ParallelPlatesCSR.cpp:48-53);
+ * returns 0, or 1 if Bi/Bi' overflow a double (Boost would throw there) */
+int ivs_airy(double x, double* ai, double* aip, double* bi, double* bip);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVS_HOST_H */
