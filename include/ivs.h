@@ -197,6 +197,8 @@ typedef struct ivs_sim_desc {
     float dq;              /* axis 0 delta (Simpson weights are built from it, as the reference) */
     float dp;              /* axis 1 delta */
     float e1;              /* damping decrement (tracking only; the stencil is in fp_weights) */
+    float qmin;            /* axis 0 minimum (moments) */
+    float pmin;            /* axis 1 minimum (moments) */
     float reserved_f;
     const float* rf_offset;     /* host, n floats: RFKickMap::_offset (getForce()) */
     const float* drift_offset;  /* host, n floats: DriftMap::_offset */

@@ -1,0 +1,49 @@
+// ivs_internal.h -- declarations shared between the translation units of libivs.so
+// (not part of the C ABI).
+#pragma once
+#include "ivs_common.cuh"
+
+struct ivs_sim;
+
+// member-batched launchers (ivs_maps.cu, ivs_reduce.cu, ivs_field.cu, ivs_track.cu)
+ivs_status ivs_kick_y_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n, uint32_t members,
+                              const float* offset, uint32_t offset_stride, uint32_t it);
+ivs_status ivs_kick_x_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n, uint32_t members,
+                              const float* offset, uint32_t offset_stride, uint32_t it);
+ivs_status ivs_fokker_planck_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n,
+                                     uint32_t members, const float* w5);
+ivs_status ivs_project_x_batched(ivs_ctx* ctx, const float* grid, uint32_t n, uint32_t members,
+                                 const float* ws, float* proj);
+ivs_status ivs_project_y_batched(ivs_ctx* ctx, const float* grid, uint32_t n, uint32_t members,
+                                 const float* ws, float* proj);
+ivs_status ivs_integrate_batched(ivs_ctx* ctx, const float* proj, uint32_t n, uint32_t members,
+                                 const float* ws, float* integral);
+ivs_status ivs_normalize_batched(ivs_ctx* ctx, float* grid, uint32_t n, uint32_t members,
+                                 float filling_set, const float* integral);
+ivs_status ivs_moments_batched(ivs_ctx* ctx, const float* proj, uint32_t n, uint32_t members,
+                               float amin, float delta, const float* integral, float* out3);
+ivs_status ivs_field_launch(ivs_ctx* ctx, const float* profile, uint32_t n, uint32_t members,
+                            const float* impedance, uint32_t nmax, const float* d_scaling,
+                            float scaling, float* wake, float* formfactor, float* spectrum,
+                            float* power, float dq, float f_scale, float cutoff, int mode);
+// all four maps' applyTo for every tracked particle of every member, one launch per step
+ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
+                                 uint32_t n, const float* wake, const float* rf, const float* drift,
+                                 const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
+                                 float dp, uint64_t seed, uint64_t step);
+
+// the fused step kernel (ivs_fused.cu)
+struct ivs_fused_plan {
+    uint32_t launches_per_step = 1;
+    uint32_t tx = 0;          // output rows per CTA
+    uint32_t halo_lo = 0, halo_hi = 0;  // extra rows the drift reads below / above a tile
+    uint32_t pad_y = 0;       // zero columns kept left and right of every staged row
+    uint32_t threads = 0;
+    size_t smem = 0;
+    void* drift_taps = nullptr;  // device table of ivs_taps per column
+    void* rf_taps = nullptr;     // device table of ivs_taps per row
+    bool ready = false;
+};
+ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan);
+void ivs_fused_plan_destroy(ivs_fused_plan* plan);
+ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s);

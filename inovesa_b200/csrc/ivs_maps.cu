@@ -1,0 +1,283 @@
+// ivs_maps.cu -- the reference's per-map kernels, one launch per map ("unfused" path).
+//
+// These are the 1:1 replacements of the OpenCL kernels K1-K6 of SURVEY.md section 2a; the
+// arithmetic follows the reference's CPU loops (the parity oracle), not its OpenCL variants.
+// They accept any grid size and any displacement (every tap is bounds checked), and are what
+// the fused step kernel (ivs_step.cu) is verified against on the device.
+#include "ivs_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------- KickMap, Axis::y
+// src/SM/KickMap.cpp:243-266.  One CTA per row x: the row's taps are computed once (thread 0)
+// with the arithmetic of updateSM(), the row is staged in shared memory (coalesced, read once
+// from L2/HBM), every thread produces outputs y = tid, tid+blockDim, ...
+template <bool FMA>
+__global__ void __launch_bounds__(kThreads)
+kick_y_kernel(const float* __restrict__ in, float* __restrict__ out, uint32_t n,
+              const float* __restrict__ offset, uint32_t offset_stride, uint32_t it) {
+    extern __shared__ float row[];
+    __shared__ ivs_taps taps;
+    const uint32_t x = blockIdx.x;  // global row = member*n + row
+    if (threadIdx.x == 0) taps = ivs_kick_taps(offset[(x / n) * offset_stride + (x % n)], n, it);
+    const float* src = in + (size_t)x * n;
+    for (uint32_t y = threadIdx.x; y < n; y += blockDim.x) row[y] = src[y];
+    __syncthreads();
+    const int first = taps.first;
+    const float w0 = taps.w[0], w1 = taps.w[1], w2 = taps.w[2], w3 = taps.w[3];
+    float* dst = out + (size_t)x * n;
+    for (uint32_t y = threadIdx.x; y < n; y += blockDim.x) {
+        const int p = (int)y + first;
+        float v = 0.0f;
+        if ((uint32_t)(p) < n) v = madd<FMA>(row[p], w0, v);
+        if ((uint32_t)(p + 1) < n) v = madd<FMA>(row[p + 1], w1, v);
+        if ((uint32_t)(p + 2) < n) v = madd<FMA>(row[p + 2], w2, v);
+        if ((uint32_t)(p + 3) < n) v = madd<FMA>(row[p + 3], w3, v);
+        dst[y] = v;
+    }
+}
+
+// ---------------------------------------------------------------- KickMap, Axis::x
+// src/SM/KickMap.cpp:221-242.  Thread = column y (coalesced along y), CTA = 32 columns x a
+// strip of rows; the per-column taps are computed once per thread and reused down the strip.
+constexpr int kXStrip = 64;
+template <bool FMA>
+__global__ void __launch_bounds__(kThreads)
+kick_x_kernel(const float* __restrict__ in_all, float* __restrict__ out_all, uint32_t n,
+              const float* __restrict__ offset, uint32_t offset_stride, uint32_t it) {
+    const uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= n) return;
+    const float* in = in_all + (size_t)blockIdx.z * n * n;
+    float* out = out_all + (size_t)blockIdx.z * n * n;
+    const ivs_taps t = ivs_kick_taps(offset[blockIdx.z * offset_stride + y], n, it);
+    const uint32_t x0 = blockIdx.y * kXStrip;
+    const uint32_t x1 = min(x0 + kXStrip, n);
+    for (uint32_t x = x0; x < x1; x++) {
+        const int p = (int)x + t.first;
+        float v = 0.0f;
+        if ((uint32_t)(p) < n) v = madd<FMA>(in[(size_t)(p)*n + y], t.w[0], v);
+        if ((uint32_t)(p + 1) < n) v = madd<FMA>(in[(size_t)(p + 1) * n + y], t.w[1], v);
+        if ((uint32_t)(p + 2) < n) v = madd<FMA>(in[(size_t)(p + 2) * n + y], t.w[2], v);
+        if ((uint32_t)(p + 3) < n) v = madd<FMA>(in[(size_t)(p + 3) * n + y], t.w[3], v);
+        out[(size_t)x * n + y] = v;
+    }
+}
+
+// ---------------------------------------------------------------- FokkerPlanckMap
+// src/SM/FokkerPlanckMap.cpp:197-211 with the stencil as 5 dense weights on y-2..y+2 (the
+// reference's 3 or 4 taps in ascending order; the padding weights are exactly 0).
+template <bool FMA>
+__global__ void __launch_bounds__(kThreads)
+fokker_planck_kernel(const float* __restrict__ in, float* __restrict__ out, uint32_t n,
+                     const float* __restrict__ w5) {
+    extern __shared__ float row[];
+    const uint32_t x = blockIdx.x;  // global row = member*n + row
+    const float* src = in + (size_t)x * n;
+    for (uint32_t y = threadIdx.x; y < n; y += blockDim.x) row[y] = src[y];
+    __syncthreads();
+    float* dst = out + (size_t)x * n;
+    for (uint32_t y = threadIdx.x; y < n; y += blockDim.x) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int p = (int)y + k - 2;
+            const float w = w5[y * 5 + k];
+            if (w != 0.0f && (uint32_t)p < n) v = madd<FMA>(row[p], w, v);
+        }
+        dst[y] = v;
+    }
+}
+
+// ---------------------------------------------------------------- generic gather
+// src/SM/SourceMap.cpp:98-107 (kernel applySM1D :121-139)
+struct hi_t {
+    uint32_t index;
+    float weight;
+};
+template <bool FMA>
+__global__ void __launch_bounds__(kThreads)
+source_map_kernel(const float* __restrict__ in, float* __restrict__ out, uint32_t ncells,
+                  const hi_t* __restrict__ sm, uint32_t ip) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncells) return;
+    float v = 0.0f;
+    for (uint32_t j = 0; j < ip; j++) {
+        const hi_t h = sm[(size_t)i * ip + j];
+        v = madd<FMA>(in[h.index], h.weight, v);
+    }
+    out[i] = v;
+}
+
+// ---------------------------------------------------------------- RotationMap
+// src/SM/RotationMap.cpp:190-260 (genHInfo) + :142-174 (apply): source coordinates and the
+// it x it Lagrange weights are recomputed per cell with the reference's fp32 expression order;
+// the table variant of the reference produces the same numbers, so there is no table here
+// (the reference's table costs 128 B/cell of traffic).
+struct rot_params {
+    float cos_dt, sin_dt;
+    float min0, min1, d0, d1, zb0, zb1;
+    uint32_t n, it;
+    int clamp;
+};
+
+template <bool FMA>
+__global__ void __launch_bounds__(kThreads)
+rotate_kernel(const float* __restrict__ in, float* __restrict__ out, rot_params p) {
+    const uint32_t y0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t x0 = blockIdx.y;
+    const uint32_t n = p.n, it = p.it;
+    if (y0 >= n) return;
+    // Ruler::at(i) = min + i*delta (inc/PS/Ruler.hpp:47-49)
+    const float ax = IVS_ADD(p.min0, IVS_MUL((float)x0, p.d0));
+    const float ay = IVS_ADD(p.min1, IVS_MUL((float)y0, p.d1));
+    float x1r = IVS_ADD(IVS_DIV(IVS_SUB(IVS_MUL(p.cos_dt, ax), IVS_MUL(p.sin_dt, ay)), p.d0), p.zb0);
+    float y1r = IVS_ADD(IVS_DIV(IVS_ADD(IVS_MUL(p.sin_dt, ax), IVS_MUL(p.cos_dt, ay)), p.d1), p.zb1);
+    const float xi = truncf(x1r), yi = truncf(y1r);
+    const float xf = IVS_SUB(x1r, xi), yf = IVS_SUB(y1r, yi);
+    const uint32_t x1 = (uint32_t)(long long)xi, y1 = (uint32_t)(long long)yi;
+    float v = 0.0f;
+    if (x1 < n && y1 < n) {
+        float icq[4], icp[4];
+        ivs_calc_coefficients(xf, it, icq);
+        ivs_calc_coefficients(yf, it, icp);
+        const uint32_t lo = (it - 1) / 2;
+        float ceil = 1.17549435e-38f /* FLT_MIN */, flor = 3.402823466e+38f /* FLT_MAX */;
+        for (uint32_t i1 = 0; i1 < it; i1++) {
+            const uint32_t i0 = x1 + i1 - lo;
+            for (uint32_t j1 = 0; j1 < it; j1++) {
+                const uint32_t j0 = y1 + j1 - lo;
+                const bool ok = (i0 < n && j0 < n);
+                // out-of-grid taps are stored as {index 0, weight 0} (:247-249)
+                const float src = in[ok ? (size_t)i0 * n + j0 : 0];
+                const float w = ok ? IVS_MUL(icq[i1], icp[j1]) : 0.0f;
+                v = madd<FMA>(src, w, v);
+                if (p.clamp && i1 >= 1 && i1 <= 2 && j1 >= 1 && j1 <= 2) {
+                    ceil = (ceil < src) ? src : ceil;  // std::max(ceil, src)
+                    flor = (src < flor) ? src : flor;  // std::min(flor, src)
+                }
+            }
+        }
+        if (p.clamp) {
+            const float m = (v < ceil) ? v : ceil;  // std::min(ceil, v)
+            v = (m < flor) ? flor : m;              // std::max(m, flor)
+        }
+    } else if (p.clamp) {
+        // all 16 taps are {0,0}: value 0 clamped to [in[0], in[0]] (:161-171)
+        const float src = in[0];
+        float ceil = 1.17549435e-38f, flor = 3.402823466e+38f;
+        ceil = (ceil < src) ? src : ceil;
+        flor = (src < flor) ? src : flor;
+        const float m = (0.0f < ceil) ? 0.0f : ceil;
+        v = (m < flor) ? flor : m;
+    }
+    out[(size_t)x0 * n + y0] = v;
+}
+
+template <typename K, typename... Args>
+ivs_status launch(ivs_ctx* ctx, K kernel_fma, K kernel_strict, dim3 grid, dim3 block, size_t smem,
+                  Args... args) {
+    if (ctx->arith == IVS_ARITH_FMA) kernel_fma<<<grid, block, smem, ctx->stream>>>(args...);
+    else kernel_strict<<<grid, block, smem, ctx->stream>>>(args...);
+    IVS_LAUNCHED(ctx);
+    return IVS_OK;
+}
+
+}  // namespace
+
+// member-batched launchers shared with the simulation object (ivs_step.cu)
+ivs_status ivs_kick_y_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n,
+                              uint32_t members, const float* offset, uint32_t offset_stride,
+                              uint32_t it) {
+    const size_t smem = n * sizeof(float);
+    if (smem > 48 * 1024) {
+        IVS_CUDA(ctx, cudaFuncSetAttribute(kick_y_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(kick_y_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    return launch(ctx, kick_y_kernel<true>, kick_y_kernel<false>, dim3(n * members), dim3(kThreads),
+                  smem, in, out, n, offset, offset_stride, it);
+}
+ivs_status ivs_kick_x_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n,
+                              uint32_t members, const float* offset, uint32_t offset_stride,
+                              uint32_t it) {
+    const uint32_t bx = 128;
+    return launch(ctx, kick_x_kernel<true>, kick_x_kernel<false>,
+                  dim3(ivs_div_up(n, bx), ivs_div_up(n, kXStrip), members), dim3(bx), 0, in, out, n,
+                  offset, offset_stride, it);
+}
+ivs_status ivs_fokker_planck_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n,
+                                     uint32_t members, const float* w5) {
+    const size_t smem = n * sizeof(float);
+    if (smem > 48 * 1024) {
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fokker_planck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fokker_planck_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    return launch(ctx, fokker_planck_kernel<true>, fokker_planck_kernel<false>, dim3(n * members),
+                  dim3(kThreads), smem, in, out, n, w5);
+}
+
+extern "C" {
+
+ivs_status ivs_kick_y(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, const void* d_offset,
+                      uint32_t it) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d_in && d_out && d_offset && n >= 2, "ivs_kick_y: null pointer or n < 2");
+    IVS_REQUIRE(ctx, it >= 1 && it <= 4, "ivs_kick_y: interpolation type must be 1..4");
+    IVS_REQUIRE(ctx, d_in != d_out, "ivs_kick_y: in-place application is not supported");
+    return ivs_kick_y_batched(ctx, (const float*)d_in, (float*)d_out, n, 1, (const float*)d_offset, 0, it);
+}
+
+ivs_status ivs_kick_x(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, const void* d_offset,
+                      uint32_t it) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d_in && d_out && d_offset && n >= 2, "ivs_kick_x: null pointer or n < 2");
+    IVS_REQUIRE(ctx, it >= 1 && it <= 4, "ivs_kick_x: interpolation type must be 1..4");
+    IVS_REQUIRE(ctx, d_in != d_out, "ivs_kick_x: in-place application is not supported");
+    return ivs_kick_x_batched(ctx, (const float*)d_in, (float*)d_out, n, 1, (const float*)d_offset, 0, it);
+}
+
+ivs_status ivs_fokker_planck(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n,
+                             const void* d_weights) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d_in && d_out && d_weights && n >= 4, "ivs_fokker_planck: null pointer or n < 4");
+    IVS_REQUIRE(ctx, d_in != d_out, "ivs_fokker_planck: in-place application is not supported");
+    return ivs_fokker_planck_batched(ctx, (const float*)d_in, (float*)d_out, n, 1, (const float*)d_weights);
+}
+
+ivs_status ivs_apply_source_map(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t ncells,
+                                const void* d_hinfo, uint32_t ip) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d_in && d_out && d_hinfo && ncells > 0, "ivs_apply_source_map: null pointer");
+    return launch(ctx, source_map_kernel<true>, source_map_kernel<false>,
+                  dim3(ivs_div_up(ncells, kThreads)), dim3(kThreads), 0, (const float*)d_in,
+                  (float*)d_out, ncells, (const hi_t*)d_hinfo, ip);
+}
+
+ivs_status ivs_identity(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n) {
+    return ivs_copy(ctx, d_out, d_in, (size_t)n * n * sizeof(float));
+}
+
+ivs_status ivs_rotate(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, float angle,
+                      float qmin, float qmax, float pmin, float pmax, uint32_t it, int clamp) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d_in && d_out && n >= 2, "ivs_rotate: null pointer or n < 2");
+    IVS_REQUIRE(ctx, it >= 1 && it <= 4, "ivs_rotate: interpolation type must be 1..4");
+    IVS_REQUIRE(ctx, qmin < qmax && pmin < pmax, "Tried to set up Ruler with min >= max.");
+    // src/SM/RotationMap.cpp:83-87
+    IVS_REQUIRE(ctx, !(clamp && it != 4),
+                "Clamping only supported with cubic interpolation and rotmapsize > 0.");
+    rot_params p;
+    p.cos_dt = cosf(-angle);  // src/SM/RotationMap.cpp:24-25, std::cos(float)
+    p.sin_dt = sinf(-angle);
+    p.n = n; p.it = it; p.clamp = clamp;
+    p.min0 = qmin; p.min1 = pmin;
+    p.d0 = (qmax - qmin) / (float)(n - 1);  // inc/PS/Ruler.hpp:38
+    p.d1 = (pmax - pmin) / (float)(n - 1);
+    p.zb0 = ((qmin + qmax) / (qmin - qmax) + 1) * (float)(n - 1) / 2;  // inc/PS/Ruler.hpp:40
+    p.zb1 = ((pmin + pmax) / (pmin - pmax) + 1) * (float)(n - 1) / 2;
+    return launch(ctx, rotate_kernel<true>, rotate_kernel<false>, dim3(ivs_div_up(n, 128), n),
+                  dim3(128), 0, (const float*)d_in, (float*)d_out, p);
+}
+
+}  // extern "C"

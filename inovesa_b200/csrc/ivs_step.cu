@@ -1,0 +1,431 @@
+// ivs_step.cu -- the simulation object: device-resident state of `members` independent
+// single-bunch simulations and the loop body of main() (src/main.cpp:948-1053) on the device.
+//
+//   wake potential -> wake kick (y) -> RF kick (y) -> drift (x) -> Fokker-Planck (y) -> X projection
+//
+// Two executions of the same step:
+//   * unfused (IVS_SIM_UNFUSED): the reference's kernel sequence, one launch per map (ivs_maps.cu),
+//     three grids t1/t2/t3 wired like src/main.cpp:593-763;
+//   * fused (default): ONE kernel per step (ivs_fused.cuh) that reads the grid once and writes it
+//     once -- 8 B per cell-update, the algorithmic minimum of SURVEY.md section 8(d).
+// Either way the step sequence is captured in a CUDA graph and replayed.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+#include "ivs_common.cuh"
+#include "ivs_internal.h"
+
+struct ivs_sim {
+    ivs_ctx* ctx = nullptr;
+    ivs_sim_desc desc{};
+    uint32_t n = 0, members = 0, it = 4, nmax = 0, np = 0;
+    bool has_wake = false, has_fp = false, has_rad = false;
+    float* grid[3] = {nullptr, nullptr, nullptr};  // t1, t2, t3 (unfused) / ping, pong (fused)
+    int cur = 0;                                   // index of the buffer holding grid_t1
+    float* profile[2] = {nullptr, nullptr};        // X projection (double buffered for the fused path)
+    int pcur = 0;
+    float* wake = nullptr;        // [members][n] offsets applied by the last wake kick
+    float* rf = nullptr;          // [n]
+    float* drift = nullptr;       // [n]
+    float* fpw = nullptr;         // [n][5]
+    float* ws = nullptr;          // [n]
+    float* impedance = nullptr;   // [nmax] complex
+    float* rad_impedance = nullptr;
+    float* wakescaling = nullptr; // [members]
+    float* wakefunction = nullptr;// [2n-1] unit-scaled wake function (fused path)
+    float* particles = nullptr;   // [members][np][2]
+    float* projy = nullptr;       // [members][n]
+    float* obs = nullptr;         // [members][8] + scratch
+    float* integral = nullptr;    // [members]
+    float* moments = nullptr;     // [members][2][3]
+    float* power = nullptr;       // [members]
+    int* status = nullptr;        // device error flag of the fused kernel
+    float f_scale = 0, cutoff = 0;
+    uint64_t steps_done = 0;
+    ivs_fused_plan plan{};
+    cudaGraphExec_t graph1 = nullptr;   // one step
+    cudaGraphExec_t graphK = nullptr;   // kGraphSteps steps
+    int graph_cur = -1;                 // buffer parity the graphs were captured for
+    static constexpr uint32_t kGraphSteps = 16;
+};
+
+namespace {
+
+template <typename T>
+ivs_status dalloc(ivs_ctx* ctx, T** p, size_t count) {
+    IVS_CUDA(ctx, cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return IVS_OK;
+}
+#define IVS_TRY(expr)                       \
+    do {                                    \
+        ivs_status st__ = (expr);           \
+        if (st__ != IVS_OK) return st__;    \
+    } while (0)
+
+// one step as the reference's kernel sequence (src/main.cpp:948-1053), grids wired
+// wm: t1->t2, rfm: t2->t1, drm: t1->t3, fpm: t3->t1 (:593-763)
+ivs_status enqueue_unfused_step(ivs_sim* s) {
+    ivs_ctx* ctx = s->ctx;
+    const uint32_t n = s->n, m = s->members;
+    float *t1 = s->grid[0], *t2 = s->grid[1], *t3 = s->grid[2];
+    float* prof = s->profile[0];
+    const size_t bytes = (size_t)m * n * n * sizeof(float);
+    if (s->has_wake) {
+        // wkm->update(): ElectricField::wakePotential -> offsets (src/SM/WakePotentialMap.cpp:34-50)
+        IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->impedance, s->nmax, s->wakescaling, 0, s->wake,
+                                 nullptr, nullptr, nullptr, 0, 0, 0, 0));
+        IVS_TRY(ivs_kick_y_batched(ctx, t1, t2, n, m, s->wake, n, s->it));
+    } else {
+        IVS_CUDA(ctx, cudaMemcpyAsync(t2, t1, bytes, cudaMemcpyDeviceToDevice, ctx->stream));  // Identity
+    }
+    IVS_TRY(ivs_kick_y_batched(ctx, t2, t1, n, m, s->rf, 0, s->it));
+    IVS_TRY(ivs_kick_x_batched(ctx, t1, t3, n, m, s->drift, 0, s->it));
+    if (s->np) {
+        IVS_TRY(ivs_track_step_launch(ctx, s->particles, s->np, m, n, s->has_wake ? s->wake : nullptr,
+                                      s->rf, s->drift, s->has_fp ? s->fpw : nullptr, t3,
+                                      s->desc.fptrack, s->desc.e1, s->desc.dp, s->desc.seed,
+                                      s->steps_done));
+    }
+    if (s->has_fp) {
+        IVS_TRY(ivs_fokker_planck_batched(ctx, t3, t1, n, m, s->fpw));
+    } else {
+        IVS_CUDA(ctx, cudaMemcpyAsync(t1, t3, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    IVS_TRY(ivs_project_x_batched(ctx, t1, n, m, s->ws, prof));
+    return IVS_OK;
+}
+
+ivs_status enqueue_step(ivs_sim* s) {
+    if (s->desc.flags & IVS_SIM_UNFUSED) return enqueue_unfused_step(s);
+    return ivs_fused_enqueue_step(s->ctx, &s->plan, s);
+}
+
+void drop_graphs(ivs_sim* s) {
+    if (s->graph1) cudaGraphExecDestroy(s->graph1);
+    if (s->graphK) cudaGraphExecDestroy(s->graphK);
+    s->graph1 = s->graphK = nullptr;
+    s->graph_cur = -1;
+}
+
+ivs_status capture(ivs_sim* s, uint32_t steps, cudaGraphExec_t* out) {
+    ivs_ctx* ctx = s->ctx;
+    cudaGraph_t g = nullptr;
+    const int cur0 = s->cur, pcur0 = s->pcur;
+    const uint64_t launches0 = ctx->launches, done0 = s->steps_done;
+    IVS_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ivs_status st = IVS_OK;
+    for (uint32_t i = 0; i < steps && st == IVS_OK; i++) {
+        st = enqueue_step(s);
+        s->steps_done++;
+    }
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    // capture only records; restore the bookkeeping it advanced
+    s->cur = cur0; s->pcur = pcur0; ctx->launches = launches0; s->steps_done = done0;
+    if (st != IVS_OK) { if (g) cudaGraphDestroy(g); return st; }
+    if (e != cudaSuccess) return ivs_check_cuda(ctx, e, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return ivs_check_cuda(ctx, e, "cudaGraphInstantiate");
+    return IVS_OK;
+}
+
+// how many kernels one step launches (for ivs_ctx_launch_count bookkeeping under graphs)
+uint32_t launches_per_step(const ivs_sim* s) {
+    if (!(s->desc.flags & IVS_SIM_UNFUSED)) return s->plan.launches_per_step + (s->np ? 1 : 0);
+    uint32_t k = 3;  // rf kick, drift, projection
+    if (s->has_wake) k += 2;
+    if (s->has_fp) k += 1;
+    if (s->np) k += 1;
+    return k;
+}
+
+// unit wake function w[m], m = -(n-1)..(n-1): c2r of the Hermitian-extended impedance with the
+// reference's conventions (imaginary part of bin 0 ignored, bins >= nmax/2 zero), in double.
+std::vector<float> wake_function_host(const float* z, uint32_t nmax, uint32_t n) {
+    const double two_pi = 6.283185307179586476925286766559005768;
+    std::vector<std::complex<double>> a(nmax, 0.0);
+    a[0] = std::complex<double>(z[0], 0.0);
+    for (uint32_t k = 1; k < nmax / 2; k++) {
+        a[k] = std::complex<double>(z[2 * k], z[2 * k + 1]);
+        a[nmax - k] = std::conj(a[k]);
+    }
+    // radix-2 FFT, sign +
+    for (uint32_t i = 1, j = 0; i < nmax; i++) {
+        uint32_t bit = nmax >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (uint32_t len = 2; len <= nmax; len <<= 1) {
+        for (uint32_t k = 0; k < len / 2; k++) {
+            const double ph = two_pi * (double)k / (double)len;
+            const std::complex<double> w(std::cos(ph), std::sin(ph));
+            for (uint32_t i = k; i < nmax; i += len) {
+                const std::complex<double> u = a[i], v = a[i + len / 2] * w;
+                a[i] = u + v;
+                a[i + len / 2] = u - v;
+            }
+        }
+    }
+    std::vector<float> w(2 * n - 1);
+    for (int m = -(int)(n - 1); m <= (int)(n - 1); m++) {
+        w[m + (int)(n - 1)] = (float)a[(uint32_t)((m + (int)nmax) % (int)nmax)].real();
+    }
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+ivs_status ivs_wake_function(ivs_ctx* ctx, const void* d_impedance, uint32_t nmax,
+                             float wakescaling, uint32_t n, void* d_wakefunction) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d_impedance && d_wakefunction, "ivs_wake_function: null pointer");
+    IVS_REQUIRE(ctx, nmax >= 2 * n && (nmax & (nmax - 1)) == 0,
+                "ivs_wake_function: nmax must be a power of two >= 2n");
+    std::vector<float> z(2 * (size_t)nmax);
+    IVS_TRY(ivs_download(ctx, z.data(), d_impedance, z.size() * sizeof(float)));
+    std::vector<float> w = wake_function_host(z.data(), nmax, n);
+    for (float& v : w) v = wakescaling * v;
+    IVS_TRY(ivs_upload(ctx, d_wakefunction, w.data(), w.size() * sizeof(float)));
+    return ivs_sync(ctx);
+}
+
+ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d && out, "ivs_sim_create: null argument");
+    *out = nullptr;
+    IVS_REQUIRE(ctx, d->n >= 8, "ivs_sim_create: grid size must be >= 8");
+    IVS_REQUIRE(ctx, d->members >= 1, "ivs_sim_create: members must be >= 1");
+    IVS_REQUIRE(ctx, d->it >= 1 && d->it <= 4, "ivs_sim_create: interpolation type must be 1..4");
+    IVS_REQUIRE(ctx, d->rf_offset && d->drift_offset && d->grid, "ivs_sim_create: rf_offset, drift_offset and grid are required");
+    IVS_REQUIRE(ctx, d->fptrack <= 3, "ivs_sim_create: FPTracking must be 0..3");
+    const bool has_wake = d->impedance != nullptr && d->nmax != 0;
+    if (has_wake) {
+        IVS_REQUIRE(ctx, (d->nmax & (d->nmax - 1)) == 0 && d->nmax >= 2 * d->n && d->nmax <= 16384,
+                    "ivs_sim_create: nmax must be a power of two with 2n <= nmax <= 16384");
+        IVS_REQUIRE(ctx, d->wakescaling != nullptr, "ivs_sim_create: wakescaling is required with an impedance");
+    }
+    IVS_REQUIRE(ctx, d->n_particles == 0 || d->particles, "ivs_sim_create: particles missing");
+    IVS_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    ivs_sim* s = new ivs_sim;
+    s->ctx = ctx; s->desc = *d;
+    s->n = d->n; s->members = d->members; s->it = d->it; s->nmax = has_wake ? d->nmax : 0;
+    s->np = d->n_particles; s->has_wake = has_wake; s->has_fp = d->fp_weights != nullptr;
+    const uint32_t n = s->n, m = s->members;
+    const size_t cells = (size_t)m * n * n;
+    const bool unfused = (d->flags & IVS_SIM_UNFUSED) != 0;
+    ivs_status st = IVS_OK;
+    auto fail = [&](ivs_status code) { ivs_sim_destroy(s); return code; };
+#define S_TRY(expr) do { st = (expr); if (st != IVS_OK) return fail(st); } while (0)
+    for (int i = 0; i < (unfused ? 3 : 2); i++) S_TRY(dalloc(ctx, &s->grid[i], cells));
+    S_TRY(dalloc(ctx, &s->profile[0], (size_t)m * n));
+    S_TRY(dalloc(ctx, &s->profile[1], (size_t)m * n));
+    S_TRY(dalloc(ctx, &s->wake, (size_t)m * n));
+    S_TRY(dalloc(ctx, &s->rf, n));
+    S_TRY(dalloc(ctx, &s->drift, n));
+    S_TRY(dalloc(ctx, &s->fpw, (size_t)n * 5));
+    S_TRY(dalloc(ctx, &s->ws, n));
+    S_TRY(dalloc(ctx, &s->projy, (size_t)m * n));
+    S_TRY(dalloc(ctx, &s->obs, (size_t)m * 8));
+    S_TRY(dalloc(ctx, &s->integral, m));
+    S_TRY(dalloc(ctx, &s->moments, (size_t)m * 6));
+    S_TRY(dalloc(ctx, &s->power, m));
+    S_TRY(dalloc(ctx, &s->status, 4));
+    S_TRY(ivs_memset_zero(ctx, s->status, 4 * sizeof(int)));
+    S_TRY(ivs_memset_zero(ctx, s->wake, (size_t)m * n * sizeof(float)));
+    S_TRY(ivs_memset_zero(ctx, s->power, m * sizeof(float)));
+    S_TRY(ivs_upload(ctx, s->grid[0], d->grid, cells * sizeof(float)));
+    S_TRY(ivs_upload(ctx, s->rf, d->rf_offset, n * sizeof(float)));
+    S_TRY(ivs_upload(ctx, s->drift, d->drift_offset, n * sizeof(float)));
+    std::vector<float> ws(n), fpw((size_t)n * 5, 0.0f);
+    ivs_simpson_weights(n, d->dq, ws.data());
+    S_TRY(ivs_upload(ctx, s->ws, ws.data(), n * sizeof(float)));
+    if (s->has_fp) {
+        S_TRY(ivs_upload(ctx, s->fpw, d->fp_weights, (size_t)n * 5 * sizeof(float)));
+    } else {
+        for (uint32_t y = 0; y < n; y++) fpw[y * 5 + 2] = 1.0f;  // Identity
+        S_TRY(ivs_upload(ctx, s->fpw, fpw.data(), (size_t)n * 5 * sizeof(float)));
+    }
+    S_TRY(ivs_sync(ctx));  // host vectors above go out of scope
+    std::vector<float> wf;
+    if (has_wake) {
+        S_TRY(dalloc(ctx, &s->impedance, (size_t)2 * s->nmax));
+        S_TRY(dalloc(ctx, &s->wakescaling, m));
+        S_TRY(dalloc(ctx, &s->wakefunction, (size_t)2 * n));
+        S_TRY(ivs_upload(ctx, s->impedance, d->impedance, (size_t)2 * s->nmax * sizeof(float)));
+        S_TRY(ivs_upload(ctx, s->wakescaling, d->wakescaling, m * sizeof(float)));
+        wf = wake_function_host(d->impedance, s->nmax, n);
+        wf.push_back(0.0f);
+        S_TRY(ivs_upload(ctx, s->wakefunction, wf.data(), (size_t)2 * n * sizeof(float)));
+    }
+    if (s->np) {
+        S_TRY(dalloc(ctx, &s->particles, (size_t)m * s->np * 2));
+        S_TRY(ivs_upload(ctx, s->particles, d->particles, (size_t)m * s->np * 2 * sizeof(float)));
+    }
+    // grid_t1->updateXProjection() before the loop (src/main.cpp:893-894)
+    S_TRY(ivs_project_x_batched(ctx, s->grid[0], n, m, s->ws, s->profile[0]));
+    if (!unfused) S_TRY(ivs_fused_plan_create(ctx, s, &s->plan));
+    S_TRY(ivs_sync(ctx));
+#undef S_TRY
+    // the descriptor's host pointers are not retained
+    s->desc.rf_offset = s->desc.drift_offset = s->desc.fp_weights = s->desc.impedance = nullptr;
+    s->desc.wakescaling = s->desc.grid = s->desc.particles = nullptr;
+    *out = s;
+    return IVS_OK;
+}
+
+ivs_status ivs_sim_destroy(ivs_sim* s) {
+    if (!s) return IVS_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    drop_graphs(s);
+    ivs_fused_plan_destroy(&s->plan);
+    float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
+                     s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
+                     s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power};
+    for (float* b : bufs) if (b) cudaFree(b);
+    if (s->status) cudaFree(s->status);
+    delete s;
+    return IVS_OK;
+}
+
+ivs_status ivs_sim_step(ivs_sim* s, uint32_t nsteps) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool use_graph = !(s->desc.flags & IVS_SIM_NO_GRAPH);
+    const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
+    // tracking with the stochastic Fokker-Planck mode keys its generator on the step counter,
+    // which a replayed graph would freeze: launch directly in that case
+    const bool graph_ok = use_graph && !(s->np && s->desc.fptrack == 3);
+    // fused steps ping-pong two buffers: a graph is valid for an even number of steps only,
+    // or for the parity it was captured at
+    const uint32_t lps = launches_per_step(s);
+    uint32_t left = nsteps;
+    if (graph_ok) {
+        const uint32_t K = ivs_sim::kGraphSteps;  // even
+        if (s->graph_cur != s->cur) drop_graphs(s);
+        while (left >= K) {
+            if (!s->graphK) { IVS_TRY(capture(s, K, &s->graphK)); s->graph_cur = s->cur; }
+            IVS_CUDA(ctx, cudaGraphLaunch(s->graphK, ctx->stream));
+            ctx->launches += (uint64_t)lps * K;
+            s->steps_done += K;
+            left -= K;
+        }
+        if (unfused) {
+            while (left > 0) {
+                if (!s->graph1) { IVS_TRY(capture(s, 1, &s->graph1)); s->graph_cur = s->cur; }
+                IVS_CUDA(ctx, cudaGraphLaunch(s->graph1, ctx->stream));
+                ctx->launches += lps;
+                s->steps_done++;
+                left--;
+            }
+        }
+    }
+    while (left > 0) {
+        IVS_TRY(enqueue_step(s));
+        s->steps_done++;
+        left--;
+    }
+    return IVS_OK;
+}
+
+uint64_t ivs_sim_steps_done(const ivs_sim* s) { return s ? s->steps_done : 0; }
+
+ivs_status ivs_sim_state(ivs_sim* s, void** d_grid, void** d_profile, void** d_wake,
+                         void** d_particles) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    if (d_grid) *d_grid = s->grid[s->cur];
+    if (d_profile) *d_profile = s->profile[s->pcur];
+    if (d_wake) *d_wake = s->wake;
+    if (d_particles) *d_particles = s->particles;
+    return IVS_OK;
+}
+
+ivs_status ivs_sim_download(ivs_sim* s, float* grid, float* profile, float* wake, float* particles) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    const size_t n = s->n, m = s->members;
+    if (grid) IVS_CUDA(ctx, cudaMemcpyAsync(grid, s->grid[s->cur], m * n * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (profile) IVS_CUDA(ctx, cudaMemcpyAsync(profile, s->profile[s->pcur], m * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (wake) IVS_CUDA(ctx, cudaMemcpyAsync(wake, s->wake, m * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (particles && s->np) IVS_CUDA(ctx, cudaMemcpyAsync(particles, s->particles, m * s->np * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    IVS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int status[4] = {0, 0, 0, 0};
+    IVS_CUDA(ctx, cudaMemcpy(status, s->status, sizeof(status), cudaMemcpyDeviceToHost));
+    if (status[0] != 0)
+        return ivs_fail(ctx, IVS_ERR_HALO,
+                        "a kick displacement exceeded the halo staged by the fused step kernel; "
+                        "re-create the simulation with IVS_SIM_UNFUSED");
+    return IVS_OK;
+}
+
+ivs_status ivs_sim_upload_grid(ivs_sim* s, const float* grid) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_REQUIRE(ctx, grid != nullptr, "ivs_sim_upload_grid: null pointer");
+    const size_t n = s->n, m = s->members;
+    IVS_CUDA(ctx, cudaMemcpyAsync(s->grid[s->cur], grid, m * n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return ivs_project_x_batched(ctx, s->grid[s->cur], s->n, s->members, s->ws, s->profile[s->pcur]);
+}
+
+ivs_status ivs_sim_set_radiation(ivs_sim* s, const float* rad_impedance, float f_scale, float cutoff) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_REQUIRE(ctx, rad_impedance != nullptr, "ivs_sim_set_radiation: null pointer");
+    uint32_t nmax = s->nmax ? s->nmax : s->desc.nmax;
+    IVS_REQUIRE(ctx, nmax != 0 && (nmax & (nmax - 1)) == 0 && nmax <= 16384 && nmax >= s->n,
+                "ivs_sim_set_radiation: the simulation needs a power-of-two nmax");
+    if (!s->rad_impedance) IVS_TRY(dalloc(ctx, &s->rad_impedance, (size_t)2 * nmax));
+    IVS_TRY(ivs_upload(ctx, s->rad_impedance, rad_impedance, (size_t)2 * nmax * sizeof(float)));
+    IVS_TRY(ivs_sync(ctx));
+    s->has_rad = true; s->f_scale = f_scale; s->cutoff = cutoff;
+    if (!s->nmax) s->nmax = nmax;
+    return IVS_OK;
+}
+
+// out-step block of src/main.cpp:961-1033: integrate, variance(0), updateYProjection,
+// variance(1), updateCSR -- all on the device, 8 floats per member come back
+ivs_status ivs_sim_observe(ivs_sim* s, float* obs) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_REQUIRE(ctx, obs != nullptr, "ivs_sim_observe: null pointer");
+    const uint32_t n = s->n, m = s->members;
+    const float* g = s->grid[s->cur];
+    const float* prof = s->profile[s->pcur];
+    IVS_TRY(ivs_integrate_batched(ctx, prof, n, m, s->ws, s->integral));
+    IVS_TRY(ivs_moments_batched(ctx, prof, n, m, s->desc.qmin, s->desc.dq, s->integral, s->moments));
+    IVS_TRY(ivs_project_y_batched(ctx, g, n, m, s->ws, s->projy));
+    IVS_TRY(ivs_moments_batched(ctx, s->projy, n, m, s->desc.pmin, s->desc.dp, s->integral, s->moments + (size_t)3 * m));
+    if (s->has_rad) {
+        IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->rad_impedance, s->nmax, nullptr, 0, nullptr, nullptr,
+                                 nullptr, s->power, s->desc.dq, s->f_scale, s->cutoff, 1));
+    }
+    std::vector<float> integral(m), mom((size_t)6 * m), power(m, 0.0f);
+    IVS_TRY(ivs_download(ctx, integral.data(), s->integral, m * sizeof(float)));
+    IVS_TRY(ivs_download(ctx, mom.data(), s->moments, (size_t)6 * m * sizeof(float)));
+    IVS_TRY(ivs_download(ctx, power.data(), s->power, m * sizeof(float)));
+    for (uint32_t i = 0; i < m; i++) {
+        obs[i * 8 + 0] = integral[i];
+        for (int k = 0; k < 3; k++) {
+            obs[i * 8 + 1 + k] = mom[(size_t)i * 3 + k];
+            obs[i * 8 + 4 + k] = mom[(size_t)3 * m + (size_t)i * 3 + k];
+        }
+        obs[i * 8 + 7] = power[i];
+    }
+    return IVS_OK;
+}
+
+ivs_status ivs_sim_renormalize(ivs_sim* s) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_TRY(ivs_integrate_batched(ctx, s->profile[s->pcur], s->n, s->members, s->ws, s->integral));
+    return ivs_normalize_batched(ctx, s->grid[s->cur], s->n, s->members, 1.0f, s->integral);
+}
+
+}  // extern "C"

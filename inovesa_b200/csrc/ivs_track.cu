@@ -1,0 +1,236 @@
+// ivs_track.cu -- passive particle tracking: SourceMap::applyToAll (src/SM/SourceMap.cpp:111-117)
+// with the applyTo() of each map, one thread per particle.  Positions are PhaseSpace::Position
+// {x, y} in grid units.  std::min / std::max are spelled out because their NaN behaviour
+// (return the first argument) is part of the reference's results.
+#include "ivs_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ uint32_t f2u(float v) {
+    return (v == v && fabsf(v) < 9.0e18f) ? (uint32_t)(long long)v : 0u;
+}
+
+// KickMap::applyTo (src/SM/KickMap.cpp:280-303): the kick is interpolated linearly in the
+// perpendicular coordinate and SUBTRACTED (forward map), then clamped to [1, n-1].
+__global__ void track_kick_kernel(float2* __restrict__ particles, uint32_t np,
+                                  const float* __restrict__ offset, uint32_t n, int axis) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    float2 p = particles[i];
+    const float perp = (axis == 0) ? p.y : p.x;
+    float par = (axis == 0) ? p.x : p.y;
+    const float ip = truncf(perp);
+    const float fr = IVS_SUB(perp, ip);
+    const uint32_t k = f2u(ip);
+    if (k + 1 < n) {
+        const float s = IVS_ADD(IVS_MUL(IVS_SUB(1.0f, fr), offset[k]), IVS_MUL(fr, offset[k + 1]));
+        par = IVS_SUB(par, s);
+    }
+    par = std_max(1.0f, std_min(par, (float)(n - 1)));
+    if (axis == 0) p.x = par; else p.y = par;
+    particles[i] = p;
+}
+
+// counter-based normal deviates for FPTracking::stochastic: splitmix64 of (seed, step, particle)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float normal01(uint64_t seed, uint64_t step, uint32_t i) {
+    const uint64_t h = mix64(mix64(seed ^ mix64(step)) + i);
+    const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
+    const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// FokkerPlanckMap::applyTo (src/SM/FokkerPlanckMap.cpp:214-268); w5 = stencil weights on
+// y-2..y+2 in the reference's tap order (ascending index)
+__global__ void track_fp_kernel(float2* __restrict__ particles, uint32_t np,
+                                const float* __restrict__ grid, uint32_t n,
+                                const float* __restrict__ w5, uint32_t fptrack, float e1, float dp,
+                                uint64_t seed, uint64_t step) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    float2 p = particles[i];
+    if (fptrack == 1) {
+        uint32_t yi = f2u(floorf(p.y));
+        if (yi > n - 1) yi = n - 1;  // (the reference would read past its table for yi == n)
+        float offset = 0.0f;
+        for (int k = 0; k < 5; k++) {
+            const float w = w5[yi * 5 + k];
+            if (w != 0.0f) offset = IVS_ADD(IVS_MUL((float)(2 - k), w), offset);
+        }
+        p.y = std_max(1.0f, std_min(IVS_ADD(p.y, offset), (float)(n - 1)));
+    } else if (fptrack == 2) {
+        uint32_t xu = f2u(floorf(p.x));
+        if (xu > n - 1) xu = n - 1;
+        int yi = (int)floorf(p.y);
+        if (yi > (int)(n - 1)) yi = (int)(n - 1);
+        if (yi < 0) yi = 0;
+        const float* row = grid + (size_t)xu * n;
+        float offset = 0.0f, charge = 0.0f;
+        for (int k = 0; k < 5; k++) {
+            const float w = w5[yi * 5 + k];
+            const int idx = yi + k - 2;
+            if (w != 0.0f && (uint32_t)idx < n) {
+                const float cw = IVS_MUL(row[idx], w);
+                charge = IVS_ADD(cw, charge);
+                offset = IVS_ADD(IVS_MUL(cw, (float)(idx - yi)), offset);
+            }
+        }
+        offset = IVS_DIV(offset, charge);
+        p.y = std_max(1.0f, std_min(IVS_ADD(p.y, offset), (float)(n - 1)));
+    } else if (fptrack == 3) {
+        // pos.y -= pos.y*e1 + N(0, sqrt(2 e1)/dp)   (:264-266, std::normal_distribution)
+        const float sigma = IVS_DIV(sqrtf(IVS_MUL(2.0f, e1)), dp);
+        const float g = IVS_MUL(sigma, normal01(seed, step, i));
+        p.y = IVS_SUB(p.y, IVS_ADD(IVS_MUL(p.y, e1), g));
+    }
+    particles[i] = p;
+}
+
+// RotationMap::applyTo (src/SM/RotationMap.cpp:178-188)
+__global__ void track_rotate_kernel(float2* __restrict__ particles, uint32_t np, float cos_dt,
+                                    float sin_dt, float zb0, float zb1) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const float2 p = particles[i];
+    const float dx = IVS_SUB(p.x, zb0), dy = IVS_SUB(p.y, zb1);
+    float2 r;
+    r.x = IVS_ADD(IVS_ADD(IVS_MUL(cos_dt, dx), IVS_MUL(sin_dt, dy)), zb0);
+    r.y = IVS_ADD(IVS_SUB(IVS_MUL(cos_dt, dy), IVS_MUL(sin_dt, dx)), zb1);
+    particles[i] = r;
+}
+
+// the four applyTo() of one simulation step (src/main.cpp:1034-1041) for one particle:
+// wake kick (y), RF kick (y), drift (x), Fokker-Planck.  grid_fp_in = input grid of the
+// Fokker-Planck map (grid_t3), only read by FPTracking::approximation2.
+__device__ __forceinline__ void kick_one(float& par, float perp, const float* __restrict__ offset,
+                                         uint32_t n) {
+    const float ip = truncf(perp);
+    const float fr = IVS_SUB(perp, ip);
+    const uint32_t k = f2u(ip);
+    if (k + 1 < n) {
+        const float s = IVS_ADD(IVS_MUL(IVS_SUB(1.0f, fr), offset[k]), IVS_MUL(fr, offset[k + 1]));
+        par = IVS_SUB(par, s);
+    }
+    par = std_max(1.0f, std_min(par, (float)(n - 1)));
+}
+
+__global__ void track_step_kernel(float2* __restrict__ particles, uint32_t np, uint32_t n,
+                                  const float* __restrict__ wake, const float* __restrict__ rf,
+                                  const float* __restrict__ drift, const float* __restrict__ w5,
+                                  const float* __restrict__ grid, uint32_t fptrack, float e1,
+                                  float dp, uint64_t seed, uint64_t step) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t member = blockIdx.y;
+    if (i >= np) return;
+    float2 p = particles[(size_t)member * np + i];
+    if (wake) kick_one(p.y, p.x, wake + (size_t)member * n, n);
+    kick_one(p.y, p.x, rf, n);
+    kick_one(p.x, p.y, drift, n);
+    if (w5 && fptrack == 1) {
+        uint32_t yi = f2u(floorf(p.y));
+        if (yi > n - 1) yi = n - 1;
+        float offset = 0.0f;
+        for (int k = 0; k < 5; k++) {
+            const float w = w5[yi * 5 + k];
+            if (w != 0.0f) offset = IVS_ADD(IVS_MUL((float)(2 - k), w), offset);
+        }
+        p.y = std_max(1.0f, std_min(IVS_ADD(p.y, offset), (float)(n - 1)));
+    } else if (w5 && fptrack == 2) {
+        uint32_t xu = f2u(floorf(p.x));
+        if (xu > n - 1) xu = n - 1;
+        int yi = (int)floorf(p.y);
+        if (yi > (int)(n - 1)) yi = (int)(n - 1);
+        if (yi < 0) yi = 0;
+        const float* row = grid + ((size_t)member * n + xu) * n;
+        float offset = 0.0f, charge = 0.0f;
+        for (int k = 0; k < 5; k++) {
+            const float w = w5[yi * 5 + k];
+            const int idx = yi + k - 2;
+            if (w != 0.0f && (uint32_t)idx < n) {
+                const float cw = IVS_MUL(row[idx], w);
+                charge = IVS_ADD(cw, charge);
+                offset = IVS_ADD(IVS_MUL(cw, (float)(idx - yi)), offset);
+            }
+        }
+        offset = IVS_DIV(offset, charge);
+        p.y = std_max(1.0f, std_min(IVS_ADD(p.y, offset), (float)(n - 1)));
+    } else if (w5 && fptrack == 3) {
+        const float sigma = IVS_DIV(sqrtf(IVS_MUL(2.0f, e1)), dp);
+        const float g = IVS_MUL(sigma, normal01(seed + member, step, i));
+        p.y = IVS_SUB(p.y, IVS_ADD(IVS_MUL(p.y, e1), g));
+    }
+    particles[(size_t)member * np + i] = p;
+}
+
+}  // namespace
+
+ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
+                                 uint32_t n, const float* wake, const float* rf, const float* drift,
+                                 const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
+                                 float dp, uint64_t seed, uint64_t step) {
+    if (np == 0) return IVS_OK;
+    track_step_kernel<<<dim3(ivs_div_up(np, 256), members), 256, 0, ctx->stream>>>(
+        (float2*)particles, np, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, dp, seed, step);
+    IVS_LAUNCHED(ctx);
+    return IVS_OK;
+}
+
+ivs_status ivs_track_kick_launch(ivs_ctx* ctx, float* particles, uint32_t np, const float* offset,
+                                 uint32_t n, int axis) {
+    if (np == 0) return IVS_OK;
+    track_kick_kernel<<<ivs_div_up(np, 256), 256, 0, ctx->stream>>>((float2*)particles, np, offset, n, axis);
+    IVS_LAUNCHED(ctx);
+    return IVS_OK;
+}
+ivs_status ivs_track_fp_launch(ivs_ctx* ctx, float* particles, uint32_t np, const float* grid,
+                               uint32_t n, const float* w5, uint32_t fptrack, float e1, float dp,
+                               uint64_t seed, uint64_t step) {
+    if (np == 0 || fptrack == 0) return IVS_OK;
+    track_fp_kernel<<<ivs_div_up(np, 256), 256, 0, ctx->stream>>>((float2*)particles, np, grid, n, w5,
+                                                                 fptrack, e1, dp, seed, step);
+    IVS_LAUNCHED(ctx);
+    return IVS_OK;
+}
+
+extern "C" {
+
+ivs_status ivs_track_kick(ivs_ctx* ctx, void* d_particles, uint32_t np, const void* d_offset,
+                          uint32_t n, int axis) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, (d_particles || np == 0) && d_offset && n >= 2, "ivs_track_kick: null pointer");
+    IVS_REQUIRE(ctx, axis == 0 || axis == 1, "ivs_track_kick: axis must be 0 (x) or 1 (y)");
+    return ivs_track_kick_launch(ctx, (float*)d_particles, np, (const float*)d_offset, n, axis);
+}
+
+ivs_status ivs_track_fokker_planck(ivs_ctx* ctx, void* d_particles, uint32_t np,
+                                   const void* d_grid, uint32_t n, const void* d_weights,
+                                   uint32_t fptrack, float e1, float dp, uint64_t seed,
+                                   uint64_t step) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, fptrack <= 3, "ivs_track_fokker_planck: FPTracking must be 0..3");
+    IVS_REQUIRE(ctx, (d_particles || np == 0) && n >= 4, "ivs_track_fokker_planck: null pointer");
+    IVS_REQUIRE(ctx, fptrack == 0 || fptrack == 3 || d_weights, "ivs_track_fokker_planck: weights needed");
+    IVS_REQUIRE(ctx, fptrack != 2 || d_grid, "ivs_track_fokker_planck: grid needed for approximation2");
+    return ivs_track_fp_launch(ctx, (float*)d_particles, np, (const float*)d_grid, n,
+                               (const float*)d_weights, fptrack, e1, dp, seed, step);
+}
+
+ivs_status ivs_track_rotate(ivs_ctx* ctx, void* d_particles, uint32_t np, float angle,
+                            float zerobin_x, float zerobin_y) {
+    if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_REQUIRE(ctx, d_particles || np == 0, "ivs_track_rotate: null pointer");
+    if (np == 0) return IVS_OK;
+    track_rotate_kernel<<<ivs_div_up(np, 256), 256, 0, ctx->stream>>>(
+        (float2*)d_particles, np, cosf(-angle), sinf(-angle), zerobin_x, zerobin_y);
+    IVS_LAUNCHED(ctx);
+    return IVS_OK;
+}
+
+}  // extern "C"

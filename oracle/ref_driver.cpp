@@ -502,13 +502,16 @@ void* ref_sim_create(const ivs_ring_params* op, const float* grid, const float* 
                                                   d.revolutionpart, d.Ib, o.E0, o.sE, d.dt));
             s->wkm.reset(new WakePotentialMap(s->t1, s->t2, s->wake_field.get(), interpolationtype,
                                               interpol_clamp, nullptr));
-            // ElectricField::_wakescaling = Ib*dt*c/bl/(dp*sE*E0)/nmax (hpp:99-100, cpp:58)
+        } else {
+            s->wm_identity.reset(new Identity(s->t1, s->t2, nullptr));
+        }
+        {
+            // ElectricField::_wakescaling = Ib*dt*c/bl/(dp*sE*E0)/nmax (hpp:99-100, cpp:58);
+            // reported even when no wake map is built
             const meshaxis_t raw = d.Ib * d.dt * physcons::c / s->t1->getScale(0, "Meter") /
                                    (s->t1->getDelta(1) * o.sE * o.E0);
             d.wakescaling = raw / d.padded_bins;
-        } else {
-            s->wm_identity.reset(new Identity(s->t1, s->t2, nullptr));
-            d.wakescaling = 0;
+            if (s->wake_field) d.wakescaling = s->wake_field->_wakescaling;
         }
         for (uint32_t i = 0; i < np; i++) {
             s->trackme.push_back({particles[2 * i], particles[2 * i + 1]});
