@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-step Vlasov-Fokker-Planck update (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path, one rank per GPU
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle/_ref)
+
+metric : phase-space cell-updates/s  (N^2 * members * steps / time of the step loop only)
+workload (config.workload): BASELINE.json configs[4] -- 2048x2048 grid, sin RF (RFKickMap) +
+  DriftMap with alpha1/alpha2, free-space CSR wake, cubic interpolation, 4000 steps/T_s -- run
+  as a batch of `members` independent simulations per GPU (a bunch-current scan, the ensemble
+  partitioning of SURVEY.md section 8e) so that the state streamed per step (2 x members x 16 MiB)
+  exceeds the 126 MB L2: the timing rule "inputs larger than L2" instead of an L2 flush.
+  A single L2-resident 2048^2 run is reported next to it as `single_run`.
+One "step" = one simulation step of every member (wake potential, wake kick, RF kick, drift,
+Fokker-Planck, X projection).  N > 1 GPUs: every rank runs its own batch (replicas, weak
+scaling, no collective on the step path); value = all ranks' cell-updates / max time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from inovesa_b200.params import kara_params  # noqa: E402
+
+f32 = np.float32
+ALGO_BYTES_PER_CELL = 8.0  # one fp32 read + one fp32 write of the grid per step
+
+
+def workload_params(name):
+    if name == "config5":
+        return kara_params(grid_size=2048, steps_per_Ts=4000, linear_rf=0, alpha1=2e-4, alpha2=3e-3,
+                           gap=-1.0, bunch_current=50e-6, fp_track=3)
+    if name == "config1":
+        return kara_params(grid_size=256, steps_per_Ts=1000, gap=-1.0, bunch_current=50e-6)
+    if name == "config4":
+        return kara_params(grid_size=256, steps_per_Ts=1000, gap=-1.0, bunch_current=50e-6)
+    raise SystemExit("unknown workload " + name)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ our arm
+
+def run_ours(args):
+    import torch
+    from inovesa_b200 import capi
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    p = workload_params(args.workload)
+    n = p.grid_size
+    members = args.members
+    arith = capi.ARITH_STRICT if args.arith == "strict" else capi.ARITH_FMA
+    flags = capi.SIM_UNFUSED if args.unfused else 0
+    ctx = capi.Context(local_rank, arith)
+    stream = torch.cuda.ExternalStream(ctx.lib.ivs_ctx_stream(ctx.h), device=local_rank)
+    d = capi.derive(p)
+    # synthetic input: the reference's Gaussian start distribution; members of the batch differ
+    # in bunch current like a current scan (config 4's partitioning applied to this grid size)
+    currents = [float(p.bunch_current) * (0.5 + i / max(members, 1)) for i in range(members)]
+    rng = np.random.default_rng(12345 + rank)
+    parts = None
+    if args.particles:
+        parts = (rng.random((args.particles, 2)) * (n / 2) + n / 4).astype(f32)  # q,p in [-3,3]
+    sim = capi.Simulation(ctx, p, members, particles=parts, flags=flags, bunch_currents=currents,
+                          seed=rank)
+    single = capi.Simulation(ctx, p, 1, flags=flags) if args.single_run else None
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        fn(steps)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sim.step(args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ms = timed(sim.step, args.steps)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    cells_per_step = float(n) * n * members
+    value = cells_per_step * args.steps * world / (ms * 1e-3)
+
+    # kernel-level view: average duration of one step launch on the stream (fused: one kernel)
+    peak, peak_src = measured_peak()
+    achieved = cells_per_step * ALGO_BYTES_PER_CELL / (ms * 1e-3 / args.steps) / 1e9
+
+    # end to end through the C ABI with HOST buffers: per step upload the density from pinned
+    # host memory (PhaseSpace::syncCLMem cpu2dev), advance one step, read the bunch profile
+    # back (what main() consumes every step on the host side of the OpenCL path)
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    host_ptr = capi.P()
+    nbytes = int(cells_per_step) * 4
+    ctx.check(ctx.lib.ivs_host_alloc(ctx.h, nbytes, capi.C.byref(host_ptr)))
+    host_grid = np.ctypeslib.as_array(capi.C.cast(host_ptr, capi.C.POINTER(capi.C.c_float)),
+                                      shape=(int(cells_per_step),))
+    host_grid[:] = sim.download(profile=False, wake=False, particles=False)[0].reshape(-1)
+    prof = np.empty((members, n), f32)
+
+    def e2e_loop(steps):
+        for _ in range(steps):
+            ctx.check(ctx.lib.ivs_sim_upload_grid(sim.h, host_grid))
+            ctx.check(ctx.lib.ivs_sim_step(sim.h, 1))
+            ctx.check(ctx.lib.ivs_sim_download(sim.h, None, capi._ptr(prof), None, None))
+
+    e2e_loop(2)
+    t0 = time.perf_counter()
+    barrier()
+    e2e_loop(e2e_steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = cells_per_step * e2e_steps * world / e2e_s
+    ctx.check(ctx.lib.ivs_host_free(ctx.h, host_ptr))
+
+    single_run = None
+    if single is not None:
+        single.step(args.warmup)
+        ms1 = timed(single.step, args.steps)
+        single_run = {"cell_updates_per_s": float(n) * n * args.steps / (ms1 * 1e-3),
+                      "steps_per_s": args.steps / (ms1 * 1e-3), "us_per_step": ms1 * 1e3 / args.steps,
+                      "note": "one 2048^2 simulation, state L2-resident (no flush): latency-bound view"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(p, args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": "phase-space cell-updates/s", "value": value, "unit": "cell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[4]: 2048^2 grid, sin-RF RFKickMap + DriftMap(alpha1,alpha2), "
+                                   "free-space CSR wake, cubic, 4000 steps/T_s; batch of %d members/GPU "
+                                   "(bunch-current scan)" % members if args.workload == "config5"
+                       else args.workload,
+                       "grid": n, "members_per_gpu": members, "particles_per_member": args.particles,
+                       "arith": args.arith, "step_path": "unfused" if args.unfused else "fused",
+                       "l2": "inputs larger than L2 (state %d MiB/GPU)" % (2 * nbytes // 2**20),
+                       "parallelism": "replicas x%d (no collective on the step path)" % world},
+            "ensemble_steps_per_s": members * world * args.steps / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": int(prof.nbytes), "steps": e2e_steps,
+                    "what": "ivs_sim_upload_grid (pinned H2D) + ivs_sim_step(1) + profile D2H per step"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": cells_per_step * ALGO_BYTES_PER_CELL
+                         * (1 if not args.unfused else 1)},
+            "clocks": clocks,
+        }
+        if single_run:
+            line["single_run"] = single_run
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    sim.close()
+    if single is not None:
+        single.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ CPU arms
+
+def _ref_worker(args):
+    """one replica of the workload on one core through the reference's own code (oracle/_ref)"""
+    pdict, steps, warmup, budget_s, fma = args
+    from oracle import pyoracle
+    from inovesa_b200.params import RingParams
+    p = RingParams(**pdict)
+    kind = "reference" if pyoracle.available("ref", fma) else "port"
+    impl = pyoracle.Ref(fma) if kind == "reference" else pyoracle.Oracle(fma)
+    sim = impl.sim(p)
+    sim.step(warmup)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        sim.step(1)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    sim.close()
+    return kind, done, dt
+
+
+def _pdict(p):
+    return {name: getattr(p, name) for name, _ in p._fields_}
+
+
+def cpu_baseline_sample(p, seconds):
+    """bounded sample for the `cpu_baseline` object of our arm: the reference's CPU path, one
+    core (the reference is single-threaded), a few steps of the same grid"""
+    kind, done, dt = _ref_worker((_pdict(p), 10**6, 1, seconds, True))
+    n = p.grid_size
+    return {"value": float(n) * n * done / dt, "unit": "cell-updates/s", "cores": 1, "kind": kind,
+            "sample": "%d steps of one %dx%d simulation in %.1f s on 1 core (reference is "
+                      "single-threaded; built -O3 -march=x86-64-v3)" % (done, n, n, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    p = workload_params(args.workload)
+    n = p.grid_size
+    cores = max(1, min(os.cpu_count() or 1, args.cpu_replicas))
+    budget = args.reference_seconds
+    with mp.get_context("spawn").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, [(_pdict(p), args.steps, args.warmup, budget, True)] * cores)
+        wall = time.perf_counter() - t0
+    kind = res[0][0]
+    total_steps = sum(r[1] for r in res)
+    tmax = max(r[2] for r in res)
+    value = float(n) * n * total_steps / tmax
+    line = {
+        "impl": "reference", "metric": "phase-space cell-updates/s", "value": value,
+        "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tmax / max(res[0][1], 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[4]: 2048^2 grid, sin-RF + DriftMap(alpha1,alpha2), free-space "
+                               "CSR wake, cubic, 4000 steps/T_s" if args.workload == "config5" else args.workload,
+                   "grid": n, "replicas": cores},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": kind,
+                         "sample": "%d independent replicas (one per core), %d steps each of %d requested "
+                                   "(bounded to %.0f s), wall %.1f s" % (cores, res[0][1], args.steps, budget, wall)},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config5")
+    ap.add_argument("--members", type=int, default=8)
+    ap.add_argument("--particles", type=int, default=100000)
+    ap.add_argument("--arith", default="fma", choices=["fma", "strict"])
+    ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--single-run", dest="single_run", action="store_true", default=True)
+    ap.add_argument("--no-single-run", dest="single_run", action="store_false")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-replicas", type=int, default=64)
+    ap.add_argument("--reference-seconds", type=float, default=120.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

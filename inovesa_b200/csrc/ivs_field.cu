@@ -207,6 +207,16 @@ bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
 }  // namespace
 
+ivs_status ivs_field_prepare(ivs_ctx* ctx, uint32_t nmax) {
+    if (!is_pow2(nmax) || nmax < 4 || nmax > 16384)
+        return ivs_fail(ctx, IVS_ERR_UNSUPPORTED, "FFT length must be a power of two in [4, 16384]");
+    const float2* tw = nullptr;
+    ivs_status st = get_twiddles(ctx, nmax, &tw);
+    if (st != IVS_OK) return st;
+    IVS_CUDA(ctx, cudaFuncSetAttribute(field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * sizeof(float2)));
+    return IVS_OK;
+}
+
 // batched entry points used by the simulation object
 ivs_status ivs_field_launch(ivs_ctx* ctx, const float* profile, uint32_t n, uint32_t members,
                             const float* impedance, uint32_t nmax, const float* d_scaling,
@@ -223,11 +233,8 @@ ivs_status ivs_field_launch(ivs_ctx* ctx, const float* profile, uint32_t n, uint
     g.wake = wake; g.formfactor = (float2*)formfactor; g.spectrum = spectrum; g.power = power;
     g.dq = dq; g.f_scale = f_scale; g.cutoff = cutoff; g.n = n; g.nmax = nmax; g.mode = mode;
     const size_t smem = sizeof(float2) * nmax;  // two buffers of nmax/2
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (smem > 48 * 1024)
         IVS_CUDA(ctx, cudaFuncSetAttribute(field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * sizeof(float2)));
-        attr_set = true;
-    }
     const int threads = (nmax / 4 >= (uint32_t)kFftThreads) ? kFftThreads : (nmax / 4 < 32 ? 32 : (int)(nmax / 4));
     field_kernel<<<members, threads, smem, ctx->stream>>>(g);
     IVS_LAUNCHED(ctx);

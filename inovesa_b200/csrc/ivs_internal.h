@@ -26,6 +26,8 @@ ivs_status ivs_field_launch(ivs_ctx* ctx, const float* profile, uint32_t n, uint
                             const float* impedance, uint32_t nmax, const float* d_scaling,
                             float scaling, float* wake, float* formfactor, float* spectrum,
                             float* power, float dq, float f_scale, float cutoff, int mode);
+// allocates the twiddle table for an FFT length (must not happen inside a graph capture)
+ivs_status ivs_field_prepare(ivs_ctx* ctx, uint32_t nmax);
 // all four maps' applyTo for every tracked particle of every member, one launch per step
 ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
                                  uint32_t n, const float* wake, const float* rf, const float* drift,
@@ -40,8 +42,10 @@ struct ivs_fused_plan {
     uint32_t pad_y = 0;       // zero columns kept left and right of every staged row
     uint32_t threads = 0;
     size_t smem = 0;
-    void* drift_taps = nullptr;  // device table of ivs_taps per column
-    void* rf_taps = nullptr;     // device table of ivs_taps per row
+    // device tables: first tap position and 4 weights per row / column
+    void* rf_first = nullptr; void* rf_w = nullptr;
+    void* dr_first = nullptr; void* dr_w = nullptr;
+    void* fp_base = nullptr; void* fp_w = nullptr;
     bool ready = false;
 };
 ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan);

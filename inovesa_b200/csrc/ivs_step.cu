@@ -16,40 +16,7 @@
 
 #include "ivs_common.cuh"
 #include "ivs_internal.h"
-
-struct ivs_sim {
-    ivs_ctx* ctx = nullptr;
-    ivs_sim_desc desc{};
-    uint32_t n = 0, members = 0, it = 4, nmax = 0, np = 0;
-    bool has_wake = false, has_fp = false, has_rad = false;
-    float* grid[3] = {nullptr, nullptr, nullptr};  // t1, t2, t3 (unfused) / ping, pong (fused)
-    int cur = 0;                                   // index of the buffer holding grid_t1
-    float* profile[2] = {nullptr, nullptr};        // X projection (double buffered for the fused path)
-    int pcur = 0;
-    float* wake = nullptr;        // [members][n] offsets applied by the last wake kick
-    float* rf = nullptr;          // [n]
-    float* drift = nullptr;       // [n]
-    float* fpw = nullptr;         // [n][5]
-    float* ws = nullptr;          // [n]
-    float* impedance = nullptr;   // [nmax] complex
-    float* rad_impedance = nullptr;
-    float* wakescaling = nullptr; // [members]
-    float* wakefunction = nullptr;// [2n-1] unit-scaled wake function (fused path)
-    float* particles = nullptr;   // [members][np][2]
-    float* projy = nullptr;       // [members][n]
-    float* obs = nullptr;         // [members][8] + scratch
-    float* integral = nullptr;    // [members]
-    float* moments = nullptr;     // [members][2][3]
-    float* power = nullptr;       // [members]
-    int* status = nullptr;        // device error flag of the fused kernel
-    float f_scale = 0, cutoff = 0;
-    uint64_t steps_done = 0;
-    ivs_fused_plan plan{};
-    cudaGraphExec_t graph1 = nullptr;   // one step
-    cudaGraphExec_t graphK = nullptr;   // kGraphSteps steps
-    int graph_cur = -1;                 // buffer parity the graphs were captured for
-    static constexpr uint32_t kGraphSteps = 16;
-};
+#include "ivs_sim_struct.h"
 
 namespace {
 
@@ -259,6 +226,7 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
         S_TRY(dalloc(ctx, &s->wakefunction, (size_t)2 * n));
         S_TRY(ivs_upload(ctx, s->impedance, d->impedance, (size_t)2 * s->nmax * sizeof(float)));
         S_TRY(ivs_upload(ctx, s->wakescaling, d->wakescaling, m * sizeof(float)));
+        S_TRY(ivs_field_prepare(ctx, s->nmax));
         wf = wake_function_host(d->impedance, s->nmax, n);
         wf.push_back(0.0f);
         S_TRY(ivs_upload(ctx, s->wakefunction, wf.data(), (size_t)2 * n * sizeof(float)));
@@ -381,6 +349,7 @@ ivs_status ivs_sim_set_radiation(ivs_sim* s, const float* rad_impedance, float f
     uint32_t nmax = s->nmax ? s->nmax : s->desc.nmax;
     IVS_REQUIRE(ctx, nmax != 0 && (nmax & (nmax - 1)) == 0 && nmax <= 16384 && nmax >= s->n,
                 "ivs_sim_set_radiation: the simulation needs a power-of-two nmax");
+    IVS_TRY(ivs_field_prepare(ctx, nmax));
     if (!s->rad_impedance) IVS_TRY(dalloc(ctx, &s->rad_impedance, (size_t)2 * nmax));
     IVS_TRY(ivs_upload(ctx, s->rad_impedance, rad_impedance, (size_t)2 * nmax * sizeof(float)));
     IVS_TRY(ivs_sync(ctx));

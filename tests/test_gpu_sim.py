@@ -1,0 +1,203 @@
+"""The whole step on the device against the oracle on identical inputs (north_star's parity
+bar: relative L1 error of the phase-space density <= 1e-5 over the first 1000 steps), plus
+ensemble batching, tracking inside the step, observables and the host round trip."""
+import numpy as np
+import pytest
+
+from conftest import rel_l1
+from inovesa_b200.params import kara_params
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+L1_TOL = 1e-5  # BASELINE.json north_star
+
+
+def run_pair(capi, ctx, oracle, p, nsteps, flags, checkpoints, particles=None):
+    osim = oracle.sim(p, None, particles)
+    t = osim.tables()
+    sim = capi.Simulation(ctx, p, 1, particles=particles, flags=flags,
+                          tables=dict(rf=t["rf"], drift=t["drift"], fp5=t["fp5"],
+                                      zwake=t["zwake"] if np.any(t["zwake"]) else None))
+    out, done = [], 0
+    try:
+        for cp in checkpoints:
+            sim.step(cp - done)
+            osim.step(cp - done)
+            done = cp
+            g, pr, w, pt = sim.download()
+            og, opr, ow, opt = osim.get()
+            out.append(dict(step=cp, l1=rel_l1(g[0], og), prof=rel_l1(pr[0], opr),
+                            wake=np.abs(w[0] - ow).max() / max(np.abs(ow).max(), 1e-30),
+                            parts=None if pt is None else np.abs(pt[0] - opt).max()))
+    finally:
+        sim.close()
+        osim.close()
+    return out
+
+
+@pytest.mark.parametrize("path", ["fused", "unfused"])
+@pytest.mark.parametrize("mode", ["strict", "fma"])
+def test_config1_parity_1000_steps(capi, ctx_strict, ctx_fma, oracle, mode, path):
+    """config 1 (256^2, free-space CSR, cubic, below threshold): L1 <= 1e-5 through step 1000"""
+    ctx = ctx_strict if mode == "strict" else ctx_fma
+    p = kara_params(grid_size=256, bunch_current=50e-6)
+    flags = capi.SIM_UNFUSED if path == "unfused" else 0
+    res = run_pair(capi, ctx, oracle, p, 1000, flags, [1, 10, 100, 500, 1000])
+    for r in res:
+        assert r["l1"] <= L1_TOL, r
+        assert r["prof"] <= L1_TOL, r
+    if mode == "strict":
+        # identical tables, identical rounding in every map; only the wake FFT and the
+        # projection order differ from the oracle -> far below the bar
+        assert res[0]["l1"] < 2e-7
+
+
+def test_unfused_variants(capi, ctx_strict, oracle, rng):
+    """parallel plates + resistive wall + collimator, sin RF with alpha1/alpha2, quadratic
+    interpolation, 3-point Fokker-Planck, no wake; with tracked particles (FPTrack 2)"""
+    cases = [
+        kara_params(grid_size=128, gap=0.032, bunch_current=100e-6, wall_conductivity=5.8e7,
+                    collimator=0.008, steps_per_Ts=2000),
+        kara_params(grid_size=128, linear_rf=0, alpha1=2e-4, alpha2=3e-3, steps_per_Ts=4000),
+        kara_params(grid_size=96, interpolation=3, derivation=3, gap=0.0),
+        kara_params(grid_size=64, interpolation=2, fp_type=1),
+    ]
+    for p in cases:
+        p.fp_track = 2
+        parts = (rng.random((500, 2)) * (p.grid_size - 3) + 1).astype(f32)
+        res = run_pair(capi, ctx_strict, oracle, p, 200, capi.SIM_UNFUSED, [1, 50, 200], parts)
+        for r in res:
+            assert r["l1"] <= L1_TOL, (p.grid_size, r)
+            assert r["parts"] < 1e-3, (p.grid_size, r)
+
+
+def _states(capi, ctx, p, flags, steps, members=1, currents=None, particles=None):
+    sim = capi.Simulation(ctx, p, members, flags=flags, bunch_currents=currents, particles=particles)
+    out = []
+    for k in steps:
+        sim.step(k)
+        out.append(sim.download())
+    sim.close()
+    return out
+
+
+@pytest.mark.parametrize("mode", ["strict", "fma"])
+@pytest.mark.parametrize("case", [
+    dict(grid_size=256),
+    dict(grid_size=512, gap=0.032, bunch_current=300e-6, steps_per_Ts=2000),
+    dict(grid_size=1024, steps_per_Ts=4000, gap=0.032, wall_conductivity=5.8e7, collimator=0.008),
+    dict(grid_size=2048, steps_per_Ts=4000, linear_rf=0, alpha1=2e-4, alpha2=3e-3),
+    dict(grid_size=2048, steps_per_Ts=1000),       # multi-cell displacements: wide halos
+    dict(grid_size=128, interpolation=3, derivation=3),
+    dict(grid_size=64, interpolation=2, gap=0.0),   # no wake map
+    dict(grid_size=96, fp_type=0),
+], ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_fused_equals_unfused_bit_for_bit(capi, ctx_strict, ctx_fma, mode, case):
+    """the one-kernel step and the reference's kernel sequence share every rounding except the
+    wake potential (Toeplitz product in double vs fp32 FFT), so with the FFT path's wake
+    differing by ~1e-7 the grids agree to that; without a wake they are identical"""
+    ctx = ctx_strict if mode == "strict" else ctx_fma
+    p = kara_params(**case)
+    a = _states(capi, ctx, p, 0, [1, 7, 24])
+    b = _states(capi, ctx, p, capi.SIM_UNFUSED, [1, 7, 24])
+    for (ga, pa, wa, _), (gb, pb, wb, _) in zip(a, b):
+        if p.gap == 0.0:
+            assert np.array_equal(ga, gb)
+        else:
+            assert rel_l1(ga, gb) < 2e-7
+            assert np.abs(wa - wb).max() <= 3e-6 * max(np.abs(wb).max(), 1e-30)
+        assert np.allclose(pa, pb, rtol=1e-5, atol=1e-9)
+
+
+def test_fused_properties_at_full_size(capi, ctx_fma):
+    """2048^2 x 4 members: charge conservation and member independence at the benchmark size"""
+    p = kara_params(grid_size=2048, steps_per_Ts=4000, linear_rf=0, alpha1=2e-4, alpha2=3e-3)
+    currents = [10e-6, 50e-6, 100e-6, 50e-6]
+    (g, pr, w, _), = _states(capi, ctx_fma, p, 0, [40], members=4, currents=currents)
+    assert np.array_equal(g[1], g[3]) and not np.array_equal(g[0], g[2])
+    d = capi.derive(p)
+    ws = capi.simpson_weights(2048, d.dq).astype(np.float64)
+    q = (pr.astype(np.float64) * ws).sum(1)
+    assert np.all(np.abs(q - 1) < 1e-5)
+    assert np.all(np.isfinite(g)) and g.min() > -1e-3
+
+
+def test_fused_tracking_matches_unfused(capi, ctx_strict, rng):
+    p = kara_params(grid_size=256)
+    p.fp_track = 1
+    parts = (rng.random((2000, 2)) * 200 + 28).astype(f32)
+    (ga, _, _, pa), = _states(capi, ctx_strict, p, 0, [30], particles=parts)
+    (gb, _, _, pb), = _states(capi, ctx_strict, p, capi.SIM_UNFUSED, [30], particles=parts)
+    assert np.abs(pa - pb).max() < 1e-3
+    p.fp_track = 2
+    with pytest.raises(capi.IvsError) as e:
+        capi.Simulation(ctx_strict, p, 1, particles=parts)
+    assert e.value.code == capi.ERR_UNSUPPORTED
+
+
+def test_fused_flags_displacements_beyond_its_halo(capi, ctx_strict):
+    """a wake kick of many cells cannot be served from the staged pad: the step must say so"""
+    p = kara_params(grid_size=128, bunch_current=5.0)  # absurd current -> huge wake offsets
+    sim = capi.Simulation(ctx_strict, p, 1)
+    sim.step(2)
+    with pytest.raises(capi.IvsError) as e:
+        sim.download()
+    assert e.value.code == capi.ERR_HALO
+    sim.close()
+
+
+def test_graph_and_direct_launch_agree(capi, ctx_strict):
+    p = kara_params(grid_size=128)
+    for base in (capi.SIM_UNFUSED, 0):
+        a = capi.Simulation(ctx_strict, p, 1, flags=base)
+        b = capi.Simulation(ctx_strict, p, 1, flags=base | capi.SIM_NO_GRAPH)
+        a.step(37); b.step(37)
+        ga, gb = a.download()[0], b.download()[0]
+        assert np.array_equal(ga, gb)
+        assert a.steps_done == b.steps_done == 37
+        a.close(); b.close()
+
+
+def test_ensemble_members_are_independent(capi, ctx_strict):
+    """config 4 in miniature: members differ only in bunch current (wake scaling)"""
+    p = kara_params(grid_size=64)
+    currents = [20e-6, 50e-6, 200e-6, 400e-6]
+    for flags in (capi.SIM_UNFUSED, 0):
+        ens = capi.Simulation(ctx_strict, p, len(currents), flags=flags, bunch_currents=currents)
+        ens.step(50)
+        g = ens.download()[0]
+        for i, ib in enumerate(currents):
+            p1 = kara_params(grid_size=64, bunch_current=ib)
+            one = capi.Simulation(ctx_strict, p1, 1, flags=flags)
+            one.step(50)
+            assert np.array_equal(one.download()[0][0], g[i])
+            one.close()
+        assert not np.array_equal(g[0], g[3])
+        ens.close()
+
+
+def test_observables(capi, ctx_strict, oracle):
+    p = kara_params(grid_size=128, bunch_current=100e-6)
+    osim = oracle.sim(p)
+    sim = capi.Simulation(ctx_strict, p, 1, flags=capi.SIM_UNFUSED)
+    sim.set_radiation()
+    sim.step(100); osim.step(100)
+    obs = sim.observe()[0]
+    oobs = osim.observe()[0]
+    # integral, sigma_q, sigma_p, CSR power
+    assert abs(obs[0] / oobs[0] - 1) < 1e-5
+    assert abs(obs[3] / oobs[3] - 1) < 1e-5 and abs(obs[6] / oobs[6] - 1) < 1e-5
+    assert abs(obs[7] / oobs[7] - 1) < 1e-4
+    assert abs(obs[1] - oobs[1]) < 1e-4 and abs(obs[4] - oobs[4]) < 1e-4
+    # charge is conserved to round-off over the run, renormalisation restores it
+    sim.renormalize()
+    sim.upload_grid(sim.download()[0])
+    assert abs(sim.observe()[0][0] - 1) < 1e-5
+    sim.close(); osim.close()
+
+
+def test_invalid_descriptors(capi, ctx_strict):
+    p = kara_params(grid_size=4)
+    with pytest.raises(capi.IvsError) as e:
+        capi.Simulation(ctx_strict, p, 1, flags=capi.SIM_UNFUSED, grid=np.zeros((4, 4), f32))
+    assert e.value.code == capi.ERR_INVALID_ARGUMENT
