@@ -214,7 +214,8 @@ enum {
     IVS_SIM_WAKE_FFT = 1u,      /* per-step wake potential through the FFT kernel instead of the
                                    Toeplitz product (same operator) */
     IVS_SIM_UNFUSED = 2u,       /* run the step as the reference's kernel sequence (debug / parity) */
-    IVS_SIM_NO_GRAPH = 4u       /* launch kernels directly instead of replaying a CUDA graph */
+    IVS_SIM_NO_GRAPH = 4u,      /* launch kernels directly instead of replaying a CUDA graph */
+    IVS_SIM_TILED = 8u          /* fused step as the tile kernel instead of the streaming pipeline */
 };
 
 ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* desc, ivs_sim** out);

@@ -19,7 +19,7 @@ struct ivs_sim {
     float* impedance = nullptr;   // [nmax] complex
     float* rad_impedance = nullptr;
     float* wakescaling = nullptr; // [members]
-    float* wakefunction = nullptr;// [2n-1] unit-scaled wake function (fused path)
+    double* wakefunction = nullptr;// [2n] unit-scaled wake function in double (fused path)
     float* particles = nullptr;   // [members][np][2]
     float* projy = nullptr;       // [members][n]
     float* obs = nullptr;         // [members][8] + scratch

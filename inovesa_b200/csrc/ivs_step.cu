@@ -110,7 +110,7 @@ uint32_t launches_per_step(const ivs_sim* s) {
 
 // unit wake function w[m], m = -(n-1)..(n-1): c2r of the Hermitian-extended impedance with the
 // reference's conventions (imaginary part of bin 0 ignored, bins >= nmax/2 zero), in double.
-std::vector<float> wake_function_host(const float* z, uint32_t nmax, uint32_t n) {
+std::vector<double> wake_function_host(const float* z, uint32_t nmax, uint32_t n) {
     const double two_pi = 6.283185307179586476925286766559005768;
     std::vector<std::complex<double>> a(nmax, 0.0);
     a[0] = std::complex<double>(z[0], 0.0);
@@ -136,9 +136,9 @@ std::vector<float> wake_function_host(const float* z, uint32_t nmax, uint32_t n)
             }
         }
     }
-    std::vector<float> w(2 * n - 1);
+    std::vector<double> w(2 * n - 1);
     for (int m = -(int)(n - 1); m <= (int)(n - 1); m++) {
-        w[m + (int)(n - 1)] = (float)a[(uint32_t)((m + (int)nmax) % (int)nmax)].real();
+        w[m + (int)(n - 1)] = a[(uint32_t)((m + (int)nmax) % (int)nmax)].real();
     }
     return w;
 }
@@ -155,8 +155,9 @@ ivs_status ivs_wake_function(ivs_ctx* ctx, const void* d_impedance, uint32_t nma
                 "ivs_wake_function: nmax must be a power of two >= 2n");
     std::vector<float> z(2 * (size_t)nmax);
     IVS_TRY(ivs_download(ctx, z.data(), d_impedance, z.size() * sizeof(float)));
-    std::vector<float> w = wake_function_host(z.data(), nmax, n);
-    for (float& v : w) v = wakescaling * v;
+    std::vector<double> wd = wake_function_host(z.data(), nmax, n);
+    std::vector<float> w(wd.size());
+    for (size_t i = 0; i < wd.size(); i++) w[i] = wakescaling * (float)wd[i];
     IVS_TRY(ivs_upload(ctx, d_wakefunction, w.data(), w.size() * sizeof(float)));
     return ivs_sync(ctx);
 }
@@ -219,7 +220,7 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
         S_TRY(ivs_upload(ctx, s->fpw, fpw.data(), (size_t)n * 5 * sizeof(float)));
     }
     S_TRY(ivs_sync(ctx));  // host vectors above go out of scope
-    std::vector<float> wf;
+    std::vector<double> wf;
     if (has_wake) {
         S_TRY(dalloc(ctx, &s->impedance, (size_t)2 * s->nmax));
         S_TRY(dalloc(ctx, &s->wakescaling, m));
@@ -228,8 +229,8 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
         S_TRY(ivs_upload(ctx, s->wakescaling, d->wakescaling, m * sizeof(float)));
         S_TRY(ivs_field_prepare(ctx, s->nmax));
         wf = wake_function_host(d->impedance, s->nmax, n);
-        wf.push_back(0.0f);
-        S_TRY(ivs_upload(ctx, s->wakefunction, wf.data(), (size_t)2 * n * sizeof(float)));
+        wf.push_back(0.0);
+        S_TRY(ivs_upload(ctx, s->wakefunction, wf.data(), (size_t)2 * n * sizeof(double)));
     }
     if (s->np) {
         S_TRY(dalloc(ctx, &s->particles, (size_t)m * s->np * 2));
@@ -255,7 +256,7 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
     ivs_fused_plan_destroy(&s->plan);
     float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
                      s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
-                     s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power};
+                     (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power};
     for (float* b : bufs) if (b) cudaFree(b);
     if (s->status) cudaFree(s->status);
     delete s;
