@@ -23,6 +23,7 @@
 // Every tap accumulation is madd<FMA>() in the reference's order, so the result is bit-identical
 // to the unfused kernel sequence (ivs_maps.cu) -- tested.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "ivs_internal.h"
@@ -518,23 +519,29 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
 
 
 // ------------------------------------------------------------------------------------------
-// Streaming variant (grid sizes that are multiples of 128): a CTA owns a strip of consecutive
-// rows of one member and pushes them through a warp-specialised pipeline over a ring of row
-// slots in shared memory -- no block-wide phases, every row is kicked once, copies overlap math:
+// Streaming variant (grid sizes that are multiples of 256, up to 2048): a CTA owns a strip of
+// consecutive rows of one member; its n/4 threads each own 4 adjacent columns (one float4) for
+// the whole strip and march down the rows:
 //
-//   producer warp   : one TMA bulk copy per row into the next free slot          (full[slot])
-//   kick warps      : wake potential of the row (Toeplitz, double), wake kick + RF kick in
-//                     place, one warp per row, float4 per lane                   (kicked[slot])
-//   drift/FP warps  : n/4 threads, each owns 4 columns for the whole strip (taps in registers):
-//                     drift from the ring into a scratch row, Fokker-Planck from the scratch row
-//                     straight to global memory (STG.128) + projection partials  (free[slot])
+//   TMA engine   : one bulk copy per input row into a ring of row slots, issued by thread 0 a
+//                  ring depth ahead (completion on one mbarrier per slot);
+//   kick         : a thread reads the 10..13 staged values its quad depends on (3-4 LDS.128) and
+//                  applies wake kick and RF kick back to back in registers -- the 7 wake-kicked
+//                  values the RF taps need are recomputed per thread instead of being exchanged,
+//                  so the row-local passes cost no shared-memory round trip and no barrier;
+//   drift        : column-local, so it is a sliding window of kicked rows in registers (4 rows, 5
+//                  where the first drift tap changes inside the quad);
+//   Fokker-Planck: needs 2 neighbours left and right: the drifted quad goes through a
+//                  double-buffered scratch row, ONE block barrier per output row, then the stencil,
+//                  STG.128 and the Simpson-weighted row sum (next step's profile).
 //
-// Synchronisation is by mbarriers only (plus one named barrier per output row inside the
-// drift/FP group).  Arithmetic per cell is identical to the tile kernels.
+// The barrier of row i also proves that nobody reads the oldest ring slot any more, so thread 0
+// re-arms it right after.  The wake potential of the strip's rows (Toeplitz product in double)
+// is formed by the whole CTA while the first copies are in flight.  Arithmetic per cell is
+// identical to the tile kernels (same taps, same order) -- tested bit for bit.
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+constexpr int kPadS = 32;  // zero columns each side of a staged row: two kicks of up to 16 cells
+
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -545,229 +552,404 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 struct stream_args {
     fused_args f;
     uint32_t strip;     // rows per strip
-    uint32_t kslots;    // ring slots (power of two)
-    uint32_t ndf;       // drift/FP warps (= n/128)
-    uint32_t nkick;     // kick warps
+    uint32_t kslots;    // ring slots
+    uint32_t dead_off;  // after the barrier of output row i, input rows < i + dead_off are dead
+    uint32_t max_strip; // capacity of the partial-sum table (rows)
+    uint32_t max_rin;   // capacity of the per-row tap tables (input rows)
 };
 
-template <bool FMA, bool REBALANCE>
-__global__ void __launch_bounds__(1024, 1) stream_step_kernel(const stream_args sa) {
+// shared-memory accessors on 32-bit shared addresses (no 64-bit generic pointer arithmetic)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(bar), "r"(phase)
+        : "memory");
+    return ok;
+}
+// blocking wait; a copy that never lands (a bug, not a load condition) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t phase) {
+    uint32_t ok, tries = 0;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(bar), "r"(phase)
+            : "memory");
+        if (!ok && ++tries > (1u << 24)) __trap();
+    } while (!ok);
+}
+
+// wake kick then RF kick of one quad of columns (y0 .. y0+3) of a staged row, in registers.
+//   k1[m] = sum_j in[m + f1 + j] w1[j]         wake kick (src/SM/KickMap.cpp:243-266), 0 outside the grid
+//   out[y] = sum_j k1[y + f2 + j] w2[j]        RF kick, same loop
+// `p` is the shared address of in[y0 + a], a = (f1+f2) rounded down to a multiple of 4, RR the rest.
+template <bool FMA, int RR>
+__device__ __forceinline__ float4 kick_quad_rr(uint32_t p, int m0, uint32_t n, const float4 w1, const float4 w2) {
+    float in[16];
+    {
+        const float4 A = lds128(p), B = lds128(p + 16), C = lds128(p + 32);
+        in[0] = A.x; in[1] = A.y; in[2] = A.z; in[3] = A.w;
+        in[4] = B.x; in[5] = B.y; in[6] = B.z; in[7] = B.w;
+        in[8] = C.x; in[9] = C.y; in[10] = C.z; in[11] = C.w;
+        if (RR == 3) {
+            const float4 D = lds128(p + 48);
+            in[12] = D.x; in[13] = D.y; in[14] = D.z; in[15] = D.w;
+        }
+    }
+    float k1[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) k1[i] = tap4<FMA>(in[RR + i], in[RR + i + 1], in[RR + i + 2], in[RR + i + 3], w1);
+    if ((uint32_t)m0 > n - 7) {  // some of m0 .. m0+6 lie outside the grid: the wake-kicked grid is 0 there
+#pragma unroll
+        for (int i = 0; i < 7; i++)
+            if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
+    }
+    float4 o;
+    o.x = tap4<FMA>(k1[0], k1[1], k1[2], k1[3], w2);
+    o.y = tap4<FMA>(k1[1], k1[2], k1[3], k1[4], w2);
+    o.z = tap4<FMA>(k1[2], k1[3], k1[4], k1[5], w2);
+    o.w = tap4<FMA>(k1[3], k1[4], k1[5], k1[6], w2);
+    return o;
+}
+template <bool FMA>
+__device__ __forceinline__ float4 kick_quad(uint32_t row_q, int fsum, int m0, uint32_t n, const float4 w1, const float4 w2) {
+    const int a = fsum & ~3;  // floor to a multiple of 4 (two's complement: also for negatives)
+    const uint32_t p = row_q + (uint32_t)(a * 4);
+    switch (fsum - a) {
+    case 0: return kick_quad_rr<FMA, 0>(p, m0, n, w1, w2);
+    case 1: return kick_quad_rr<FMA, 1>(p, m0, n, w1, w2);
+    case 2: return kick_quad_rr<FMA, 2>(p, m0, n, w1, w2);
+    default: return kick_quad_rr<FMA, 3>(p, m0, n, w1, w2);
+    }
+}
+
+template <bool FMA>
+__global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args sa) {
     const fused_args& g = sa.f;
     extern __shared__ __align__(128) float smem[];
     const uint32_t n = g.n, nq = g.n >> 2, pitch = g.pitch, hl = g.hl;
     const uint32_t H = g.hl + g.hr;
-    const uint32_t K = sa.kslots, kmask = K - 1;
-    const uint32_t klog = 31 - __clz(K);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t K = sa.kslots;
+    const uint32_t T = blockDim.x;  // == nq
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
     const uint32_t member = blockIdx.y;
     const uint32_t xa = blockIdx.x * sa.strip;
     const uint32_t S = min(sa.strip, n - xa);  // output rows of this strip
     const uint32_t RIN = S + H;                // input rows streamed through the ring
     const int xs = (int)xa - (int)hl;          // grid row of input row 0
 
-    float* ring = smem;                                                   // K x pitch
-    float* scratch = ring + (size_t)K * pitch;                            // 2 x pitch
-    double* rho = reinterpret_cast<double*>(scratch + 2 * (size_t)pitch); // n
-    uint64_t* full = reinterpret_cast<uint64_t*>(rho + n);                // K
-    uint64_t* kicked = full + K;                                          // K
-    uint64_t* freeb = kicked + K;                                         // K
-    float* red = reinterpret_cast<float*>(freeb + K);                     // 2 x 32
+    // shared memory carve-up (every block 16-byte aligned)
+    unsigned char* sp = reinterpret_cast<unsigned char*>(smem);
+    auto carve = [&sp](size_t bytes) {
+        unsigned char* p = sp;
+        sp += (bytes + 15) & ~(size_t)15;
+        return p;
+    };
+    float* ring = reinterpret_cast<float*>(carve((size_t)K * pitch * 4));        // K row slots
+    float* scratch = reinterpret_cast<float*>(carve((size_t)2 * pitch * 4));     // 2 drifted rows
+    double* rho = reinterpret_cast<double*>(carve((size_t)(n + (n >> 5)) * 8));  // last step's profile (skewed)
+    double* partial = reinterpret_cast<double*>(carve((size_t)NW * sa.max_rin * 8));  // wake partial sums
+    float* red = reinterpret_cast<float*>(carve((size_t)sa.max_strip * NW * 4)); // row-sum partials
+    float4* tab_w1 = reinterpret_cast<float4*>(carve((size_t)sa.max_rin * 16));  // wake taps per input row
+    float4* tab_w2 = reinterpret_cast<float4*>(carve((size_t)sa.max_rin * 16));  // RF taps per input row
+    int2* tab_f = reinterpret_cast<int2*>(carve((size_t)sa.max_rin * 8));        // (f1 + f2, f2)
+    uint64_t* full = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
 
     const float* gin = g.in + (size_t)member * n * n;
+    const uint32_t pitchB = pitch * 4;
+    const uint32_t full_b = smem_u32(full);
 
-    // ---- set-up by everybody: barriers, zero pads, last step's profile in double
-    if (tid == 0) {
-        for (uint32_t s = 0; s < K; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&kicked[s], 1);
-            mbar_init(&freeb[s], 1);
+    // ---- thread 0 drives the TMA engine: row r lives in slot r % K, phase (r / K) & 1
+    uint32_t top = 0;  // rows issued so far
+    auto issue_rows = [&](uint32_t limit) {  // thread 0 only
+        for (; top < limit; top++) {
+            const int x = xs + (int)top;
+            const uint32_t slot = top % K;
+            if ((uint32_t)x >= n) {
+                // rows outside the grid are never staged (readers substitute zeros); the slot's
+                // barrier still moves on one phase so that phase == (row / K) & 1 holds for every row
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_b + slot * 8) : "memory");
+                continue;
+            }
+            fence_proxy_async();  // earlier generic-proxy reads of the slot are ordered before the async write
+            mbar_expect_tx(&full[slot], n * (uint32_t)sizeof(float));
+            bulk_g2s(ring + (size_t)slot * pitch + kPadS, gin + (size_t)x * n, n * (uint32_t)sizeof(float), &full[slot]);
         }
+    };
+    auto row_bar = [&](uint32_t r, uint32_t& bar, uint32_t& phase) {
+        const uint32_t use = r / K;
+        bar = full_b + (r - use * K) * 8;
+        phase = use & 1;
+    };
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < K; s++) mbar_init(&full[s], 1);
     }
-    for (uint32_t r = warp; r < K + 2; r += (blockDim.x >> 5)) {
+    __syncthreads();
+    if (tid == 0) issue_rows(min(K, RIN));
+
+    // ---- set-up by everybody: zero pads, RF taps, last step's profile in double
+    for (uint32_t r = warp; r < K + 2; r += NW) {
         float* row = ring + (size_t)r * pitch;  // the two scratch rows follow the ring
-        if (lane < kPad) row[lane] = 0.0f; else row[n + kPad + (lane - kPad)] = 0.0f;
+        row[lane] = 0.0f;
+        row[n + kPadS + lane] = 0.0f;
     }
     if (g.has_wake) {
         const float* rin = g.rho_in + (size_t)member * n;
-        for (uint32_t i = tid; i < n; i += blockDim.x) rho[i] = (double)rin[i];
-    }
-    __syncthreads();
-
-    if (warp < sa.ndf) {
-        // =============================== drift + Fokker-Planck group ===========================
-        if (REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-        const uint32_t ndf_threads = sa.ndf * 32;
-        const uint32_t q = tid;            // this thread's quad of columns, y = 4q .. 4q+3
-        const uint32_t y = q << 2;
-        // drift taps of the 4 columns
-        const int4 df = __ldg(reinterpret_cast<const int4*>(g.dr_first) + q);
-        const float4 dw0 = __ldg(&g.dr_w[y]), dw1 = __ldg(&g.dr_w[y + 1]);
-        const float4 dw2 = __ldg(&g.dr_w[y + 2]), dw3 = __ldg(&g.dr_w[y + 3]);
-        const bool uniform = (df.x == df.y) && (df.y == df.z) && (df.z == df.w);
-        // Fokker-Planck weights (5 per column) and Simpson weights
-        float w5[4][5];
-        {
-            const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)y * 5);
-            float t[20];
+        for (uint32_t i = tid; i < n; i += T) rho[i + (i >> 5)] = (double)rin[i];
+        __syncthreads();
+        // W[x] = scaling * sum_x' rho[x'] w[x-x']  (src/PS/ElectricField.cpp:186-253 as a Toeplitz
+        // product).  Warp w sums x' in [128 w, 128 w + 128); a lane owns 8 consecutive rows and 32
+        // consecutive x', so the 8 wake-function values it needs slide through registers: one table
+        // load and one profile load per 8 multiply-adds.
+        const uint32_t rbk = lane & 7, sub = lane >> 3;
+        const uint32_t xb = warp * 128 + sub * 32;
+        const double* rp = rho + xb + (xb >> 5);
+        const int wtop = (int)(2 * n - 1);
+        for (uint32_t pass = 0; pass * 64 < RIN; pass++) {  // warp-uniform trip count
+            const uint32_t r0 = pass * 64 + rbk * 8;
+            // w[x - x'] is stored at index x - x' + n - 1
+            const int base = xs + (int)r0 + (int)n - 1 - (int)xb;
+            double wv[8], acc[8];
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const float4 v = __ldg(wp + k);
-                t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
+            for (int j = 0; j < 8; j++) {
+                wv[j] = __ldg(g.wakefn + min(max(base + j, 0), wtop));  // clamped entries belong to rows outside the grid
+                acc[j] = 0.0;
+            }
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const double rh = rp[k];
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = __fma_rn(rh, wv[j], acc[j]);
+#pragma unroll
+                for (int j = 7; j > 0; j--) wv[j] = wv[j - 1];
+                wv[0] = __ldg(g.wakefn + min(max(base - k - 1, 0), wtop));
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int j = 0; j < 8; j++) {
+                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+            }
+            if (sub == 0) {
 #pragma unroll
-                for (int k = 0; k < 5; k++) w5[j][k] = t[j * 5 + k];
+                for (int j = 0; j < 8; j++)
+                    if (r0 + j < RIN) partial[(size_t)warp * sa.max_rin + r0 + j] = acc[j];
+            }
         }
-        const float4 ws4 = __ldg(reinterpret_cast<const float4*>(g.ws) + q);
-        float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + q;
-        const uint32_t pitch4 = pitch >> 2;
-        const float4* ring4 = reinterpret_cast<const float4*>(ring + kPad) + q;
-
-        // the first output needs input rows 0..H kicked; afterwards one new row per output
-        for (uint32_t r = 0; r < H; r++) mbar_wait(&kicked[r & kmask], (r >> klog) & 1);
-        for (uint32_t i = 0; i < S; i++) {
-            {
-                const uint32_t r = i + H;
-                mbar_wait(&kicked[r & kmask], (r >> klog) & 1);
+        __syncthreads();
+    }
+    {
+        const float scal = g.has_wake ? g.wakescaling[member] : 0.0f;
+        for (uint32_t r = tid; r < RIN; r += T) {
+            const int x = xs + (int)r;
+            const bool valid = (uint32_t)x < n;
+            // no wake map: the identity as a 4-tap row (0, 1, 0, 0) at first = -1
+            ivs_taps t;
+            t.first = -1;
+            t.w[0] = 0.0f; t.w[1] = 1.0f; t.w[2] = 0.0f; t.w[3] = 0.0f;
+            if (valid && g.has_wake) {
+                double acc = 0.0;
+                for (uint32_t k = 0; k < NW; k++) acc += partial[(size_t)k * sa.max_rin + r];
+                const float wk = __fmul_rn(scal, (float)acc);  // src/PS/ElectricField.cpp:236-241
+                t = ivs_kick_taps(wk, n, g.it);
+                if (t.first < -16 || t.first > 8) {  // beyond the staged pad: flag, neutralise
+                    atomicExch(g.status, 1);
+                    t.first = -1;
+                    t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.0f;
+                }
+                if (r >= hl && r < hl + S) g.wake_out[(size_t)member * n + x] = wk;
             }
-            // ---- drift (src/SM/KickMap.cpp:221-242): column-local 4-tap along x
+            const int f2 = valid ? __ldg(&g.rf_first[x]) : -1;
+            tab_w1[r] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+            tab_w2[r] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);
+            tab_f[r] = make_int2(t.first + f2, f2);
+        }
+    }
+
+    // ---- per-thread constants: drift taps, Fokker-Planck and Simpson weights of the 4 columns
+    const uint32_t q = tid;  // this thread's quad of columns, y = 4q .. 4q+3
+    const uint32_t y = q << 2;
+    const int4 df = __ldg(reinterpret_cast<const int4*>(g.dr_first) + q);
+    const int fmin = min(min(df.x, df.y), min(df.z, df.w));
+    const bool tmixed = (df.x != fmin) || (df.y != fmin) || (df.z != fmin) || (df.w != fmin);  // some first == fmin+1
+    const bool wmixed = __any_sync(0xffffffffu, tmixed);
+    float w5[4][5];
+    {
+        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)y * 5);
+        float t[20];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float4 v = __ldg(wp + k);
+            t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) w5[j][k] = t[j * 5 + k];
+    }
+    const float4 ws4 = __ldg(reinterpret_cast<const float4*>(g.ws) + q);
+    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + q;
+
+    const uint32_t ring_q = smem_u32(ring + kPadS) + q * 16;  // this quad in slot 0
+    const uint32_t ring_end = ring_q + K * pitchB;
+    const uint32_t scr_q = smem_u32(scratch + kPadS) + q * 16;
+    const uint32_t tw1_b = smem_u32(tab_w1), tw2_b = smem_u32(tab_w2), tf_b = smem_u32(tab_f);
+
+    // thread 0: the rows the priming and the first output read (0 .. H+1) have to be complete
+    uint32_t wrow = 0;  // next row whose copy has not been waited for
+    if (tid == 0) {
+        for (; wrow < min(H + 2, RIN); wrow++) {
+            if ((uint32_t)(xs + (int)wrow) >= n) continue;
+            uint32_t bar, ph;
+            row_bar(wrow, bar, ph);
+            mbar_wait_addr(bar, ph);
+        }
+    }
+    __syncthreads();  // tables, pads and staged rows visible to everybody
+
+    // ---- the row loop.  MIXED: the first drift tap differs inside some quad of this warp, so the
+    // window holds 5 rows and every column has 5 weights, one of them 0 (x*0 adds nothing).
+    auto run = [&](auto mixed_tag) {
+        constexpr bool MIXED = decltype(mixed_tag)::value;
+        constexpr int NT = MIXED ? 5 : 4;
+        float dw[4][NT];
+        {
+            const int fs[4] = {df.x, df.y, df.z, df.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float4 w = __ldg(&g.dr_w[y + c]);
+                if (MIXED) {
+                    const bool s = fs[c] != fmin;
+                    dw[c][0] = s ? 0.0f : w.x;
+                    dw[c][1] = s ? w.x : w.y;
+                    dw[c][2] = s ? w.y : w.z;
+                    dw[c][3] = s ? w.z : w.w;
+                    dw[c][NT - 1] = s ? w.w : 0.0f;
+                } else {
+                    dw[c][0] = w.x; dw[c][1] = w.y; dw[c][2] = w.z; dw[c][3] = w.w;
+                }
+            }
+        }
+        // the next input row this thread kicks, its slot address
+        uint32_t r = (uint32_t)((int)hl + fmin);
+        uint32_t aload = ring_q + (r % K) * pitchB;
+        float4 A0 = make_float4(0, 0, 0, 0), A1 = A0, A2 = A0, A3 = A0, A4 = A0;
+        auto kick_row = [&]() -> float4 {
+            float4 k = make_float4(0, 0, 0, 0);
+            if ((uint32_t)(xs + (int)r) < n) {
+                int f_sum, f_2;
+                asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(f_sum), "=r"(f_2) : "r"(tf_b + r * 8));
+                const float4 w1 = lds128(tw1_b + r * 16), w2 = lds128(tw2_b + r * 16);
+                k = kick_quad<FMA>(aload, f_sum, (int)y + f_2, n, w1, w2);
+            }
+            r++;
+            aload += pitchB;
+            if (aload == ring_end) aload = ring_q;
+            return k;
+        };
+        auto push = [&](const float4 k) {
+            A0 = A1; A1 = A2; A2 = A3;
+            if (MIXED) { A3 = tmixed ? A4 : k; A4 = k; }
+            else A3 = k;
+        };
+        auto drift = [&]() -> float4 {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
             float4 d;
-            if (uniform) {
-                const uint32_t rb = i + hl + (uint32_t)df.x;  // >= i by construction of hl
-                const float4 A0 = ring4[(size_t)((rb) & kmask) * pitch4];
-                const float4 A1 = ring4[(size_t)((rb + 1) & kmask) * pitch4];
-                const float4 A2 = ring4[(size_t)((rb + 2) & kmask) * pitch4];
-                const float4 A3 = ring4[(size_t)((rb + 3) & kmask) * pitch4];
-                d.x = tap4<FMA>(A0.x, A1.x, A2.x, A3.x, dw0);
-                d.y = tap4<FMA>(A0.y, A1.y, A2.y, A3.y, dw1);
-                d.z = tap4<FMA>(A0.z, A1.z, A2.z, A3.z, dw2);
-                d.w = tap4<FMA>(A0.w, A1.w, A2.w, A3.w, dw3);
-            } else {
-                const float* ringc = ring + kPad + y;
-                const int fs[4] = {df.x, df.y, df.z, df.w};
-                const float4 dws[4] = {dw0, dw1, dw2, dw3};
+            float v;
+#define IVS_DRIFT_COL(c, m)                                                     \
+            v = __fmul_rn(A0.m, dw[c][0]);                                      \
+            v = madd<FMA>(A1.m, dw[c][1], v);                                   \
+            v = madd<FMA>(A2.m, dw[c][2], v);                                   \
+            v = madd<FMA>(A3.m, dw[c][3], v);                                   \
+            if (MIXED) v = madd<FMA>(A4.m, dw[c][NT - 1], v);                   \
+            d.m = v;
+            IVS_DRIFT_COL(0, x)
+            IVS_DRIFT_COL(1, y)
+            IVS_DRIFT_COL(2, z)
+            IVS_DRIFT_COL(3, w)
+#undef IVS_DRIFT_COL
+            return d;
+        };
+        // priming: the first window
+        {
+            const int np = (MIXED && tmixed) ? 5 : 4;
+            for (int k = 0; k < np; k++) push(kick_row());
+        }
+        float4 d = drift();
+        sts128(scr_q, d);
+
+        uint32_t pending = 1, pbar = 0, pph = 0;  // thread 0: outcome of the early probe of row `wrow`
+        for (uint32_t i = 0; i < S; i++) {
+            if (tid == 0 && !pending) mbar_wait_addr(pbar, pph);
+            __syncwarp();  // bar.sync is warp-aligned: lane 0 rejoins its warp first
+            named_bar_sync(1, T);
+            if (tid == 0) {
+                // everybody is past reading input rows < i + dead_off: re-arm their slots
+                issue_rows(min(RIN, K + i + sa.dead_off));
+                // the rows read after the next barrier: probe now, block (if at all) just before it
+                pending = 1;
+                if (wrow < RIN && wrow <= i + 2 + H) {
+                    if ((uint32_t)(xs + (int)wrow) < n) {
+                        row_bar(wrow, pbar, pph);
+                        pending = mbar_test(pbar, pph);
+                    }
+                    wrow++;
+                }
+            }
+            const uint32_t srow = scr_q + (i & 1) * pitchB;
+            const float4 L = lds128(srow - 16), R = lds128(srow + 16);
+            float4 knew = make_float4(0, 0, 0, 0);
+            const bool more = i + 1 < S;
+            if (more) knew = kick_row();
+            // ---- Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211), store, projection partial
+            {
+                const float in[8] = {L.z, L.w, d.x, d.y, d.z, d.w, R.x, R.y};
                 float o[4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const uint32_t rb = i + hl + (uint32_t)fs[c];
-                    const float a0 = ringc[(size_t)((rb) & kmask) * pitch + c];
-                    const float a1 = ringc[(size_t)((rb + 1) & kmask) * pitch + c];
-                    const float a2 = ringc[(size_t)((rb + 2) & kmask) * pitch + c];
-                    const float a3 = ringc[(size_t)((rb + 3) & kmask) * pitch + c];
-                    o[c] = tap4<FMA>(a0, a1, a2, a3, dws[c]);
+                for (int j = 0; j < 4; j++) {
+                    float v = __fmul_rn(in[j], w5[j][0]);
+                    v = madd<FMA>(in[1 + j], w5[j][1], v);
+                    v = madd<FMA>(in[2 + j], w5[j][2], v);
+                    v = madd<FMA>(in[3 + j], w5[j][3], v);
+                    v = madd<FMA>(in[4 + j], w5[j][4], v);
+                    o[j] = v;
                 }
-                d = make_float4(o[0], o[1], o[2], o[3]);
-            }
-            float* srow = scratch + (size_t)(i & 1) * pitch + kPad;
-            reinterpret_cast<float4*>(srow)[q] = d;
-            named_bar_sync(1, ndf_threads);
-            // input row i is not needed any more: hand its slot back to the producer
-            if (tid == 0) mbar_arrive(&freeb[i & kmask]);
-            // ---- Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211), store, projection partial
-            const float4* s4 = reinterpret_cast<const float4*>(srow) + q;
-            const float4 A = s4[-1], B = s4[0], C = s4[1];
-            const float in[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
-            float o[4];
+                *gout = make_float4(o[0], o[1], o[2], o[3]);
+                gout += nq;
+                float p = __fmul_rn(o[0], ws4.x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
+                p = __fadd_rn(p, __fmul_rn(o[1], ws4.y));
+                p = __fadd_rn(p, __fmul_rn(o[2], ws4.z));
+                p = __fadd_rn(p, __fmul_rn(o[3], ws4.w));
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float v = __fmul_rn(in[2 + j], w5[j][0]);
-                v = madd<FMA>(in[3 + j], w5[j][1], v);
-                v = madd<FMA>(in[4 + j], w5[j][2], v);
-                v = madd<FMA>(in[5 + j], w5[j][3], v);
-                v = madd<FMA>(in[6 + j], w5[j][4], v);
-                o[j] = v;
+                for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
+                if (lane == 0) red[i * NW + warp] = p;
             }
-            gout[(size_t)i * nq] = make_float4(o[0], o[1], o[2], o[3]);
-            float p = __fmul_rn(o[0], ws4.x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
-            p = __fadd_rn(p, __fmul_rn(o[1], ws4.y));
-            p = __fadd_rn(p, __fmul_rn(o[2], ws4.z));
-            p = __fadd_rn(p, __fmul_rn(o[3], ws4.w));
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
-            if (lane == 0) red[(i & 1) * 32 + warp] = p;
-            // the previous row's warp partials are complete (they were written before this
-            // row's barrier): one thread adds them in fixed order
-            if (tid == 32 % ndf_threads && i > 0) {
-                float v = 0.0f;
-                for (uint32_t k = 0; k < sa.ndf; k++) v = __fadd_rn(v, red[((i - 1) & 1) * 32 + k]);
-                g.rho_out[(size_t)member * n + xa + i - 1] = v;
+            if (more) {
+                push(knew);
+                d = drift();
+                sts128(scr_q + ((i + 1) & 1) * pitchB, d);
             }
         }
-        named_bar_sync(1, ndf_threads);
-        if (tid == 0) {
-            float v = 0.0f;
-            for (uint32_t k = 0; k < sa.ndf; k++) v = __fadd_rn(v, red[((S - 1) & 1) * 32 + k]);
-            g.rho_out[(size_t)member * n + xa + S - 1] = v;
-        }
-    } else {
-        if (REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == sa.ndf) {
-            // =============================== producer warp ====================================
-            for (uint32_t r = 0; r < RIN; r++) {
-                const uint32_t s = r & kmask;
-                if (r >= K) mbar_wait(&freeb[s], ((r >> klog) - 1) & 1);
-                const int x = xs + (int)r;
-                float* dst = ring + (size_t)s * pitch + kPad;
-                if ((uint32_t)x < n) {
-                    if (lane == 0) {
-                        fence_proxy_async();  // earlier generic-proxy accesses to the slot are done
-                        mbar_expect_tx(&full[s], n * (uint32_t)sizeof(float));
-                        bulk_g2s(dst, gin + (size_t)x * n, n * sizeof(float), &full[s]);
-                    }
-                } else {
-                    // row outside the grid: zeros ("taps outside the grid are dropped")
-                    for (uint32_t i = lane; i < nq; i += 32) reinterpret_cast<float4*>(dst)[i] = make_float4(0, 0, 0, 0);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[s]);
-                }
-                __syncwarp();
-            }
-        } else {
-            // =============================== kick warps =======================================
-            const uint32_t kw = warp - sa.ndf - 1;
-            const float scal = g.has_wake ? g.wakescaling[member] : 0.0f;
-            for (uint32_t r = kw; r < RIN; r += sa.nkick) {
-                const uint32_t s = r & kmask;
-                const int x = xs + (int)r;
-                int wfirst = -1;
-                float4 wwt = make_float4(0, 0, 0, 0);
-                if ((uint32_t)x < n && g.has_wake) {
-                    // wake potential of row x while its copy is still in flight
-                    const double* wf = g.wakefn + (x + (int)n - 1) - (int)lane;
-                    const double* rl = rho + lane;
-                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 4
-                    for (uint32_t j = 0; j < n; j += 128) {
-                        a0 = __fma_rn(rl[j], __ldg(wf - (int)j), a0);
-                        a1 = __fma_rn(rl[j + 32], __ldg(wf - (int)j - 32), a1);
-                        a2 = __fma_rn(rl[j + 64], __ldg(wf - (int)j - 64), a2);
-                        a3 = __fma_rn(rl[j + 96], __ldg(wf - (int)j - 96), a3);
-                    }
-                    double acc = (a0 + a1) + (a2 + a3);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    const float wk = __fmul_rn(scal, (float)acc);  // src/PS/ElectricField.cpp:236-241
-                    ivs_taps t = ivs_kick_taps(wk, n, g.it);
-                    if (t.first < -kPad || t.first > kPad - 4) {
-                        if (lane == 0) atomicExch(g.status, 1);
-                        t.first = -1;
-                        t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.0f;
-                    }
-                    wfirst = t.first;
-                    wwt = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
-                    if (lane == 0 && r >= hl && r < hl + S) g.wake_out[(size_t)member * n + x] = wk;
-                }
-                mbar_wait(&full[s], (r >> klog) & 1);
-                if ((uint32_t)x < n) {
-                    float* row = ring + (size_t)s * pitch + kPad;
-                    if (g.has_wake) row_pass_v4<FMA>(row, nq, wfirst, wwt, lane);
-                    row_pass_v4<FMA>(row, nq, __ldg(&g.rf_first[x]), __ldg(&g.rf_w[x]), lane);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&kicked[s]);
-            }
-        }
+    };
+    if (wmixed) run(std::true_type{});
+    else run(std::false_type{});
+
+    // the strip's row sums: one thread per row adds the warp partials in fixed order
+    __syncthreads();
+    for (uint32_t i = tid; i < S; i += T) {
+        float v = 0.0f;
+        for (uint32_t k = 0; k < NW; k++) v = __fadd_rn(v, red[i * NW + k]);
+        g.rho_out[(size_t)member * n + xa + i] = v;
     }
 }
 
@@ -862,36 +1044,63 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
     plan->halo_lo = std::max(plan->halo_lo, 1u);
     plan->halo_hi = std::max(plan->halo_hi, 2u);
     plan->pad_y = kPad;
-    // ---- streaming pipeline (default for grid sizes 256/512/1024/2048)
+    // ---- streaming kernel (default for grid sizes that are multiples of 256, up to 2048)
     plan->stream = false;
-    if (n % 256 == 0 && n <= 2048 && !(s->desc.flags & IVS_SIM_TILED)) {
+    bool quads_ok = true;  // a thread's 4 columns may start their drift taps on at most 2 adjacent rows
+    for (uint32_t i = 0; i + 3 < n && quads_ok; i += 4) {
+        const int lo = std::min(std::min(dr_first[i], dr_first[i + 1]), std::min(dr_first[i + 2], dr_first[i + 3]));
+        const int hi = std::max(std::max(dr_first[i], dr_first[i + 1]), std::max(dr_first[i + 2], dr_first[i + 3]));
+        quads_ok = hi - lo <= 1;
+    }
+    if (n % 256 == 0 && n <= 2048 && quads_ok && !(s->desc.flags & IVS_SIM_TILED)) {
         const uint32_t H = plan->halo_lo + plan->halo_hi;
-        const uint32_t ndf = n / 128;
-        const uint32_t warps = (ndf >= 16) ? 32 : std::max<uint32_t>(8, 2 * ndf);
-        const uint32_t threads_s = warps * 32;
-        uint32_t K = 16;
-        while (K < H + 4) K <<= 1;
-        const uint32_t pitch = n + 2 * kPad;
-        const size_t sb = (size_t)(K + 2) * pitch * 4 + (size_t)n * 8 + (size_t)3 * K * 8 + 2 * 32 * 4;
-        if (sb <= 227 * 1024) {
-            const uint32_t per_sm = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(227 * 1024 / (sb + 1024)), 1024 / threads_s));
-            // strips per member: minimise rounds x (rows through the pipeline per CTA)
+        const uint32_t threads_s = n / 4, NW = n / 128;
+        const uint32_t pitch = n + 2 * kPadS;
+        // after the barrier of output row i nobody reads input rows below i + dead_off any more
+        const int dfirst_min = *std::min_element(dr_first.begin(), dr_first.end());
+        const uint32_t dead_off = (uint32_t)(4 + (int)plan->halo_lo + dfirst_min);
+        const uint32_t live = H + 2 - dead_off;  // rows that have to sit in the ring at the same time
+        const uint32_t max_strip = std::min<uint32_t>(n, (n >= 2048) ? 64 : 128);
+        const uint32_t max_rin = max_strip + H;
+        auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+        const size_t fixed = a16((size_t)2 * pitch * 4) + a16((size_t)(n + n / 32) * 8) + a16((size_t)NW * max_rin * 8) +
+                             a16((size_t)max_strip * NW * 4) + 2 * a16((size_t)max_rin * 16) + a16((size_t)max_rin * 8);
+        cudaFuncAttributes fa;
+        IVS_CUDA(ctx, cudaFuncGetAttributes(&fa, ctx->arith == IVS_ARITH_FMA ? stream_step_kernel<true> : stream_step_kernel<false>));
+        const uint32_t by_regs = std::max<uint32_t>(1, 65536u / (std::max(fa.numRegs, 32) * threads_s));
+        uint32_t want = std::min<uint32_t>(by_regs, 16);  // CTAs per SM the registers allow
+        uint32_t K = 0;
+        size_t sb = 0;
+        for (; want >= 1; want--) {
+            const size_t budget = (size_t)227 * 1024 / want - 1024;  // 1 KB per CTA is reserved by the system
+            const uint32_t kmin = std::max(live + 3, H + 3);  // the set-up waits for rows 0 .. H+1
+            if (budget < fixed + (size_t)kmin * (pitch * 4 + 8)) continue;
+            K = (uint32_t)std::min<size_t>(std::max(live + 12, kmin), (budget - fixed) / ((size_t)pitch * 4 + 8));
+            sb = a16((size_t)K * pitch * 4) + fixed + a16((size_t)K * 8);
+            if (sb <= budget) break;
+            K = 0;
+        }
+        if (K >= live + 3 && K >= H + 3) {
+            const uint32_t per_sm = want;
+            // strips per member: minimise rounds x (rows through the pipeline per CTA + set-up)
             uint64_t best = ~0ull;
             uint32_t bestP = 1;
             for (uint32_t P = 1; P <= n / 8; P++) {
                 const uint32_t S0 = ivs_div_up(n, P);
                 if ((uint64_t)S0 * (P - 1) >= n) continue;  // last strip would be empty
+                if (S0 > max_strip) continue;
                 const uint64_t units = (uint64_t)P * s->members;
                 const uint64_t slots = (uint64_t)ctx->sm_count * per_sm;
                 const uint64_t rounds = (units + slots - 1) / slots;
-                const uint64_t cost = rounds * (S0 + H + 10);
+                const uint64_t cost = rounds * (S0 + H + 6);
                 if (cost < best) { best = cost; bestP = P; }
             }
             plan->stream = true;
             plan->strip = ivs_div_up(n, bestP);
             plan->kslots = K;
-            plan->ndf = ndf;
-            plan->nkick = warps - ndf - 1;
+            plan->dead_off = dead_off;
+            plan->max_strip = max_strip;
+            plan->max_rin = max_rin;
             plan->threads = threads_s;
             plan->smem = sb;
             plan->tx = 0;
@@ -938,10 +1147,8 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         return st;
     // opt in to the large dynamic shared memory once (not per launch)
     if (plan->stream) {
-        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
         plan->ready = true;
         return IVS_OK;
     }
@@ -986,14 +1193,12 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
     if (plan->stream) {
         stream_args sa;
         sa.f = a;
-        sa.strip = plan->strip; sa.kslots = plan->kslots; sa.ndf = plan->ndf; sa.nkick = plan->nkick;
+        sa.f.pitch = s->n + 2 * kPadS;
+        sa.strip = plan->strip; sa.kslots = plan->kslots; sa.dead_off = plan->dead_off;
+        sa.max_strip = plan->max_strip; sa.max_rin = plan->max_rin;
         const dim3 sgrid(ivs_div_up(s->n, plan->strip), s->members);
-        const bool fma = ctx->arith == IVS_ARITH_FMA;
-        const bool reb = false;  // setmaxnreg rebalancing: ptxas keeps the 64-register allocation, not used yet
-        if (fma && reb) stream_step_kernel<true, true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
-        else if (fma) stream_step_kernel<true, false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
-        else if (reb) stream_step_kernel<false, true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
-        else stream_step_kernel<false, false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+        if (ctx->arith == IVS_ARITH_FMA) stream_step_kernel<true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+        else stream_step_kernel<false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
         IVS_LAUNCHED(ctx);
         st = IVS_OK;
         goto launched;

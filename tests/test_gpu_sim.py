@@ -110,7 +110,7 @@ def test_fused_equals_unfused_bit_for_bit(capi, ctx_strict, ctx_fma, mode, case)
             assert np.array_equal(ga, gb)
         else:
             assert rel_l1(ga, gb) < 3e-6  # wake offsets differ in the last bits: a few rows re-quantise
-            assert np.abs(wa - wb).max() <= 6e-6 * max(np.abs(wb).max(), 1e-30)  # fp32 FFT vs double Toeplitz
+            assert np.abs(wa - wb).max() <= 2e-5 * max(np.abs(wb).max(), 1e-30)  # fp32 FFT (offsets feed back) vs double Toeplitz
         assert np.allclose(pa, pb, rtol=1e-5, atol=1e-9)
 
 
