@@ -23,6 +23,7 @@
 // Every tap accumulation is madd<FMA>() in the reference's order, so the result is bit-identical
 // to the unfused kernel sequence (ivs_maps.cu) -- tested.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -520,42 +521,46 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
 
 // ------------------------------------------------------------------------------------------
 // Streaming variant (grid sizes that are multiples of 256, up to 2048): a CTA owns a strip of
-// consecutive rows of one member; its n/4 threads each own 4 adjacent columns (one float4) for
-// the whole strip and march down the rows:
+// consecutive rows of one member and streams them through a ring of row slots in shared memory.
+// A thread owns ONE quad of columns (a float4) for the whole strip, a warp 128 adjacent columns;
+// the n/128 warps of a CTA run independently of each other -- no block-wide barrier in the row loop:
 //
-//   TMA engine   : one bulk copy per input row into a ring of row slots, issued by thread 0 a
-//                  ring depth ahead (completion on one mbarrier per slot);
-//   kick         : a thread reads the 10..13 staged values its quad depends on (3-4 LDS.128) and
-//                  applies wake kick and RF kick back to back in registers -- the 7 wake-kicked
-//                  values the RF taps need are recomputed per thread instead of being exchanged,
-//                  so the row-local passes cost no shared-memory round trip and no barrier;
-//   drift        : column-local, so it is a sliding window of kicked rows in registers (4 rows, 5
-//                  where the first drift tap changes inside the quad);
-//   Fokker-Planck: needs 2 neighbours left and right: the drifted quad goes through a
-//                  double-buffered scratch row, ONE block barrier per output row, then the stencil,
-//                  STG.128 and the Simpson-weighted row sum (next step's profile).
+//   staging : one TMA bulk copy per input row into the next free slot.  full[slot] completes when
+//             the bytes have landed, empty[slot] counts the warps that are done with the row that
+//             was there.  There is no producer warp (it would unbalance the four schedulers): the
+//             duty rotates, row r is issued by lane 0 of warp r mod n_warps when its probe of
+//             empty[slot] (started a row earlier) says the slot is free.
+//   kick    : all lanes of a warp work on the same input row; a lane reads the 10..13 staged values
+//             its quad depends on (3-4 LDS.128) and applies wake kick and RF kick back to back in
+//             registers -- the 7 wake-kicked values the RF taps need are recomputed per lane instead
+//             of being exchanged, so the row-local passes cost no shared-memory round trip;
+//   drift   : column-local, a sliding window of kicked rows in registers.  The window holds
+//             NT = 4 + spread rows, spread = how far the first drift tap varies over the warp's 128
+//             columns; a column's 4 weights sit at its offset, the other slots hold 0;
+//   Fokker-Planck: needs 2 neighbours left and right: warp shuffles inside the warp; across a
+//             warp boundary the two edge lanes post their values in a small mailbox (sequence
+//             number = row) that the neighbour warp's edge lane polls.  The stencil runs two rows
+//             behind the drift, so a warp only waits if its neighbour is more than a row late.
+//   then STG.128 and the Simpson-weighted partial row sum (next step's profile).
 //
-// The barrier of row i also proves that nobody reads the oldest ring slot any more, so thread 0
-// re-arms it right after.  The wake potential of the strip's rows (Toeplitz product in double)
-// is formed by the whole CTA while the first copies are in flight.  Arithmetic per cell is
-// identical to the tile kernels (same taps, same order) -- tested bit for bit.
+// The wake potential of the strip's rows (Toeplitz product in double) is formed by the whole CTA
+// while the first copies are in flight.  Arithmetic per cell is identical to the tile kernels
+// (same taps, same order, same summation tree of the profile).
 
-constexpr int kPadS = 32;  // zero columns each side of a staged row: two kicks of up to 16 cells
+constexpr int kPadS = 32;     // zero columns each side of a staged row: two kicks of up to 16 cells
+constexpr int kMailSlots = 32; // mailbox depth per warp edge (> ring slots + 6, see the hand-back rule)
 
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 struct stream_args {
     fused_args f;
-    uint32_t strip;     // rows per strip
-    uint32_t kslots;    // ring slots
-    uint32_t dead_off;  // after the barrier of output row i, input rows < i + dead_off are dead
-    uint32_t max_strip; // capacity of the partial-sum table (rows)
-    uint32_t max_rin;   // capacity of the per-row tap tables (input rows)
+    uint32_t strip;      // rows per strip
+    uint32_t kslots;     // ring slots
+    uint32_t max_strip;  // capacity of the partial-sum table (rows)
+    uint32_t max_rin;    // capacity of the per-row tap tables (input rows)
+    uint32_t wwin_len;   // doubles in the staged wake-function window
 };
 
 // shared-memory accessors on 32-bit shared addresses (no 64-bit generic pointer arithmetic)
@@ -564,8 +569,22 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ float4 lds128_volatile(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128_volatile(uint32_t addr, const float4 v) {
+    asm volatile("st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ int2 lds64i(uint32_t addr) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
 }
 // non-blocking probe of an mbarrier phase
 __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t phase) {
@@ -577,23 +596,24 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t phase) {
         : "memory");
     return ok;
 }
-// blocking wait; a copy that never lands (a bug, not a load condition) traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t phase) {
-    uint32_t ok, tries = 0;
-    do {
-        asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-            : "=r"(ok)
-            : "r"(bar), "r"(phase)
-            : "memory");
-        if (!ok && ++tries > (1u << 24)) __trap();
-    } while (!ok);
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(bar), "r"(phase)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // wake kick then RF kick of one quad of columns (y0 .. y0+3) of a staged row, in registers.
-//   k1[m] = sum_j in[m + f1 + j] w1[j]         wake kick (src/SM/KickMap.cpp:243-266), 0 outside the grid
-//   out[y] = sum_j k1[y + f2 + j] w2[j]        RF kick, same loop
-// `p` is the shared address of in[y0 + a], a = (f1+f2) rounded down to a multiple of 4, RR the rest.
+//   k1[m] = sum_t in[m + f1 + t] w1[t]         wake kick (src/SM/KickMap.cpp:243-266), 0 outside the grid
+//   out[y] = sum_t k1[y + f2 + t] w2[t]        RF kick, same loop
+// `p` is the shared address of in[y0 + a], a = (f1+f2) rounded down to a multiple of 4, RR the rest;
+// m0 = y0 + f2 is the first wake-kicked column the quad needs.
 template <bool FMA, int RR>
 __device__ __forceinline__ float4 kick_quad_rr(uint32_t p, int m0, uint32_t n, const float4 w1, const float4 w2) {
     float in[16];
@@ -634,6 +654,10 @@ __device__ __forceinline__ float4 kick_quad(uint32_t row_q, int fsum, int m0, ui
     }
 }
 
+// staged wake-function window: one pad double after every 8 keeps lanes that are 8 entries apart
+// on different banks
+__device__ __forceinline__ uint32_t wwin_pos(uint32_t t) { return t + (t >> 3); }
+
 template <bool FMA>
 __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args sa) {
     const fused_args& g = sa.f;
@@ -641,7 +665,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     const uint32_t n = g.n, nq = g.n >> 2, pitch = g.pitch, hl = g.hl;
     const uint32_t H = g.hl + g.hr;
     const uint32_t K = sa.kslots;
-    const uint32_t T = blockDim.x;  // == nq
+    const uint32_t T = blockDim.x;             // == nq: one quad of columns per thread
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
     const uint32_t member = blockIdx.y;
     const uint32_t xa = blockIdx.x * sa.strip;
@@ -657,84 +681,113 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         return p;
     };
     float* ring = reinterpret_cast<float*>(carve((size_t)K * pitch * 4));        // K row slots
-    float* scratch = reinterpret_cast<float*>(carve((size_t)2 * pitch * 4));     // 2 drifted rows
     double* rho = reinterpret_cast<double*>(carve((size_t)(n + (n >> 5)) * 8));  // last step's profile (skewed)
+    double* wwin = reinterpret_cast<double*>(carve((size_t)sa.wwin_len * 8));    // wake function window
     double* partial = reinterpret_cast<double*>(carve((size_t)NW * sa.max_rin * 8));  // wake partial sums
-    float* red = reinterpret_cast<float*>(carve((size_t)sa.max_strip * NW * 4)); // row-sum partials
-    float4* tab_w1 = reinterpret_cast<float4*>(carve((size_t)sa.max_rin * 16));  // wake taps per input row
-    float4* tab_w2 = reinterpret_cast<float4*>(carve((size_t)sa.max_rin * 16));  // RF taps per input row
-    int2* tab_f = reinterpret_cast<int2*>(carve((size_t)sa.max_rin * 8));        // (f1 + f2, f2)
+    float* red = reinterpret_cast<float*>(carve((size_t)sa.max_strip * NW * 4));       // row-sum partials
+    float4* tab_w1 = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 16));  // wake taps per input row
+    float4* tab_w2 = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 16));  // RF taps per input row
+    int2* tab_f = reinterpret_cast<int2*>(carve((size_t)(sa.max_rin + 1) * 8));        // (f1 + f2, f2)
+    float4* mail = reinterpret_cast<float4*>(carve((size_t)NW * 2 * kMailSlots * 16)); // [warp][side][slot] = (a, b, seq, -)
     uint64_t* full = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
+    uint64_t* empty = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
 
     const float* gin = g.in + (size_t)member * n * n;
     const uint32_t pitchB = pitch * 4;
-    const uint32_t full_b = smem_u32(full);
+    const uint32_t full_b = smem_u32(full), empty_b = smem_u32(empty);
 
-    // ---- thread 0 drives the TMA engine: row r lives in slot r % K, phase (r / K) & 1
-    uint32_t top = 0;  // rows issued so far
-    auto issue_rows = [&](uint32_t limit) {  // thread 0 only
-        for (; top < limit; top++) {
-            const int x = xs + (int)top;
-            const uint32_t slot = top % K;
-            if ((uint32_t)x >= n) {
-                // rows outside the grid are never staged (readers substitute zeros); the slot's
-                // barrier still moves on one phase so that phase == (row / K) & 1 holds for every row
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_b + slot * 8) : "memory");
-                continue;
-            }
-            fence_proxy_async();  // earlier generic-proxy reads of the slot are ordered before the async write
+    // one staged row: copy it, or (outside the grid, where the RF taps are 0) complete the phase by hand
+    auto issue_row = [&](uint32_t r, uint32_t slot) {
+        const int x = xs + (int)r;
+        if ((uint32_t)x < n) {
+            fence_proxy_async();  // generic-proxy reads of the slot are ordered before the async write
             mbar_expect_tx(&full[slot], n * (uint32_t)sizeof(float));
             bulk_g2s(ring + (size_t)slot * pitch + kPadS, gin + (size_t)x * n, n * (uint32_t)sizeof(float), &full[slot]);
+        } else {
+            mbar_arrive_addr(full_b + slot * 8);
         }
-    };
-    auto row_bar = [&](uint32_t r, uint32_t& bar, uint32_t& phase) {
-        const uint32_t use = r / K;
-        bar = full_b + (r - use * K) * 8;
-        phase = use & 1;
     };
 
     if (tid == 0) {
-        for (uint32_t s = 0; s < K; s++) mbar_init(&full[s], 1);
+        for (uint32_t s = 0; s < K; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
     }
+    // ---- per-thread constants, requested early: drift taps, Fokker-Planck and Simpson weights
+    const uint32_t q = tid;  // this thread's quad of columns, y = 4q .. 4q+3
+    const int4 df = __ldg(reinterpret_cast<const int4*>(g.dr_first) + q);
+    float4 dwl[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) dwl[c] = __ldg(&g.dr_w[4 * q + c]);
+    float w5[4][5];
+    {
+        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)q * 20);
+        float t[20];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float4 v = __ldg(wp + k);
+            t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) w5[c][k] = t[c * 5 + k];
+    }
+    const float4 ws4 = __ldg(reinterpret_cast<const float4*>(g.ws) + q);
     __syncthreads();
-    if (tid == 0) issue_rows(min(K, RIN));
+    if (tid == 0) {
+        for (uint32_t r = 0; r < min(K, RIN); r++) issue_row(r, r);  // the first ring-full flies during the set-up
+    }
 
-    // ---- set-up by everybody: zero pads, RF taps, last step's profile in double
-    for (uint32_t r = warp; r < K + 2; r += NW) {
-        float* row = ring + (size_t)r * pitch;  // the two scratch rows follow the ring
+    // ---- set-up: zero pads (and slots of rows outside the grid, whose stale contents would
+    // otherwise meet the zero weights as NaN * 0), mailboxes, last step's profile and the
+    // wake-function window in shared memory
+    for (uint32_t r = warp; r < K; r += NW) {
+        float* row = ring + (size_t)r * pitch;
         row[lane] = 0.0f;
         row[n + kPadS + lane] = 0.0f;
+        if (r < RIN && (uint32_t)(xs + (int)r) >= n) {
+            for (uint32_t i = lane; i < nq; i += 32) reinterpret_cast<float4*>(row + kPadS)[i] = make_float4(0, 0, 0, 0);
+        }
     }
+    for (uint32_t i = tid; i < NW * 2 * kMailSlots; i += T) mail[i] = make_float4(0, 0, 0, 0);  // seq 0 = nothing posted
     if (g.has_wake) {
         const float* rin = g.rho_in + (size_t)member * n;
-        for (uint32_t i = tid; i < n; i += T) rho[i + (i >> 5)] = (double)rin[i];
-        __syncthreads();
+        for (uint32_t i = tid; i < n; i += T) rho[i + (i >> 5)] = (double)__ldg(rin + i);
+        // w[x - x'] is stored at table index x - x' + n - 1; window entry t holds the table
+        // entry xs + t, so row r and x' meet at t = r - x' + n - 1
+        const int wtop = (int)(2 * n - 1);
+        const uint32_t tcount = n + ((RIN + 63) & ~63u);
+        for (uint32_t t = tid; t < tcount; t += T)
+            wwin[wwin_pos(t)] = __ldg(g.wakefn + min(max(xs + (int)t, 0), wtop));  // clamped entries belong to rows outside the grid
+    }
+    __syncthreads();
+    if (g.has_wake) {
         // W[x] = scaling * sum_x' rho[x'] w[x-x']  (src/PS/ElectricField.cpp:186-253 as a Toeplitz
         // product).  Warp w sums x' in [128 w, 128 w + 128); a lane owns 8 consecutive rows and 32
-        // consecutive x', so the 8 wake-function values it needs slide through registers: one table
-        // load and one profile load per 8 multiply-adds.
+        // consecutive x', so the 8 wake-function values it needs slide through registers: one
+        // window load and one profile load per 8 multiply-adds.
         const uint32_t rbk = lane & 7, sub = lane >> 3;
         const uint32_t xb = warp * 128 + sub * 32;
         const double* rp = rho + xb + (xb >> 5);
-        const int wtop = (int)(2 * n - 1);
         for (uint32_t pass = 0; pass * 64 < RIN; pass++) {  // warp-uniform trip count
             const uint32_t r0 = pass * 64 + rbk * 8;
-            // w[x - x'] is stored at index x - x' + n - 1
-            const int base = xs + (int)r0 + (int)n - 1 - (int)xb;
+            const uint32_t t0 = r0 + n - 1 - xb;
             double wv[8], acc[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                wv[j] = __ldg(g.wakefn + min(max(base + j, 0), wtop));  // clamped entries belong to rows outside the grid
+                wv[j] = wwin[wwin_pos(t0 + j)];
                 acc[j] = 0.0;
             }
 #pragma unroll 8
-            for (int k = 0; k < 32; k++) {
+            for (uint32_t k = 0; k < 32; k++) {
                 const double rh = rp[k];
 #pragma unroll
                 for (int j = 0; j < 8; j++) acc[j] = __fma_rn(rh, wv[j], acc[j]);
 #pragma unroll
                 for (int j = 7; j > 0; j--) wv[j] = wv[j - 1];
-                wv[0] = __ldg(g.wakefn + min(max(base - k - 1, 0), wtop));
+                wv[0] = wwin[wwin_pos(max((int)(t0 - k) - 1, 0))];
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -747,8 +800,8 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
                     if (r0 + j < RIN) partial[(size_t)warp * sa.max_rin + r0 + j] = acc[j];
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
     {
         const float scal = g.has_wake ? g.wakescaling[member] : 0.0f;
         for (uint32_t r = tid; r < RIN; r += T) {
@@ -772,157 +825,169 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             }
             const int f2 = valid ? __ldg(&g.rf_first[x]) : -1;
             tab_w1[r] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
-            tab_w2[r] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);
+            tab_w2[r] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
             tab_f[r] = make_int2(t.first + f2, f2);
         }
+        if (tid == 0) tab_f[RIN] = make_int2(-2, -1);  // read ahead by the row loop, never used
     }
+    __syncthreads();  // tables, pads and mailboxes visible to everybody
 
-    // ---- per-thread constants: drift taps, Fokker-Planck and Simpson weights of the 4 columns
-    const uint32_t q = tid;  // this thread's quad of columns, y = 4q .. 4q+3
-    const uint32_t y = q << 2;
-    const int4 df = __ldg(reinterpret_cast<const int4*>(g.dr_first) + q);
-    const int fmin = min(min(df.x, df.y), min(df.z, df.w));
-    const bool tmixed = (df.x != fmin) || (df.y != fmin) || (df.z != fmin) || (df.w != fmin);  // some first == fmin+1
-    const bool wmixed = __any_sync(0xffffffffu, tmixed);
-    float w5[4][5];
-    {
-        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)y * 5);
-        float t[20];
+    // =============================== the row loop ==============================================
+    int wfmin = min(min(df.x, df.y), min(df.z, df.w)), wfmax = max(max(df.x, df.y), max(df.z, df.w));
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const float4 v = __ldg(wp + k);
-            t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int k = 0; k < 5; k++) w5[j][k] = t[j * 5 + k];
+    for (int o = 16; o > 0; o >>= 1) {
+        wfmin = min(wfmin, __shfl_xor_sync(0xffffffffu, wfmin, o));
+        wfmax = max(wfmax, __shfl_xor_sync(0xffffffffu, wfmax, o));
     }
-    const float4 ws4 = __ldg(reinterpret_cast<const float4*>(g.ws) + q);
-    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + q;
+    const int spread = wfmax - wfmin;  // <= 2 (checked when the plan was made)
 
     const uint32_t ring_q = smem_u32(ring + kPadS) + q * 16;  // this quad in slot 0
     const uint32_t ring_end = ring_q + K * pitchB;
-    const uint32_t scr_q = smem_u32(scratch + kPadS) + q * 16;
-    const uint32_t tw1_b = smem_u32(tab_w1), tw2_b = smem_u32(tab_w2), tf_b = smem_u32(tab_f);
+    const int y0 = (int)(q << 2);
+    float* redw = red + warp;  // row i's partial at redw[i * NW]
+    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + q;
+    // mailboxes: this warp posts the drifted x,y of its first quad (for the left neighbour) and
+    // the z,w of its last quad (for the right neighbour); lane 0 / lane 31 read the neighbours'
+    const uint32_t mail_b = smem_u32(mail);
+    const uint32_t post_l = mail_b + (warp * 2 + 0) * kMailSlots * 16;   // written by lane 0
+    const uint32_t post_r = mail_b + (warp * 2 + 1) * kMailSlots * 16;   // written by lane 31
+    const bool edge_l = lane == 0 && warp > 0, edge_r = lane == 31 && warp + 1 < NW;
+    // lane 0 reads the left neighbour's right post, lane 31 the right neighbour's left post
+    const uint32_t peek = edge_l ? mail_b + ((warp - 1) * 2 + 1) * kMailSlots * 16
+                                 : mail_b + ((warp + 1) * 2 + 0) * kMailSlots * 16;
 
-    // thread 0: the rows the priming and the first output read (0 .. H+1) have to be complete
-    uint32_t wrow = 0;  // next row whose copy has not been waited for
-    if (tid == 0) {
-        for (; wrow < min(H + 2, RIN); wrow++) {
-            if ((uint32_t)(xs + (int)wrow) >= n) continue;
-            uint32_t bar, ph;
-            row_bar(wrow, bar, ph);
-            mbar_wait_addr(bar, ph);
-        }
-    }
-    __syncthreads();  // tables, pads and staged rows visible to everybody
-
-    // ---- the row loop.  MIXED: the first drift tap differs inside some quad of this warp, so the
-    // window holds 5 rows and every column has 5 weights, one of them 0 (x*0 adds nothing).
-    auto run = [&](auto mixed_tag) {
-        constexpr bool MIXED = decltype(mixed_tag)::value;
-        constexpr int NT = MIXED ? 5 : 4;
+    auto run = [&](auto nt_tag) {
+        constexpr int NT = decltype(nt_tag)::value;
         float dw[4][NT];
         {
             const int fs[4] = {df.x, df.y, df.z, df.w};
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const float4 w = __ldg(&g.dr_w[y + c]);
-                if (MIXED) {
-                    const bool s = fs[c] != fmin;
-                    dw[c][0] = s ? 0.0f : w.x;
-                    dw[c][1] = s ? w.x : w.y;
-                    dw[c][2] = s ? w.y : w.z;
-                    dw[c][3] = s ? w.z : w.w;
-                    dw[c][NT - 1] = s ? w.w : 0.0f;
-                } else {
-                    dw[c][0] = w.x; dw[c][1] = w.y; dw[c][2] = w.z; dw[c][3] = w.w;
+                const float wv[4] = {dwl[c].x, dwl[c].y, dwl[c].z, dwl[c].w};
+                const int off = fs[c] - wfmin;  // 0 .. NT-4
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    float v = 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (t - u >= 0 && t - u <= NT - 4) v = (off == t - u) ? wv[u] : v;
+                    dw[c][t] = v;
                 }
             }
         }
-        // the next input row this thread kicks, its slot address
-        uint32_t r = (uint32_t)((int)hl + fmin);
-        uint32_t aload = ring_q + (r % K) * pitchB;
-        float4 A0 = make_float4(0, 0, 0, 0), A1 = A0, A2 = A0, A3 = A0, A4 = A0;
-        auto kick_row = [&]() -> float4 {
-            float4 k = make_float4(0, 0, 0, 0);
-            if ((uint32_t)(xs + (int)r) < n) {
-                int f_sum, f_2;
-                asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(f_sum), "=r"(f_2) : "r"(tf_b + r * 8));
-                const float4 w1 = lds128(tw1_b + r * 16), w2 = lds128(tw2_b + r * 16);
-                k = kick_quad<FMA>(aload, f_sum, (int)y + f_2, n, w1, w2);
-            }
-            r++;
-            aload += pitchB;
-            if (aload == ring_end) aload = ring_q;
-            return k;
-        };
-        auto push = [&](const float4 k) {
-            A0 = A1; A1 = A2; A2 = A3;
-            if (MIXED) { A3 = tmixed ? A4 : k; A4 = k; }
-            else A3 = k;
-        };
-        auto drift = [&]() -> float4 {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
-            float4 d;
-            float v;
-#define IVS_DRIFT_COL(c, m)                                                     \
-            v = __fmul_rn(A0.m, dw[c][0]);                                      \
-            v = madd<FMA>(A1.m, dw[c][1], v);                                   \
-            v = madd<FMA>(A2.m, dw[c][2], v);                                   \
-            v = madd<FMA>(A3.m, dw[c][3], v);                                   \
-            if (MIXED) v = madd<FMA>(A4.m, dw[c][NT - 1], v);                   \
-            d.m = v;
-            IVS_DRIFT_COL(0, x)
-            IVS_DRIFT_COL(1, y)
-            IVS_DRIFT_COL(2, z)
-            IVS_DRIFT_COL(3, w)
-#undef IVS_DRIFT_COL
-            return d;
-        };
-        // priming: the first window
-        {
-            const int np = (MIXED && tmixed) ? 5 : 4;
-            for (int k = 0; k < np; k++) push(kick_row());
-        }
-        float4 d = drift();
-        sts128(scr_q, d);
+        // rows r0 .. r0+NT-1 make output row 0; kick number k (k = 0, 1, ...) reads row r0 + k
+        const uint32_t r0 = (uint32_t)((int)hl + wfmin);
+        const uint32_t nkicks = S + NT - 1;
 
-        uint32_t pending = 1, pbar = 0, pph = 0;  // thread 0: outcome of the early probe of row `wrow`
-        for (uint32_t i = 0; i < S; i++) {
-            if (tid == 0 && !pending) mbar_wait_addr(pbar, pph);
-            __syncwarp();  // bar.sync is warp-aligned: lane 0 rejoins its warp first
-            named_bar_sync(1, T);
-            if (tid == 0) {
-                // everybody is past reading input rows < i + dead_off: re-arm their slots
-                issue_rows(min(RIN, K + i + sa.dead_off));
-                // the rows read after the next barrier: probe now, block (if at all) just before it
-                pending = 1;
-                if (wrow < RIN && wrow <= i + 2 + H) {
-                    if ((uint32_t)(xs + (int)wrow) < n) {
-                        row_bar(wrow, pbar, pph);
-                        pending = mbar_test(pbar, pph);
-                    }
-                    wrow++;
-                }
+        // ---- staging duty: rows >= K are issued by lane 0 of warp (row mod NW)
+        uint32_t prow = K + ((warp + NW - K % NW) % NW);  // first row >= K with row % NW == warp
+        uint32_t pslot = prow % K, puse = prow / K;
+        uint32_t pfree = 0;  // outcome of the last probe of empty[pslot]
+        uint32_t kicked = 0; // rows this warp has kicked so far
+        auto duty_probe = [&]() {
+            // the slot cannot be free before this warp itself has handed back the row that is in it
+            if (lane == 0 && prow < RIN && r0 + kicked + K > prow)
+                pfree = mbar_test(empty_b + pslot * 8, (puse - 1) & 1);
+        };
+        auto duty_issue = [&]() {
+            if (lane == 0 && prow < RIN && pfree) {
+                issue_row(prow, pslot);
+                prow += NW;
+                pslot += NW;
+                while (pslot >= K) { pslot -= K; puse++; }
+                pfree = 0;
             }
-            const uint32_t srow = scr_q + (i & 1) * pitchB;
-            const float4 L = lds128(srow - 16), R = lds128(srow + 16);
-            float4 knew = make_float4(0, 0, 0, 0);
-            const bool more = i + 1 < S;
-            if (more) knew = kick_row();
-            // ---- Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211), store, projection partial
-            {
-                const float in[8] = {L.z, L.w, d.x, d.y, d.z, d.w, R.x, R.y};
+        };
+        // blocking wait for a staged row; keeps serving the staging duty so that nobody starves
+        auto wait_row = [&](uint32_t bar, uint32_t ph) {
+            uint32_t tries = 0;
+            while (!mbar_try(bar, ph)) {
+                duty_probe();
+                duty_issue();
+                if (++tries > (1u << 22)) __trap();  // a copy that never lands is a bug: do not hang the GPU
+            }
+        };
+
+        uint32_t aload = ring_q + (r0 % K) * pitchB;
+        uint32_t tw1 = smem_u32(tab_w1) + r0 * 16, tw2 = smem_u32(tab_w2) + r0 * 16, tf = smem_u32(tab_f) + r0 * 8;
+        int2 f = lds64i(tf);
+        float4 A[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) A[t] = make_float4(0, 0, 0, 0);
+        // cursors: the staged row the next kick reads (slot, use), the row to hand back
+        uint32_t kslot = r0 % K, kuse = r0 / K;
+        uint32_t rel = empty_b + kslot * 8;
+        const uint32_t rel_end = empty_b + K * 8;
+
+        // the rows below the window are never read by this warp
+        if (lane == 0) {
+            for (uint32_t r = 0; r < r0; r++) mbar_arrive_addr(empty_b + (r % K) * 8);
+        }
+        wait_row(full_b + kslot * 8, kuse & 1);  // the first kick's row
+
+        float4 d = make_float4(0, 0, 0, 0), dprev = d;  // drifted rows of the last two iterations
+        float pprev = 0.0f;   // this lane's part of a finished row's sum (reduced an iteration later)
+
+        // iteration `it`: kick row r0 + it (while there are any); from it = NT-1 on a drifted row
+        // (output row it - NT + 1) comes out; the stencil handles the drifted row of two iterations
+        // before (output row it - NT - 1), which gives the neighbour warps a row of slack.
+        for (uint32_t it = 0; it <= nkicks + 1; it++) {
+            const bool kick = it < nkicks;              // there is a row to kick
+            const bool have = it >= (uint32_t)NT + 1;   // dprev holds drifted output row it - NT - 1
+            // ---- probes whose answers are needed at the end of the iteration
+            uint32_t landed = 1;
+            uint32_t nbar = 0, nph = 0;
+            if (it + 1 < nkicks) {  // the row the next iteration kicks
+                uint32_t s2 = kslot + 1, u2 = kuse;
+                if (s2 == K) { s2 = 0; u2++; }
+                nbar = full_b + s2 * 8;
+                nph = u2 & 1;
+                landed = mbar_test(nbar, nph);
+            }
+            duty_probe();
+            if (have) {
+                // ---- neighbours of the previous drifted row: shuffles inside the warp, the
+                // mailboxes across warp boundaries
+                float Lz = __shfl_up_sync(0xffffffffu, dprev.z, 1);
+                float Lw = __shfl_up_sync(0xffffffffu, dprev.w, 1);
+                float Rx = __shfl_down_sync(0xffffffffu, dprev.x, 1);
+                float Ry = __shfl_down_sync(0xffffffffu, dprev.y, 1);
+                {
+                    const uint32_t orow = it - NT - 1;  // the output row in dprev
+                    const uint32_t pa = peek + (orow & (kMailSlots - 1)) * 16;
+                    const bool edge = edge_l || edge_r;
+                    float4 m = make_float4(0, 0, 0, 0);
+                    if (edge) m = lds128_volatile(pa);
+                    uint32_t tries = 0;
+                    // the poll is warp-uniform so that lane 0 keeps serving the staging duty
+                    while (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1)) {
+                        __nanosleep(64);  // the neighbour is a row behind: do not steal its issue slots
+                        duty_probe();
+                        duty_issue();
+                        if (edge) m = lds128_volatile(pa);
+                        if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
+                    }
+                    if (edge_l) { Lz = m.x; Lw = m.y; }
+                    if (edge_r) { Rx = m.x; Ry = m.y; }
+                }
+                // ---- the sum of the row before: the shuffle chain hides behind the stencil
+                {
+                    float p = pprev;
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
+                    if (lane == 0 && it > (uint32_t)NT + 1) redw[(it - NT - 2) * NW] = p;
+                }
+                // ---- Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211), store, projection partial
+                const float in[8] = {Lz, Lw, dprev.x, dprev.y, dprev.z, dprev.w, Rx, Ry};
                 float o[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float v = __fmul_rn(in[j], w5[j][0]);
-                    v = madd<FMA>(in[1 + j], w5[j][1], v);
-                    v = madd<FMA>(in[2 + j], w5[j][2], v);
-                    v = madd<FMA>(in[3 + j], w5[j][3], v);
-                    v = madd<FMA>(in[4 + j], w5[j][4], v);
-                    o[j] = v;
+                for (int c = 0; c < 4; c++) {
+                    float v = __fmul_rn(in[c], w5[c][0]);
+                    v = madd<FMA>(in[1 + c], w5[c][1], v);
+                    v = madd<FMA>(in[2 + c], w5[c][2], v);
+                    v = madd<FMA>(in[3 + c], w5[c][3], v);
+                    v = madd<FMA>(in[4 + c], w5[c][4], v);
+                    o[c] = v;
                 }
                 *gout = make_float4(o[0], o[1], o[2], o[3]);
                 gout += nq;
@@ -930,21 +995,72 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
                 p = __fadd_rn(p, __fmul_rn(o[1], ws4.y));
                 p = __fadd_rn(p, __fmul_rn(o[2], ws4.z));
                 p = __fadd_rn(p, __fmul_rn(o[3], ws4.w));
-#pragma unroll
-                for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
-                if (lane == 0) red[i * NW + warp] = p;
+                pprev = p;
             }
-            if (more) {
-                push(knew);
-                d = drift();
-                sts128(scr_q + ((i + 1) & 1) * pitchB, d);
+            dprev = d;
+            if (kick) {
+                // ---- wake kick + RF kick of the staged row, into the window; drift
+                const float4 w1 = lds128(tw1), w2 = lds128(tw2);
+                const float4 k = kick_quad<FMA>(aload, f.x, y0 + f.y, n, w1, w2);
+                tw1 += 16; tw2 += 16; tf += 8;
+                f = lds64i(tf);  // next row's entry, a row ahead of its use
+                aload += pitchB;
+                if (aload == ring_end) aload = ring_q;
+#pragma unroll
+                for (int t = 0; t + 1 < NT; t++) A[t] = A[t + 1];
+                A[NT - 1] = k;
+                {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
+                    float v;
+#define IVS_DRIFT_COL(c, m)                                                             \
+                    v = __fmul_rn(A[0].m, dw[c][0]);                                    \
+                    _Pragma("unroll") for (int t = 1; t < NT; t++) v = madd<FMA>(A[t].m, dw[c][t], v); \
+                    d.m = v;
+                    IVS_DRIFT_COL(0, x)
+                    IVS_DRIFT_COL(1, y)
+                    IVS_DRIFT_COL(2, z)
+                    IVS_DRIFT_COL(3, w)
+#undef IVS_DRIFT_COL
+                }
+                if (it + 1 >= (uint32_t)NT) {
+                    // d is drifted output row it - NT + 1: post the warp's edge values
+                    const uint32_t seq = it - NT + 2;
+                    const uint32_t ms = (it - NT + 1) & (kMailSlots - 1);
+                    if (lane == 0) sts128_volatile(post_l + ms * 16, make_float4(d.x, d.y, __uint_as_float(seq), 0.0f));
+                    if (lane == 31) sts128_volatile(post_r + ms * 16, make_float4(d.z, d.w, __uint_as_float(seq), 0.0f));
+                }
+                // the staged row is in registers everywhere (its drift has been computed): hand it back
+                __syncwarp();
+                if (lane == 0) mbar_arrive_addr(rel);
+                rel += 8;
+                if (rel == rel_end) rel = empty_b;
+                if (++kslot == K) { kslot = 0; kuse++; }
+                kicked++;
+            }
+            duty_issue();
+            if (!landed) wait_row(nbar, nph);
+        }
+        // the last row's sum
+        {
+            float p = pprev;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
+            if (lane == 0) redw[(S - 1) * NW] = p;
+        }
+        // rows this warp still has to issue (its probe may have failed on the last iterations)
+        {
+            uint32_t tries = 0;
+            while (lane == 0 && prow < RIN) {
+                duty_probe();
+                duty_issue();
+                if (++tries > (1u << 24)) __trap();
             }
         }
     };
-    if (wmixed) run(std::true_type{});
-    else run(std::false_type{});
+    if (spread == 0) run(std::integral_constant<int, 4>{});
+    else if (spread == 1) run(std::integral_constant<int, 5>{});
+    else run(std::integral_constant<int, 6>{});
 
-    // the strip's row sums: one thread per row adds the warp partials in fixed order
+    // the strip's row sums: one thread per row adds the warps' partials in fixed order
     __syncthreads();
     for (uint32_t i = tid; i < S; i += T) {
         float v = 0.0f;
@@ -1046,41 +1162,46 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
     plan->pad_y = kPad;
     // ---- streaming kernel (default for grid sizes that are multiples of 256, up to 2048)
     plan->stream = false;
-    bool quads_ok = true;  // a thread's 4 columns may start their drift taps on at most 2 adjacent rows
-    for (uint32_t i = 0; i + 3 < n && quads_ok; i += 4) {
-        const int lo = std::min(std::min(dr_first[i], dr_first[i + 1]), std::min(dr_first[i + 2], dr_first[i + 3]));
-        const int hi = std::max(std::max(dr_first[i], dr_first[i + 1]), std::max(dr_first[i + 2], dr_first[i + 3]));
-        quads_ok = hi - lo <= 1;
+    const uint32_t NW = n / 128;  // warps: one quad of columns per thread
+    bool quads_ok = n % 256 == 0 && n <= 2048;
+    // over a warp's 128 columns the first drift tap may vary by at most 2 rows (window of up to 6 rows)
+    for (uint32_t w = 0; quads_ok && w < NW; w++) {
+        const auto mm = std::minmax_element(dr_first.begin() + 128 * w, dr_first.begin() + 128 * (w + 1));
+        quads_ok = *mm.second - *mm.first <= 2;
     }
-    if (n % 256 == 0 && n <= 2048 && quads_ok && !(s->desc.flags & IVS_SIM_TILED)) {
+    if (quads_ok && !(s->desc.flags & IVS_SIM_TILED)) {
         const uint32_t H = plan->halo_lo + plan->halo_hi;
-        const uint32_t threads_s = n / 4, NW = n / 128;
+        const uint32_t threads_s = n / 4;
         const uint32_t pitch = n + 2 * kPadS;
-        // after the barrier of output row i nobody reads input rows below i + dead_off any more
-        const int dfirst_min = *std::min_element(dr_first.begin(), dr_first.end());
-        const uint32_t dead_off = (uint32_t)(4 + (int)plan->halo_lo + dfirst_min);
-        const uint32_t live = H + 2 - dead_off;  // rows that have to sit in the ring at the same time
-        const uint32_t max_strip = std::min<uint32_t>(n, (n >= 2048) ? 64 : 128);
+        const uint32_t max_strip = std::min<uint32_t>(n, 128);
         const uint32_t max_rin = max_strip + H;
+        const uint32_t wcount = n + ((max_rin + 63) & ~63u);
+        const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
         auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-        const size_t fixed = a16((size_t)2 * pitch * 4) + a16((size_t)(n + n / 32) * 8) + a16((size_t)NW * max_rin * 8) +
-                             a16((size_t)max_strip * NW * 4) + 2 * a16((size_t)max_rin * 16) + a16((size_t)max_rin * 8);
+        const size_t fixed = a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) + a16((size_t)NW * max_rin * 8) +
+                             a16((size_t)max_strip * NW * 4) + 2 * a16((size_t)(max_rin + 1) * 16) +
+                             a16((size_t)(max_rin + 1) * 8) + a16((size_t)NW * 2 * kMailSlots * 16);
+        const bool fma = ctx->arith == IVS_ARITH_FMA;
+        const void* kfn = fma ? (const void*)stream_step_kernel<true> : (const void*)stream_step_kernel<false>;
         cudaFuncAttributes fa;
-        IVS_CUDA(ctx, cudaFuncGetAttributes(&fa, ctx->arith == IVS_ARITH_FMA ? stream_step_kernel<true> : stream_step_kernel<false>));
-        const uint32_t by_regs = std::max<uint32_t>(1, 65536u / (std::max(fa.numRegs, 32) * threads_s));
+        IVS_CUDA(ctx, cudaFuncGetAttributes(&fa, kfn));
+        const uint32_t regs_thread = (std::max(fa.numRegs, 32) + 7) & ~7;
+        const uint32_t by_regs = std::max<uint32_t>(1, 65536u / (regs_thread * threads_s));
         uint32_t want = std::min<uint32_t>(by_regs, 16);  // CTAs per SM the registers allow
         uint32_t K = 0;
         size_t sb = 0;
-        for (; want >= 1; want--) {
+        // ring depth: the warps' windows start up to H rows apart, plus rows in flight; the
+        // mailboxes (kMailSlots deep) bound it from above
+        const uint32_t kmin = H + 4, kmax = kMailSlots - 8;
+        for (; want >= 1 && kmin <= kmax; want--) {
             const size_t budget = (size_t)227 * 1024 / want - 1024;  // 1 KB per CTA is reserved by the system
-            const uint32_t kmin = std::max(live + 3, H + 3);  // the set-up waits for rows 0 .. H+1
-            if (budget < fixed + (size_t)kmin * (pitch * 4 + 8)) continue;
-            K = (uint32_t)std::min<size_t>(std::max(live + 12, kmin), (budget - fixed) / ((size_t)pitch * 4 + 8));
-            sb = a16((size_t)K * pitch * 4) + fixed + a16((size_t)K * 8);
+            if (budget < fixed + (size_t)kmin * (pitch * 4 + 16)) continue;
+            K = (uint32_t)std::min<size_t>(std::min(kmin + 12, kmax), (budget - fixed) / ((size_t)pitch * 4 + 16));
+            sb = a16((size_t)K * pitch * 4) + fixed + 2 * a16((size_t)K * 8);
             if (sb <= budget) break;
             K = 0;
         }
-        if (K >= live + 3 && K >= H + 3) {
+        if (K >= kmin) {
             const uint32_t per_sm = want;
             // strips per member: minimise rounds x (rows through the pipeline per CTA + set-up)
             uint64_t best = ~0ull;
@@ -1092,18 +1213,28 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
                 const uint64_t units = (uint64_t)P * s->members;
                 const uint64_t slots = (uint64_t)ctx->sm_count * per_sm;
                 const uint64_t rounds = (units + slots - 1) / slots;
-                const uint64_t cost = rounds * (S0 + H + 6);
+                const uint64_t cost = rounds * (S0 + H + 16);  // set-up ~ 16 rows' worth of time
                 if (cost < best) { best = cost; bestP = P; }
             }
+            // Fokker-Planck weights with the taps that fall outside the grid zeroed: the shuffles
+            // deliver a lane's own value there instead of the tile kernels' zero pad
+            std::vector<float> fps(fpw);
+            fps[0] = fps[1] = 0.0f;
+            fps[5] = 0.0f;
+            fps[(size_t)(n - 1) * 5 + 3] = fps[(size_t)(n - 1) * 5 + 4] = 0.0f;
+            fps[(size_t)(n - 2) * 5 + 4] = 0.0f;
+            IVS_CUDA(ctx, cudaMalloc(&plan->fp5, (size_t)n * 20));
+            IVS_CUDA(ctx, cudaMemcpy(plan->fp5, fps.data(), (size_t)n * 20, cudaMemcpyHostToDevice));
             plan->stream = true;
             plan->strip = ivs_div_up(n, bestP);
             plan->kslots = K;
-            plan->dead_off = dead_off;
             plan->max_strip = max_strip;
             plan->max_rin = max_rin;
+            plan->wwin_len = wwin_len;
             plan->threads = threads_s;
             plan->smem = sb;
             plan->tx = 0;
+            IVS_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
         }
     }
     // tile height: minimise (rounds of CTAs over the machine) x (rows staged per CTA)
@@ -1147,8 +1278,6 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         return st;
     // opt in to the large dynamic shared memory once (not per launch)
     if (plan->stream) {
-        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(stream_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
         plan->ready = true;
         return IVS_OK;
     }
@@ -1163,7 +1292,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
 }
 
 void ivs_fused_plan_destroy(ivs_fused_plan* plan) {
-    void** bufs[] = {&plan->rf_first, &plan->rf_w, &plan->dr_first, &plan->dr_w, &plan->fp_base, &plan->fp_w};
+    void** bufs[] = {&plan->rf_first, &plan->rf_w, &plan->dr_first, &plan->dr_w, &plan->fp_base, &plan->fp_w, &plan->fp5};
     for (void** b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
@@ -1194,8 +1323,9 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
         stream_args sa;
         sa.f = a;
         sa.f.pitch = s->n + 2 * kPadS;
-        sa.strip = plan->strip; sa.kslots = plan->kslots; sa.dead_off = plan->dead_off;
-        sa.max_strip = plan->max_strip; sa.max_rin = plan->max_rin;
+        sa.f.fp_w5 = (const float*)plan->fp5;
+        sa.strip = plan->strip; sa.kslots = plan->kslots;
+        sa.max_strip = plan->max_strip; sa.max_rin = plan->max_rin; sa.wwin_len = plan->wwin_len;
         const dim3 sgrid(ivs_div_up(s->n, plan->strip), s->members);
         if (ctx->arith == IVS_ARITH_FMA) stream_step_kernel<true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
         else stream_step_kernel<false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);

@@ -47,8 +47,9 @@ struct ivs_fused_plan {
     void* dr_first = nullptr; void* dr_w = nullptr;
     void* fp_base = nullptr; void* fp_w = nullptr;
     bool vec = false;   // float4-per-lane kernel (grid size multiple of 256)
-    bool stream = false;  // streaming kernel (threads own columns)
-    uint32_t strip = 0, kslots = 0, dead_off = 0, max_strip = 0, max_rin = 0;
+    bool stream = false;  // streaming kernel (independent warps, one quad of columns per thread)
+    uint32_t strip = 0, kslots = 0, max_strip = 0, max_rin = 0, wwin_len = 0;
+    void* fp5 = nullptr;  // Fokker-Planck weights, out-of-grid taps zeroed (streaming kernel)
     bool ready = false;
 };
 ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan);

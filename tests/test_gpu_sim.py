@@ -101,9 +101,14 @@ def test_fused_equals_unfused_bit_for_bit(capi, ctx_strict, ctx_fma, mode, case)
     a = _states(capi, ctx, p, 0, [1, 7, 24])
     t = _states(capi, ctx, p, capi.SIM_TILED, [1, 7, 24])
     b = _states(capi, ctx, p, capi.SIM_UNFUSED, [1, 7, 24])
-    # streaming pipeline and tile kernel: same wake arithmetic, same maps -> identical grids
+    # streaming kernel and tile kernel: same maps, same wake arithmetic; only the summation trees
+    # of the profile (and of the Toeplitz product) differ, so the first step is identical and
+    # later ones differ by the round-off of the profile fed back through the wake
+    (ga, pa, wa, _), (gt, pt, wt, _) = a[0], t[0]
+    assert np.array_equal(ga, gt)
     for (ga, pa, wa, _), (gt, pt, wt, _) in zip(a, t):
-        assert np.array_equal(ga, gt) and np.array_equal(wa, wt)
+        assert rel_l1(ga, gt) < 1e-6
+        assert np.abs(wa - wt).max() <= 2e-6 * max(np.abs(wt).max(), 1e-30)
         assert np.allclose(pa, pt, rtol=2e-6, atol=1e-12)
     for (ga, pa, wa, _), (gb, pb, wb, _) in zip(a, b):
         if p.gap == 0.0:

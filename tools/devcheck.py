@@ -54,7 +54,7 @@ if __name__ == "__main__":
                 b = states(ctx, p, capi.SIM_UNFUSED, [1, 7, 24])
                 for k, ((ga, pa, wa, _), (gt, pt, wt, _), (gb, pb, wb, _)) in enumerate(zip(a, t, b)):
                     eq = np.array_equal(ga, gt)
-                    ok &= eq
+                    ok &= (eq if k == 0 else rel_l1(ga, gt) < 1e-6)
                     print("mode %d n %4d chk %d: stream==tiled %s (L1 %.2e, wake eq %s, prof %.1e) | vs unfused L1 %.2e"
                           % (mode, n, k, eq, rel_l1(ga, gt), np.array_equal(wa, wt),
                              np.abs(pa - pt).max() / np.abs(pt).max(), rel_l1(ga, gb)), flush=True)
