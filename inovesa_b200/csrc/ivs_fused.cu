@@ -608,6 +608,17 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t phase) {
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// the same as predicated instructions (no branch around a one-lane operation)
+__device__ __forceinline__ void mbar_arrive_if(uint32_t bar, bool on) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p mbarrier.arrive.shared::cta.b64 _, [%0]; }" ::"r"(bar),
+                 "r"((uint32_t)on)
+                 : "memory");
+}
+__device__ __forceinline__ void sts128_volatile_if(uint32_t addr, const float4 v, bool on) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(addr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)on)
+                 : "memory");
+}
 
 // wake kick then RF kick of one quad of columns (y0 .. y0+3) of a staged row, in registers.
 //   k1[m] = sum_t in[m + f1 + t] w1[t]         wake kick (src/SM/KickMap.cpp:243-266), 0 outside the grid
@@ -685,9 +696,8 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     double* wwin = reinterpret_cast<double*>(carve((size_t)sa.wwin_len * 8));    // wake function window
     double* partial = reinterpret_cast<double*>(carve((size_t)NW * sa.max_rin * 8));  // wake partial sums
     float* red = reinterpret_cast<float*>(carve((size_t)sa.max_strip * NW * 4));       // row-sum partials
-    float4* tab_w1 = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 16));  // wake taps per input row
-    float4* tab_w2 = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 16));  // RF taps per input row
-    int2* tab_f = reinterpret_cast<int2*>(carve((size_t)(sa.max_rin + 1) * 8));        // (f1 + f2, f2)
+    // per input row: wake taps, RF taps, (f1 + f2, f2, -, -)
+    float4* tab = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 48));
     float4* mail = reinterpret_cast<float4*>(carve((size_t)NW * 2 * kMailSlots * 16)); // [warp][side][slot] = (a, b, seq, -)
     uint64_t* full = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
     uint64_t* empty = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
@@ -824,11 +834,11 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
                 if (r >= hl && r < hl + S) g.wake_out[(size_t)member * n + x] = wk;
             }
             const int f2 = valid ? __ldg(&g.rf_first[x]) : -1;
-            tab_w1[r] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
-            tab_w2[r] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
-            tab_f[r] = make_int2(t.first + f2, f2);
+            tab[3 * r] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+            tab[3 * r + 1] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
+            tab[3 * r + 2] = make_float4(__int_as_float(t.first + f2), __int_as_float(f2), 0.0f, 0.0f);
         }
-        if (tid == 0) tab_f[RIN] = make_int2(-2, -1);  // read ahead by the row loop, never used
+        if (tid == 0) tab[3 * RIN + 2] = make_float4(__int_as_float(-2), __int_as_float(-1), 0.0f, 0.0f);  // read ahead, never used
     }
     __syncthreads();  // tables, pads and mailboxes visible to everybody
 
@@ -879,165 +889,183 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         const uint32_t r0 = (uint32_t)((int)hl + wfmin);
         const uint32_t nkicks = S + NT - 1;
 
-        // ---- staging duty: rows >= K are issued by lane 0 of warp (row mod NW)
+        // ---- staging duty: rows >= K are issued by lane 0 of warp (row mod NW).  The slot of row
+        // `prow` cannot be free before this warp itself has handed back the row that is in it, so
+        // the probing starts at iteration `pwin`.
         uint32_t prow = K + ((warp + NW - K % NW) % NW);  // first row >= K with row % NW == warp
         uint32_t pslot = prow % K, puse = prow / K;
         uint32_t pfree = 0;  // outcome of the last probe of empty[pslot]
-        uint32_t kicked = 0; // rows this warp has kicked so far
-        auto duty_probe = [&]() {
-            // the slot cannot be free before this warp itself has handed back the row that is in it
-            if (lane == 0 && prow < RIN && r0 + kicked + K > prow)
-                pfree = mbar_test(empty_b + pslot * 8, (puse - 1) & 1);
+        int pwin = prow < RIN ? (int)prow - (int)K - (int)r0 + 1 : 0x7fffffff;
+        auto duty_probe = [&]() {  // warp-uniform: every lane reads the same barrier word
+            pfree = mbar_test(empty_b + pslot * 8, (puse - 1) & 1);
         };
         auto duty_issue = [&]() {
-            if (lane == 0 && prow < RIN && pfree) {
-                issue_row(prow, pslot);
+            if (pfree) {
+                if (lane == 0) issue_row(prow, pslot);
                 prow += NW;
                 pslot += NW;
                 while (pslot >= K) { pslot -= K; puse++; }
                 pfree = 0;
             }
+            pwin = prow < RIN ? (int)prow - (int)K - (int)r0 + 1 : 0x7fffffff;
         };
         // blocking wait for a staged row; keeps serving the staging duty so that nobody starves
-        auto wait_row = [&](uint32_t bar, uint32_t ph) {
+        auto wait_row = [&](uint32_t bar, uint32_t ph, int it) {
             uint32_t tries = 0;
             while (!mbar_try(bar, ph)) {
-                duty_probe();
-                duty_issue();
+                if (it >= pwin) {
+                    duty_probe();
+                    duty_issue();
+                }
                 if (++tries > (1u << 22)) __trap();  // a copy that never lands is a bug: do not hang the GPU
             }
         };
 
         uint32_t aload = ring_q + (r0 % K) * pitchB;
-        uint32_t tw1 = smem_u32(tab_w1) + r0 * 16, tw2 = smem_u32(tab_w2) + r0 * 16, tf = smem_u32(tab_f) + r0 * 8;
-        int2 f = lds64i(tf);
+        uint32_t tp = smem_u32(tab) + r0 * 48;
+        int2 f = lds64i(tp + 32);
         float4 A[NT];
 #pragma unroll
         for (int t = 0; t < NT; t++) A[t] = make_float4(0, 0, 0, 0);
-        // cursors: the staged row the next kick reads (slot, use), the row to hand back
-        uint32_t kslot = r0 % K, kuse = r0 / K;
-        uint32_t rel = empty_b + kslot * 8;
-        const uint32_t rel_end = empty_b + K * 8;
+        // cursor: full[] entry of the staged row the next kick reads and its phase; empty[] sits eoff behind
+        uint32_t kbar = full_b + (r0 % K) * 8, kpar = (r0 / K) & 1;
+        const uint32_t full_end = full_b + K * 8, eoff = empty_b - full_b;
 
         // the rows below the window are never read by this warp
         if (lane == 0) {
             for (uint32_t r = 0; r < r0; r++) mbar_arrive_addr(empty_b + (r % K) * 8);
         }
-        wait_row(full_b + kslot * 8, kuse & 1);  // the first kick's row
+        wait_row(kbar, kpar, 0);  // the first kick's row
 
         float4 d = make_float4(0, 0, 0, 0), dprev = d;  // drifted rows of the last two iterations
         float pprev = 0.0f;   // this lane's part of a finished row's sum (reduced an iteration later)
+        uint32_t redp = smem_u32(red) + warp * 4 - NW * 4;  // where the row sum reduced next goes
+        const size_t gstride = (size_t)nq;
+        const bool edge = edge_l || edge_r;
 
-        // iteration `it`: kick row r0 + it (while there are any); from it = NT-1 on a drifted row
-        // (output row it - NT + 1) comes out; the stencil handles the drifted row of two iterations
-        // before (output row it - NT - 1), which gives the neighbour warps a row of slack.
-        for (uint32_t it = 0; it <= nkicks + 1; it++) {
-            const bool kick = it < nkicks;              // there is a row to kick
-            const bool have = it >= (uint32_t)NT + 1;   // dprev holds drifted output row it - NT - 1
-            // ---- probes whose answers are needed at the end of the iteration
-            uint32_t landed = 1;
-            uint32_t nbar = 0, nph = 0;
-            if (it + 1 < nkicks) {  // the row the next iteration kicks
-                uint32_t s2 = kslot + 1, u2 = kuse;
-                if (s2 == K) { s2 = 0; u2++; }
-                nbar = full_b + s2 * 8;
-                nph = u2 & 1;
-                landed = mbar_test(nbar, nph);
+        // ---- one kick step: staged row r0 + it -> wake kick + RF kick -> window -> drifted row d
+        // (output row it - NT + 1 once the window is full).  POST: d is a real output row whose edge
+        // values the neighbour warps need.  MORE: another kick follows, its row has to have landed.
+        auto kick_step = [&](const int it, const bool POST, const bool MORE) {
+            // probes whose answers are needed at the end of the step
+            uint32_t nbar = kbar + 8, npar = kpar;
+            if (nbar == full_end) { nbar = full_b; npar ^= 1; }
+            const uint32_t landed = mbar_test(MORE ? nbar : kbar, MORE ? npar : kpar);
+            const bool duty = it >= pwin;
+            if (duty) duty_probe();
+            const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
+#pragma unroll
+            for (int t = 0; t + 1 < NT; t++) A[t] = A[t + 1];
+            A[NT - 1] = kick_quad<FMA>(aload, f.x, y0 + f.y, n, w1, w2);
+            tp += 48;
+            f = lds64i(tp + 32);  // next row's entry, a row ahead of its use
+            aload += pitchB;
+            if (aload == ring_end) aload = ring_q;
+            {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
+                float v;
+#define IVS_DRIFT_COL(c, m)                                                             \
+                v = __fmul_rn(A[0].m, dw[c][0]);                                        \
+                _Pragma("unroll") for (int t = 1; t < NT; t++) v = madd<FMA>(A[t].m, dw[c][t], v); \
+                d.m = v;
+                IVS_DRIFT_COL(0, x)
+                IVS_DRIFT_COL(1, y)
+                IVS_DRIFT_COL(2, z)
+                IVS_DRIFT_COL(3, w)
+#undef IVS_DRIFT_COL
             }
-            duty_probe();
-            if (have) {
-                // ---- neighbours of the previous drifted row: shuffles inside the warp, the
-                // mailboxes across warp boundaries
-                float Lz = __shfl_up_sync(0xffffffffu, dprev.z, 1);
-                float Lw = __shfl_up_sync(0xffffffffu, dprev.w, 1);
-                float Rx = __shfl_down_sync(0xffffffffu, dprev.x, 1);
-                float Ry = __shfl_down_sync(0xffffffffu, dprev.y, 1);
-                {
-                    const uint32_t orow = it - NT - 1;  // the output row in dprev
-                    const uint32_t pa = peek + (orow & (kMailSlots - 1)) * 16;
-                    const bool edge = edge_l || edge_r;
-                    float4 m = make_float4(0, 0, 0, 0);
-                    if (edge) m = lds128_volatile(pa);
-                    uint32_t tries = 0;
-                    // the poll is warp-uniform so that lane 0 keeps serving the staging duty
-                    while (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1)) {
-                        __nanosleep(64);  // the neighbour is a row behind: do not steal its issue slots
+            if (POST) {
+                const uint32_t orow = (uint32_t)(it - NT + 1);
+                const uint32_t ms = (orow & (kMailSlots - 1)) * 16;
+                // lane 0 posts (x, y) for the left neighbour, lane 31 (z, w) for the right one
+                const bool l0 = lane == 0;
+                sts128_volatile_if((l0 ? post_l : post_r) + ms,
+                                   make_float4(l0 ? d.x : d.z, l0 ? d.y : d.w, __uint_as_float(orow + 1), 0.0f),
+                                   l0 || lane == 31);
+            }
+            // the staged row is in registers everywhere (its drift has been computed): hand it back
+            mbar_arrive_if(kbar + eoff, lane == 0);
+            kbar = nbar;
+            kpar = npar;
+            if (duty) duty_issue();
+            if (!landed) wait_row(nbar, npar, it);
+        };
+        // ---- one stencil step on dprev = drifted output row `orow`: neighbours, Fokker-Planck, store,
+        // partial row sum; the warp sum of the row before is reduced on the side
+        auto fp_step = [&](const int it, const uint32_t orow) {
+            float4 m = make_float4(0, 0, 0, 0);
+            const uint32_t pa = peek + (orow & (kMailSlots - 1)) * 16;
+            if (edge) m = lds128_volatile(pa);
+            float Lz = __shfl_up_sync(0xffffffffu, dprev.z, 1);
+            float Lw = __shfl_up_sync(0xffffffffu, dprev.w, 1);
+            float Rx = __shfl_down_sync(0xffffffffu, dprev.x, 1);
+            float Ry = __shfl_down_sync(0xffffffffu, dprev.y, 1);
+            float ps = pprev;
+            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 16));
+            if (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1)) {
+                // the neighbour is more than a row behind: poll (warp-uniformly, so that lane 0
+                // keeps serving the staging duty)
+                uint32_t tries = 0;
+                do {
+                    if (it >= pwin) {
                         duty_probe();
                         duty_issue();
-                        if (edge) m = lds128_volatile(pa);
-                        if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
                     }
-                    if (edge_l) { Lz = m.x; Lw = m.y; }
-                    if (edge_r) { Rx = m.x; Ry = m.y; }
-                }
-                // ---- the sum of the row before: the shuffle chain hides behind the stencil
-                {
-                    float p = pprev;
-#pragma unroll
-                    for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
-                    if (lane == 0 && it > (uint32_t)NT + 1) redw[(it - NT - 2) * NW] = p;
-                }
-                // ---- Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211), store, projection partial
-                const float in[8] = {Lz, Lw, dprev.x, dprev.y, dprev.z, dprev.w, Rx, Ry};
-                float o[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    float v = __fmul_rn(in[c], w5[c][0]);
-                    v = madd<FMA>(in[1 + c], w5[c][1], v);
-                    v = madd<FMA>(in[2 + c], w5[c][2], v);
-                    v = madd<FMA>(in[3 + c], w5[c][3], v);
-                    v = madd<FMA>(in[4 + c], w5[c][4], v);
-                    o[c] = v;
-                }
-                *gout = make_float4(o[0], o[1], o[2], o[3]);
-                gout += nq;
-                float p = __fmul_rn(o[0], ws4.x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
-                p = __fadd_rn(p, __fmul_rn(o[1], ws4.y));
-                p = __fadd_rn(p, __fmul_rn(o[2], ws4.z));
-                p = __fadd_rn(p, __fmul_rn(o[3], ws4.w));
-                pprev = p;
+                    if (edge) m = lds128_volatile(pa);
+                    if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
+                } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1));
             }
+            if (edge_l) { Lz = m.x; Lw = m.y; }
+            if (edge_r) { Rx = m.x; Ry = m.y; }
+            // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
+            const float in[8] = {Lz, Lw, dprev.x, dprev.y, dprev.z, dprev.w, Rx, Ry};
+            float o[4];
+#define IVS_FP_COL(c)                                                   \
+            {                                                           \
+                float v = __fmul_rn(in[c], w5[c][0]);                   \
+                v = madd<FMA>(in[1 + c], w5[c][1], v);                  \
+                v = madd<FMA>(in[2 + c], w5[c][2], v);                  \
+                v = madd<FMA>(in[3 + c], w5[c][3], v);                  \
+                v = madd<FMA>(in[4 + c], w5[c][4], v);                  \
+                o[c] = v;                                               \
+            }
+            IVS_FP_COL(0)
+            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
+            IVS_FP_COL(1)
+            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
+            IVS_FP_COL(2)
+            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
+            IVS_FP_COL(3)
+            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
+#undef IVS_FP_COL
+            *gout = make_float4(o[0], o[1], o[2], o[3]);
+            gout += gstride;
+            if (lane == 0 && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
+            redp += NW * 4;
+            float p = __fmul_rn(o[0], ws4.x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
+            p = __fadd_rn(p, __fmul_rn(o[1], ws4.y));
+            p = __fadd_rn(p, __fmul_rn(o[2], ws4.z));
+            p = __fadd_rn(p, __fmul_rn(o[3], ws4.w));
+            pprev = p;
+        };
+
+        // Iteration `it` kicks row r0 + it; from it = NT-1 on a drifted output row (it - NT + 1) comes
+        // out; the stencil handles the drifted row of two iterations before (output row it - NT - 1),
+        // which gives the neighbour warps a row of slack.
+        int it = 0;
+        for (; it <= NT; it++) {  // fill the window, the first two drifted rows
+            if (it < (int)nkicks) kick_step(it, it + 1 >= NT, it + 1 < (int)nkicks);
+            dprev = (it == NT - 1) ? d : dprev;
+        }
+        // here d = output row 1, dprev = output row 0
+        for (; it + 1 < (int)nkicks; it++) {  // steady state
+            fp_step(it, (uint32_t)(it - NT - 1));
             dprev = d;
-            if (kick) {
-                // ---- wake kick + RF kick of the staged row, into the window; drift
-                const float4 w1 = lds128(tw1), w2 = lds128(tw2);
-                const float4 k = kick_quad<FMA>(aload, f.x, y0 + f.y, n, w1, w2);
-                tw1 += 16; tw2 += 16; tf += 8;
-                f = lds64i(tf);  // next row's entry, a row ahead of its use
-                aload += pitchB;
-                if (aload == ring_end) aload = ring_q;
-#pragma unroll
-                for (int t = 0; t + 1 < NT; t++) A[t] = A[t + 1];
-                A[NT - 1] = k;
-                {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
-                    float v;
-#define IVS_DRIFT_COL(c, m)                                                             \
-                    v = __fmul_rn(A[0].m, dw[c][0]);                                    \
-                    _Pragma("unroll") for (int t = 1; t < NT; t++) v = madd<FMA>(A[t].m, dw[c][t], v); \
-                    d.m = v;
-                    IVS_DRIFT_COL(0, x)
-                    IVS_DRIFT_COL(1, y)
-                    IVS_DRIFT_COL(2, z)
-                    IVS_DRIFT_COL(3, w)
-#undef IVS_DRIFT_COL
-                }
-                if (it + 1 >= (uint32_t)NT) {
-                    // d is drifted output row it - NT + 1: post the warp's edge values
-                    const uint32_t seq = it - NT + 2;
-                    const uint32_t ms = (it - NT + 1) & (kMailSlots - 1);
-                    if (lane == 0) sts128_volatile(post_l + ms * 16, make_float4(d.x, d.y, __uint_as_float(seq), 0.0f));
-                    if (lane == 31) sts128_volatile(post_r + ms * 16, make_float4(d.z, d.w, __uint_as_float(seq), 0.0f));
-                }
-                // the staged row is in registers everywhere (its drift has been computed): hand it back
-                __syncwarp();
-                if (lane == 0) mbar_arrive_addr(rel);
-                rel += 8;
-                if (rel == rel_end) rel = empty_b;
-                if (++kslot == K) { kslot = 0; kuse++; }
-                kicked++;
-            }
-            duty_issue();
-            if (!landed) wait_row(nbar, nph);
+            kick_step(it, true, true);
+        }
+        for (; it <= (int)nkicks + 1; it++) {  // the last kick and the two rows still in flight
+            fp_step(it, (uint32_t)(it - NT - 1));
+            dprev = d;
+            if (it < (int)nkicks) kick_step(it, true, false);
         }
         // the last row's sum
         {
@@ -1049,7 +1077,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         // rows this warp still has to issue (its probe may have failed on the last iterations)
         {
             uint32_t tries = 0;
-            while (lane == 0 && prow < RIN) {
+            while (prow < RIN) {
                 duty_probe();
                 duty_issue();
                 if (++tries > (1u << 24)) __trap();
@@ -1179,8 +1207,8 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
         auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
         const size_t fixed = a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) + a16((size_t)NW * max_rin * 8) +
-                             a16((size_t)max_strip * NW * 4) + 2 * a16((size_t)(max_rin + 1) * 16) +
-                             a16((size_t)(max_rin + 1) * 8) + a16((size_t)NW * 2 * kMailSlots * 16);
+                             a16((size_t)max_strip * NW * 4) + a16((size_t)(max_rin + 1) * 48) +
+                             a16((size_t)NW * 2 * kMailSlots * 16);
         const bool fma = ctx->arith == IVS_ARITH_FMA;
         const void* kfn = fma ? (const void*)stream_step_kernel<true> : (const void*)stream_step_kernel<false>;
         cudaFuncAttributes fa;
