@@ -32,6 +32,9 @@ from inovesa_b200.params import kara_params  # noqa: E402
 
 f32 = np.float32
 ALGO_BYTES_PER_CELL = 8.0  # one fp32 read + one fp32 write of the grid per step
+# dram__bytes_read.sum + dram__bytes_write.sum of one stream_step_kernel launch on the benchmark
+# batch (8 x 2048^2), from the ncu --set full capture summarised in profiles/ (updated per round)
+TRAFFIC_BYTES_PER_LAUNCH = 236951552  # r1: 141.5 MB read + 95.4 MB written (L2 still holds dirty lines at kernel end)
 
 
 def workload_params(name):
@@ -166,9 +169,18 @@ def run_ours(args):
     cells_per_step = float(n) * n * members
     value = cells_per_step * args.steps * world / (ms * 1e-3)
 
-    # kernel-level view: average duration of one step launch on the stream (fused: one kernel)
+    # kernel-level view for the roofline: the dominant kernel is the fused step kernel.  With tracked
+    # particles a step is two launches (step kernel + tracking kernel), so the kernel's own average
+    # duration is measured on the same batch without particles, where a step is exactly that one
+    # launch (CUDA events on the launching stream, same warm-up, same number of steps).
     peak, peak_src = measured_peak()
-    achieved = cells_per_step * ALGO_BYTES_PER_CELL / (ms * 1e-3 / args.steps) / 1e9
+    ms_kernel = ms
+    if args.particles and not args.unfused:
+        simk = capi.Simulation(ctx, p, members, flags=flags, bunch_currents=currents, seed=rank)
+        simk.step(args.warmup)
+        ms_kernel = timed(simk.step, args.steps)
+        simk.close()
+    achieved = cells_per_step * ALGO_BYTES_PER_CELL / (ms_kernel * 1e-3 / args.steps) / 1e9
 
     # end to end through the C ABI with HOST buffers: per step upload the density from pinned
     # host memory (PhaseSpace::syncCLMem cpu2dev), advance one step, read the bunch profile
@@ -233,9 +245,11 @@ def run_ours(args):
                     "what": "ivs_sim_upload_grid (pinned H2D) + ivs_sim_step(1) + profile D2H per step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": cells_per_step * ALGO_BYTES_PER_CELL
-                         * (1 if not args.unfused else 1)},
+                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if not args.unfused and members == 8 and n == 2048 else None,
+                         "peak_source": peak_src,
+                         "kernel": "stream_step_kernel" if not args.unfused else "kick/drift/fokker_planck/project sequence",
+                         "us_per_launch": ms_kernel * 1e3 / args.steps,
+                         "algorithmic_bytes_per_launch": cells_per_step * ALGO_BYTES_PER_CELL},
             "clocks": clocks,
         }
         if single_run:

@@ -121,19 +121,10 @@ __device__ __forceinline__ void kick_one(float& par, float perp, const float* __
     par = std_max(1.0f, std_min(par, (float)(n - 1)));
 }
 
-__global__ void track_step_kernel(float2* __restrict__ particles, uint32_t np, uint32_t n,
-                                  const float* __restrict__ wake, const float* __restrict__ rf,
-                                  const float* __restrict__ drift, const float* __restrict__ w5,
-                                  const float* __restrict__ grid, uint32_t fptrack, float e1,
-                                  float dp, uint64_t seed, uint64_t step) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t member = blockIdx.y;
-    if (i >= np) return;
-    float2 p = particles[(size_t)member * np + i];
-    if (wake) kick_one(p.y, p.x, wake + (size_t)member * n, n);
-    kick_one(p.y, p.x, rf, n);
-    kick_one(p.x, p.y, drift, n);
-    if (w5 && fptrack == 1) {
+// Fokker-Planck applyTo of one particle for the deterministic tracking modes 1 and 2
+__device__ __forceinline__ void fp_track_one(float2& p, uint32_t n, const float* __restrict__ w5,
+                                             const float* __restrict__ grid_member, uint32_t fptrack) {
+    if (fptrack == 1) {
         uint32_t yi = f2u(floorf(p.y));
         if (yi > n - 1) yi = n - 1;
         float offset = 0.0f;
@@ -142,13 +133,13 @@ __global__ void track_step_kernel(float2* __restrict__ particles, uint32_t np, u
             if (w != 0.0f) offset = IVS_ADD(IVS_MUL((float)(2 - k), w), offset);
         }
         p.y = std_max(1.0f, std_min(IVS_ADD(p.y, offset), (float)(n - 1)));
-    } else if (w5 && fptrack == 2) {
+    } else {
         uint32_t xu = f2u(floorf(p.x));
         if (xu > n - 1) xu = n - 1;
         int yi = (int)floorf(p.y);
         if (yi > (int)(n - 1)) yi = (int)(n - 1);
         if (yi < 0) yi = 0;
-        const float* row = grid + ((size_t)member * n + xu) * n;
+        const float* row = grid_member + (size_t)xu * n;
         float offset = 0.0f, charge = 0.0f;
         for (int k = 0; k < 5; k++) {
             const float w = w5[yi * 5 + k];
@@ -161,12 +152,53 @@ __global__ void track_step_kernel(float2* __restrict__ particles, uint32_t np, u
         }
         offset = IVS_DIV(offset, charge);
         p.y = std_max(1.0f, std_min(IVS_ADD(p.y, offset), (float)(n - 1)));
-    } else if (w5 && fptrack == 3) {
-        const float sigma = IVS_DIV(sqrtf(IVS_MUL(2.0f, e1)), dp);
-        const float g = IVS_MUL(sigma, normal01(seed + member, step, i));
-        p.y = IVS_SUB(p.y, IVS_ADD(IVS_MUL(p.y, e1), g));
     }
-    particles[(size_t)member * np + i] = p;
+}
+
+// One thread advances TWO particles (i and i + half) through the four maps: their dependent
+// table look-ups interleave, and in the stochastic mode one Box-Muller transform serves both.
+// `key` = hash of (seed, step), `sigma` = sqrt(2 e1)/dp: both uniform, computed on the host.
+__global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ particles, uint32_t np, uint32_t half,
+                                  uint32_t n, const float* __restrict__ wake, const float* __restrict__ rf,
+                                  const float* __restrict__ drift, const float* __restrict__ w5,
+                                  const float* __restrict__ grid, uint32_t fptrack, float e1,
+                                  float sigma, uint64_t key) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t member = blockIdx.y;
+    if (i >= half) return;
+    const uint32_t j = i + half;
+    const bool two = j < np;
+    float2* base = particles + (size_t)member * np;
+    float2 p = base[i];
+    float2 q = two ? base[j] : p;
+    if (wake) {
+        const float* wm = wake + (size_t)member * n;
+        kick_one(p.y, p.x, wm, n);
+        kick_one(q.y, q.x, wm, n);
+    }
+    kick_one(p.y, p.x, rf, n);
+    kick_one(q.y, q.x, rf, n);
+    kick_one(p.x, p.y, drift, n);
+    kick_one(q.x, q.y, drift, n);
+    if (w5 && (fptrack == 1 || fptrack == 2)) {
+        const float* gm = grid ? grid + (size_t)member * n * n : nullptr;
+        fp_track_one(p, n, w5, gm, fptrack);
+        fp_track_one(q, n, w5, gm, fptrack);
+    } else if (w5 && fptrack == 3) {
+        // pos.y -= pos.y*e1 + N(0, sqrt(2 e1)/dp)   (src/SM/FokkerPlanckMap.cpp:264-266); the
+        // reference draws from an unseeded mt19937, here a counter-based generator keyed on
+        // (seed, member, step, pair): reproducible run to run
+        const uint64_t h = mix64(key + ((uint64_t)member << 32) + i);
+        const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
+        const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+        const float r = sqrtf(-2.0f * __logf(u1));
+        float sn, cs;
+        __sincosf(6.2831853071795864f * u2, &sn, &cs);
+        p.y = IVS_SUB(p.y, IVS_ADD(IVS_MUL(p.y, e1), IVS_MUL(sigma, r * cs)));
+        q.y = IVS_SUB(q.y, IVS_ADD(IVS_MUL(q.y, e1), IVS_MUL(sigma, r * sn)));
+    }
+    base[i] = p;
+    if (two) base[j] = q;
 }
 
 }  // namespace
@@ -176,8 +208,18 @@ ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, ui
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
                                  float dp, uint64_t seed, uint64_t step) {
     if (np == 0) return IVS_OK;
-    track_step_kernel<<<dim3(ivs_div_up(np, 256), members), 256, 0, ctx->stream>>>(
-        (float2*)particles, np, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, dp, seed, step);
+    const uint32_t half = (np + 1) / 2;
+    // uniform quantities of the stochastic mode, in the reference's fp32 operations
+    const float sigma = sqrtf(2.0f * e1) / dp;
+    auto mix = [](uint64_t z) {
+        z += 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    const uint64_t key = mix(seed ^ mix(step));
+    track_step_kernel<<<dim3(ivs_div_up(half, 256), members), 256, 0, ctx->stream>>>(
+        (float2*)particles, np, half, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, sigma, key);
     IVS_LAUNCHED(ctx);
     return IVS_OK;
 }
