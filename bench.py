@@ -129,7 +129,10 @@ def run_ours(args):
     d = capi.derive(p)
     # synthetic input: the reference's Gaussian start distribution; members of the batch differ
     # in bunch current like a current scan (config 4's partitioning applied to this grid size)
-    currents = [float(p.bunch_current) * (0.5 + i / max(members, 1)) for i in range(members)]
+    from inovesa_b200.ensemble import member_block, scan_currents
+    lo, hi = member_block(members * world, world, rank)  # this rank's block of the scan
+    currents = [float(c) for c in scan_currents(0.5 * p.bunch_current, 1.5 * p.bunch_current,
+                                                members * world)[lo:hi]]
     rng = np.random.default_rng(12345 + rank)
     parts = None
     if args.particles:

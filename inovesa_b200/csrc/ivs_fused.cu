@@ -763,14 +763,32 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     }
     for (uint32_t i = tid; i < NW * 2 * kMailSlots; i += T) mail[i] = make_float4(0, 0, 0, 0);  // seq 0 = nothing posted
     if (g.has_wake) {
+        // all loads first, then the stores: one round trip to L2 instead of one per element
+        // (T = n/4 threads: 4 profile entries and at most 5 window entries each)
         const float* rin = g.rho_in + (size_t)member * n;
-        for (uint32_t i = tid; i < n; i += T) rho[i + (i >> 5)] = (double)__ldg(rin + i);
+        float rv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) rv[k] = __ldg(rin + tid + k * T);
         // w[x - x'] is stored at table index x - x' + n - 1; window entry t holds the table
         // entry xs + t, so row r and x' meet at t = r - x' + n - 1
         const int wtop = (int)(2 * n - 1);
-        const uint32_t tcount = n + ((RIN + 63) & ~63u);
-        for (uint32_t t = tid; t < tcount; t += T)
-            wwin[wwin_pos(t)] = __ldg(g.wakefn + min(max(xs + (int)t, 0), wtop));  // clamped entries belong to rows outside the grid
+        const uint32_t tcount = n + ((RIN + 63) & ~63u);  // <= 5 T for n >= 1024
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i = tid + k * T;
+            rho[i + (i >> 5)] = (double)rv[k];
+        }
+        for (uint32_t t0 = tid; t0 < tcount; t0 += 5 * T) {
+            double wv[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                wv[k] = __ldg(g.wakefn + min(max(xs + (int)(t0 + k * T), 0), wtop));  // clamped entries belong to rows outside the grid
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const uint32_t t = t0 + k * T;
+                if (t < tcount) wwin[wwin_pos(t)] = wv[k];
+            }
+        }
     }
     __syncthreads();
     if (g.has_wake) {
