@@ -1402,7 +1402,7 @@ launched:
     if (s->np) {
         st = ivs_track_step_launch(ctx, s->particles, s->np, s->members, s->n, s->has_wake ? s->wake : nullptr,
                                    s->rf, s->drift, s->has_fp ? s->fpw : nullptr, nullptr, s->desc.fptrack,
-                                   s->desc.e1, s->desc.dp, s->desc.seed, s->steps_done);
+                                   s->desc.e1, s->desc.dp, s->desc.seed, s->track_counter);
     }
     return st;
 }

@@ -28,11 +28,12 @@ ivs_status ivs_field_launch(ivs_ctx* ctx, const float* profile, uint32_t n, uint
                             float* power, float dq, float f_scale, float cutoff, int mode);
 // allocates the twiddle table for an FFT length (must not happen inside a graph capture)
 ivs_status ivs_field_prepare(ivs_ctx* ctx, uint32_t nmax);
-// all four maps' applyTo for every tracked particle of every member, one launch per step
+// all four maps' applyTo for every tracked particle of every member, one launch per step;
+// step_counter: 4 device words {step lo, step hi, blocks done, -} kept by the kernel itself
 ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
                                  uint32_t n, const float* wake, const float* rf, const float* drift,
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
-                                 float dp, uint64_t seed, uint64_t step);
+                                 float dp, uint64_t seed, unsigned int* step_counter);
 
 // the fused step kernel (ivs_fused.cu)
 struct ivs_fused_plan {

@@ -27,6 +27,7 @@ struct ivs_sim {
     float* moments = nullptr;     // [members][2][3]
     float* power = nullptr;       // [members]
     int* status = nullptr;        // device error flag of the fused kernel
+    unsigned int* track_counter = nullptr;  // device step counter of the stochastic tracking mode (+ block ticket)
     float f_scale = 0, cutoff = 0;
     uint64_t steps_done = 0;
     ivs_fused_plan plan{};

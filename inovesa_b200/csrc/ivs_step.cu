@@ -52,8 +52,7 @@ ivs_status enqueue_unfused_step(ivs_sim* s) {
     if (s->np) {
         IVS_TRY(ivs_track_step_launch(ctx, s->particles, s->np, m, n, s->has_wake ? s->wake : nullptr,
                                       s->rf, s->drift, s->has_fp ? s->fpw : nullptr, t3,
-                                      s->desc.fptrack, s->desc.e1, s->desc.dp, s->desc.seed,
-                                      s->steps_done));
+                                      s->desc.fptrack, s->desc.e1, s->desc.dp, s->desc.seed, s->track_counter));
     }
     if (s->has_fp) {
         IVS_TRY(ivs_fokker_planck_batched(ctx, t3, t1, n, m, s->fpw));
@@ -205,6 +204,8 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
     S_TRY(dalloc(ctx, &s->power, m));
     S_TRY(dalloc(ctx, &s->status, 4));
     S_TRY(ivs_memset_zero(ctx, s->status, 4 * sizeof(int)));
+    S_TRY(dalloc(ctx, &s->track_counter, 4));
+    S_TRY(ivs_memset_zero(ctx, s->track_counter, 4 * sizeof(unsigned int)));
     S_TRY(ivs_memset_zero(ctx, s->wake, (size_t)m * n * sizeof(float)));
     S_TRY(ivs_memset_zero(ctx, s->power, m * sizeof(float)));
     S_TRY(ivs_upload(ctx, s->grid[0], d->grid, cells * sizeof(float)));
@@ -256,7 +257,8 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
     ivs_fused_plan_destroy(&s->plan);
     float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
                      s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
-                     (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power};
+                     (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power,
+                     (float*)s->track_counter};
     for (float* b : bufs) if (b) cudaFree(b);
     if (s->status) cudaFree(s->status);
     delete s;
@@ -269,9 +271,9 @@ ivs_status ivs_sim_step(ivs_sim* s, uint32_t nsteps) {
     IVS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool use_graph = !(s->desc.flags & IVS_SIM_NO_GRAPH);
     const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
-    // tracking with the stochastic Fokker-Planck mode keys its generator on the step counter,
-    // which a replayed graph would freeze: launch directly in that case
-    const bool graph_ok = use_graph && !(s->np && s->desc.fptrack == 3);
+    // (tracking with the stochastic Fokker-Planck mode keys its generator on a step counter the
+    // tracking kernel keeps on the device, so a replayed graph draws fresh numbers every step)
+    const bool graph_ok = use_graph;
     // fused steps ping-pong two buffers: a graph is valid for an even number of steps only,
     // or for the parity it was captured at
     const uint32_t lps = launches_per_step(s);

@@ -157,48 +157,72 @@ __device__ __forceinline__ void fp_track_one(float2& p, uint32_t n, const float*
 
 // One thread advances TWO particles (i and i + half) through the four maps: their dependent
 // table look-ups interleave, and in the stochastic mode one Box-Muller transform serves both.
-// `key` = hash of (seed, step), `sigma` = sqrt(2 e1)/dp: both uniform, computed on the host.
+// The stochastic mode keys its generator on a step counter that lives on the DEVICE
+// (counter[0..1] = step as 64 bit, counter[2] = blocks finished), so that a replayed CUDA graph
+// still draws fresh numbers every step: every block reads the step when it starts, the last block
+// to finish advances it.
 __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ particles, uint32_t np, uint32_t half,
                                   uint32_t n, const float* __restrict__ wake, const float* __restrict__ rf,
                                   const float* __restrict__ drift, const float* __restrict__ w5,
                                   const float* __restrict__ grid, uint32_t fptrack, float e1,
-                                  float sigma, uint64_t key) {
+                                  float sigma, uint64_t seed, unsigned int* counter) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t member = blockIdx.y;
-    if (i >= half) return;
-    const uint32_t j = i + half;
-    const bool two = j < np;
-    float2* base = particles + (size_t)member * np;
-    float2 p = base[i];
-    float2 q = two ? base[j] : p;
-    if (wake) {
-        const float* wm = wake + (size_t)member * n;
-        kick_one(p.y, p.x, wm, n);
-        kick_one(q.y, q.x, wm, n);
+    const bool stochastic = w5 && fptrack == 3;
+    __shared__ unsigned long long skey;
+    if (stochastic) {
+        if (threadIdx.x == 0) {
+            const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(counter);
+            skey = mix64(seed ^ mix64(step));
+        }
+        __syncthreads();
     }
-    kick_one(p.y, p.x, rf, n);
-    kick_one(q.y, q.x, rf, n);
-    kick_one(p.x, p.y, drift, n);
-    kick_one(q.x, q.y, drift, n);
-    if (w5 && (fptrack == 1 || fptrack == 2)) {
-        const float* gm = grid ? grid + (size_t)member * n * n : nullptr;
-        fp_track_one(p, n, w5, gm, fptrack);
-        fp_track_one(q, n, w5, gm, fptrack);
-    } else if (w5 && fptrack == 3) {
-        // pos.y -= pos.y*e1 + N(0, sqrt(2 e1)/dp)   (src/SM/FokkerPlanckMap.cpp:264-266); the
-        // reference draws from an unseeded mt19937, here a counter-based generator keyed on
-        // (seed, member, step, pair): reproducible run to run
-        const uint64_t h = mix64(key + ((uint64_t)member << 32) + i);
-        const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
-        const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
-        const float r = sqrtf(-2.0f * __logf(u1));
-        float sn, cs;
-        __sincosf(6.2831853071795864f * u2, &sn, &cs);
-        p.y = IVS_SUB(p.y, IVS_ADD(IVS_MUL(p.y, e1), IVS_MUL(sigma, r * cs)));
-        q.y = IVS_SUB(q.y, IVS_ADD(IVS_MUL(q.y, e1), IVS_MUL(sigma, r * sn)));
+    if (i < half) {
+        const uint32_t j = i + half;
+        const bool two = j < np;
+        float2* base = particles + (size_t)member * np;
+        float2 p = base[i];
+        float2 q = two ? base[j] : p;
+        if (wake) {
+            const float* wm = wake + (size_t)member * n;
+            kick_one(p.y, p.x, wm, n);
+            kick_one(q.y, q.x, wm, n);
+        }
+        kick_one(p.y, p.x, rf, n);
+        kick_one(q.y, q.x, rf, n);
+        kick_one(p.x, p.y, drift, n);
+        kick_one(q.x, q.y, drift, n);
+        if (w5 && (fptrack == 1 || fptrack == 2)) {
+            const float* gm = grid ? grid + (size_t)member * n * n : nullptr;
+            fp_track_one(p, n, w5, gm, fptrack);
+            fp_track_one(q, n, w5, gm, fptrack);
+        } else if (stochastic) {
+            // pos.y -= pos.y*e1 + N(0, sqrt(2 e1)/dp)   (src/SM/FokkerPlanckMap.cpp:264-266); the
+            // reference draws from an unseeded mt19937, here a counter-based generator keyed on
+            // (seed, step, member, pair): reproducible run to run
+            const uint64_t h = mix64(skey + ((uint64_t)member << 32) + i);
+            const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
+            const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+            const float r = sqrtf(-2.0f * __logf(u1));
+            float sn, cs;
+            __sincosf(6.2831853071795864f * u2, &sn, &cs);
+            p.y = IVS_SUB(p.y, IVS_ADD(IVS_MUL(p.y, e1), IVS_MUL(sigma, r * cs)));
+            q.y = IVS_SUB(q.y, IVS_ADD(IVS_MUL(q.y, e1), IVS_MUL(sigma, r * sn)));
+        }
+        base[i] = p;
+        if (two) base[j] = q;
     }
-    base[i] = p;
-    if (two) base[j] = q;
+    if (stochastic) {
+        __syncthreads();  // every thread of the block has used skey
+        if (threadIdx.x == 0) {
+            const unsigned int total = gridDim.x * gridDim.y;
+            if (atomicAdd(counter + 2, 1u) == total - 1) {  // the last block: everybody has read the step
+                counter[2] = 0;
+                unsigned long long* st = reinterpret_cast<unsigned long long*>(counter);
+                *st = *st + 1ull;
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -206,20 +230,13 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
 ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
                                  uint32_t n, const float* wake, const float* rf, const float* drift,
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
-                                 float dp, uint64_t seed, uint64_t step) {
+                                 float dp, uint64_t seed, unsigned int* step_counter) {
     if (np == 0) return IVS_OK;
     const uint32_t half = (np + 1) / 2;
-    // uniform quantities of the stochastic mode, in the reference's fp32 operations
-    const float sigma = sqrtf(2.0f * e1) / dp;
-    auto mix = [](uint64_t z) {
-        z += 0x9E3779B97F4A7C15ull;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        return z ^ (z >> 31);
-    };
-    const uint64_t key = mix(seed ^ mix(step));
+    const float sigma = sqrtf(2.0f * e1) / dp;  // uniform, in the reference's fp32 operations
     track_step_kernel<<<dim3(ivs_div_up(half, 256), members), 256, 0, ctx->stream>>>(
-        (float2*)particles, np, half, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, sigma, key);
+        (float2*)particles, np, half, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, sigma, seed,
+        step_counter);
     IVS_LAUNCHED(ctx);
     return IVS_OK;
 }

@@ -169,6 +169,33 @@ def test_fused_tracking_matches_unfused(capi, ctx_strict, rng):
     assert e.value.code == capi.ERR_UNSUPPORTED
 
 
+def test_stochastic_tracking_is_reproducible_and_graph_safe(capi, ctx_fma, rng):
+    """FPTracking::stochastic (src/SM/FokkerPlanckMap.cpp:262-266): the generator is keyed on a
+    device-side step counter, so replayed CUDA graphs, direct launches and any split of the step
+    count draw the same numbers; the kicks keep the cloud at the natural energy spread"""
+    p = kara_params(grid_size=256)
+    p.fp_track = 3
+    n = p.grid_size
+    parts = np.stack([rng.normal(n / 2, n / 12, 4001), rng.normal(n / 2, n / 12, 4001)], 1).astype(f32)
+    runs = {}
+    for name, flags, split in (("graph", 0, [48]), ("direct", capi.SIM_NO_GRAPH, [48]),
+                               ("split", 0, [5, 16, 27])):
+        sim = capi.Simulation(ctx_fma, p, 2, particles=parts, flags=flags, seed=7)
+        for k in split:
+            sim.step(k)
+        runs[name] = sim.download()[3]
+        sim.close()
+    assert np.array_equal(runs["graph"], runs["direct"]) and np.array_equal(runs["graph"], runs["split"])
+    assert not np.array_equal(runs["graph"][0], runs["graph"][1])  # members draw different numbers
+    other = capi.Simulation(ctx_fma, p, 2, particles=parts, seed=8)
+    other.step(48)
+    assert not np.array_equal(other.download()[3], runs["graph"])
+    other.close()
+    d = capi.derive(p)
+    spread = runs["graph"][..., 1].std() * d.dp  # in units of the natural energy spread
+    assert 0.9 < spread < 1.1
+
+
 def test_fused_flags_displacements_beyond_its_halo(capi, ctx_strict):
     """a wake kick of many cells cannot be served from the staged pad: the step must say so"""
     p = kara_params(grid_size=128, bunch_current=5.0)  # absurd current -> huge wake offsets
