@@ -12,8 +12,16 @@ workload (config.workload): BASELINE.json configs[4] -- 2048x2048 grid, sin RF (
   exceeds the 126 MB L2: the timing rule "inputs larger than L2" instead of an L2 flush.
   A single L2-resident 2048^2 run is reported next to it as `single_run`.
 One "step" = one simulation step of every member (wake potential, wake kick, RF kick, drift,
-Fokker-Planck, X projection).  N > 1 GPUs: every rank runs its own batch (replicas, weak
-scaling, no collective on the step path); value = all ranks' cell-updates / max time.
+Fokker-Planck, X projection, tracking of the passive particles): two launches, the fused step
+kernel and the tracking kernel.  N > 1 GPUs: every rank runs its own block of the scan (replicas,
+weak scaling, no collective on the step path); value = all ranks' cell-updates / max time.
+roofline : the step kernel alone (the dominant kernel), timed with CUDA events on the same batch
+  without tracked particles; achieved = members * N^2 * 8 B / launch duration against the measured
+  HBM copy bandwidth of MEASURED_PEAKS.json; traffic = DRAM bytes of one launch from the ncu
+  capture in profiles/.
+e2e      : the same metric through the C ABI with HOST buffers (pinned H2D of the density, one
+  step, D2H of the bunch profile, every step): PCIe-bound by construction.
+cpu_baseline / --impl reference : the reference's own CPU code (oracle/_ref) on the host cores.
 """
 import argparse
 import json

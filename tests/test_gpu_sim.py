@@ -257,6 +257,60 @@ def test_observables(capi, ctx_strict, oracle):
     sim.close(); osim.close()
 
 
+@pytest.mark.parametrize("mode", ["strict", "fma"])
+def test_time_series_match_oracle(capi, ctx_strict, ctx_fma, oracle, mode):
+    """north_star: bunch length, energy spread and CSR power time series against the reference
+    CPU path (configs[0]: 256^2, free-space CSR, below threshold), out-step every 100 steps for
+    1000 steps, through the fused streaming kernel.  Stated tolerance: 1e-5 relative for the
+    integral and the two rms sizes, 1e-4 for the CSR power (an fp32 sum over 2048 spectral bins)."""
+    ctx = ctx_strict if mode == "strict" else ctx_fma
+    p = kara_params(grid_size=256, bunch_current=50e-6)
+    osim = oracle.sim(p)
+    sim = capi.Simulation(ctx, p, 1)
+    sim.set_radiation()
+    series = []
+    for k in range(10):
+        sim.step(100)
+        osim.step(100)
+        o, oo = sim.observe()[0], osim.observe()[0]
+        series.append((o, oo))
+        assert abs(o[0] / oo[0] - 1) < 1e-5, (k, o, oo)          # charge
+        assert abs(o[3] / oo[3] - 1) < 1e-5, (k, o, oo)          # sigma_q (bunch length)
+        assert abs(o[6] / oo[6] - 1) < 1e-5, (k, o, oo)          # sigma_p (energy spread)
+        assert abs(o[7] / oo[7] - 1) < 1e-4, (k, o, oo)          # CSR power
+    # the series is not trivially constant: the bunch breathes and radiates
+    sq = np.array([a[3] for a, _ in series])
+    assert sq.std() > 0 and np.all(np.array([a[7] for a, _ in series]) > 0)
+    sim.close()
+    osim.close()
+
+
+def test_above_threshold_statistics_match_oracle(capi, ctx_fma, oracle):
+    """north_star: beyond the chaotic horizon (bunch current far above the microbunching
+    threshold) trajectories decorrelate, so the comparison is statistical: mean and fluctuation
+    of the energy spread and of the CSR power over steps 2000..6000 against the reference CPU
+    path.  Stated tolerance: 10 % on the means, a factor 2 on the fluctuation amplitudes."""
+    p = kara_params(grid_size=256, bunch_current=600e-6)
+    osim = oracle.sim(p)
+    sim = capi.Simulation(ctx_fma, p, 1)
+    sim.set_radiation()
+    sim.step(2000)
+    osim.step(2000)
+    a, b = [], []
+    for _ in range(40):
+        sim.step(100)
+        osim.step(100)
+        a.append(sim.observe()[0][[6, 7]])
+        b.append(osim.observe()[0][[6, 7]])
+    a, b = np.array(a, np.float64), np.array(b, np.float64)
+    assert np.all(np.isfinite(a))
+    assert np.all(np.abs(a.mean(0) / b.mean(0) - 1) < 0.10), (a.mean(0), b.mean(0))
+    sa, sb = a.std(0), b.std(0)
+    assert np.all(sa < 2 * sb + 1e-3 * np.abs(b.mean(0))) and np.all(sb < 2 * sa + 1e-3 * np.abs(b.mean(0))), (sa, sb)
+    sim.close()
+    osim.close()
+
+
 def test_invalid_descriptors(capi, ctx_strict):
     p = kara_params(grid_size=4)
     with pytest.raises(capi.IvsError) as e:
