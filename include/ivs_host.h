@@ -79,6 +79,15 @@ int ivs_derive(const ivs_ring_params* p, ivs_derived* d);
 int ivs_rf_kick_offsets(const ivs_ring_params* p, const ivs_derived* d, float* offset);
 /* DriftMap::DriftMap (src/SM/DriftMap.cpp:21-30): n floats */
 int ivs_drift_offsets(const ivs_ring_params* p, const ivs_derived* d, float* offset);
+/* the same three with the map constructors' own arguments (axis limits, axis scales "Meter" =
+ * bl and "ElectronVolt" = dE, and what src/main.cpp:640-679 passes), for host code that mirrors
+ * the reference's classes (include/vfps_b200.hpp) */
+int ivs_rf_kick_linear(uint32_t n, float qmin, float qmax, float bl, float angle, float f_RF,
+                       float* offset);
+int ivs_rf_kick_sine(uint32_t n, float qmin, float qmax, float pmin, float pmax, float bl, float dE,
+                     float revolutionpart, float V_RF, float f_RF, float V0, float* offset);
+int ivs_drift_slip(uint32_t n, float qmin, float qmax, float pmin, float pmax, float dE,
+                   const float* slip, uint32_t nslip, float E0, float* offset);
 /* makeImpedance (src/Z/ImpedanceFactory.cpp:21-84) without the file contribution:
  * z = nfreqs complex<float> (interleaved re,im); *nonzero = 0 if "no impedance is used" */
 int ivs_make_impedance(size_t nfreqs, float fmax, double R_bend, double f_rev, double gap,
@@ -87,6 +96,9 @@ int ivs_make_impedance(size_t nfreqs, float fmax, double R_bend, double f_rev, d
 /* the wake impedance (src/main.cpp:717-721) and the radiation impedance (:724-727) */
 int ivs_wake_impedance(const ivs_ring_params* p, const ivs_derived* d, float* z, int* nonzero);
 int ivs_radiation_impedance(const ivs_ring_params* p, const ivs_derived* d, float* z);
+/* PhaseSpace::gaus (src/PS/PhaseSpace.cpp:471-484): exp(-a_i^2 / (2 zoom^2)) / sqrt(2 pi) on the
+ * axis values of a Ruler(n, amin, amax): n floats */
+int ivs_gaussian_projection(uint32_t n, float amin, float amax, double zoom, float* proj);
 /* PhaseSpace::PhaseSpace with data == nullptr followed by main()'s initial
  * renormalisation (src/PS/PhaseSpace.cpp:52-65,457-484; src/main.cpp:528-532): n*n floats */
 int ivs_initial_grid(const ivs_derived* d, uint32_t n, double zoom, float* grid);

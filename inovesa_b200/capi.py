@@ -77,10 +77,14 @@ SIGNATURES = {
     "ivs_derive": (ci, [C.POINTER(RingParams), C.POINTER(Derived)]),
     "ivs_rf_kick_offsets": (ci, [C.POINTER(RingParams), C.POINTER(Derived), _fp]),
     "ivs_drift_offsets": (ci, [C.POINTER(RingParams), C.POINTER(Derived), _fp]),
+    "ivs_rf_kick_linear": (ci, [u32, cf, cf, cf, cf, cf, _fp]),
+    "ivs_rf_kick_sine": (ci, [u32, cf, cf, cf, cf, cf, cf, cf, cf, cf, cf, _fp]),
+    "ivs_drift_slip": (ci, [u32, cf, cf, cf, cf, cf, _fp, u32, cf, _fp]),
     "ivs_make_impedance": (ci, [sz, cf, cd, cd, cd, ci, cd, cd, cd, _fp, C.POINTER(ci)]),
     "ivs_wake_impedance": (ci, [C.POINTER(RingParams), C.POINTER(Derived), _fp, C.POINTER(ci)]),
     "ivs_radiation_impedance": (ci, [C.POINTER(RingParams), C.POINTER(Derived), _fp]),
     "ivs_initial_grid": (ci, [C.POINTER(Derived), u32, cd, _fp]),
+    "ivs_gaussian_projection": (ci, [u32, cf, cf, cd, _fp]),
     "ivs_airy": (ci, [cd] + [C.POINTER(cd)] * 4),
 }
 

@@ -290,32 +290,61 @@ int ivs_derive(const ivs_ring_params* o, ivs_derived* d) {
     return IVS_OK;
 }
 
-// src/SM/RFKickMap.cpp:15-83
+// RFKickMap's linear constructor + _calcKick (src/SM/RFKickMap.cpp:15-33,59-68) with the
+// constructor's own arguments; bl = "Meter" scale of the x axis
+int ivs_rf_kick_linear(uint32_t n, float qmin, float qmax, float bl, float angle, float f_RF, float* offset) {
+    if (!offset || n < 2) return IVS_ERR_INVALID_ARGUMENT;
+    const Axis ax0(n, qmin, qmax);
+    const float bl2phase = bl / phys::c * f_RF * kTwoPi;
+    const float syncphase = 0, phase = 0, ampl = 1;
+    const float phaseoffs = syncphase - phase;
+    const float xcenter = ax0.zerobin;
+    for (uint32_t x = 0; x < n; x++) {
+        offset[x] = std::tan(angle) * (xcenter - x);
+        offset[x] += std::tan(angle) * phaseoffs / bl2phase / ax0.delta;
+        offset[x] *= ampl;
+    }
+    return IVS_OK;
+}
+
+// RFKickMap's sine constructor + _calcKick (src/SM/RFKickMap.cpp:35-57,69-80); dE = "ElectronVolt"
+// scale of the y axis
+int ivs_rf_kick_sine(uint32_t n, float qmin, float qmax, float pmin, float pmax, float bl, float dE,
+                     float revolutionpart, float V_RF, float f_RF, float V0, float* offset) {
+    if (!offset || n < 2) return IVS_ERR_INVALID_ARGUMENT;
+    const Axis ax0(n, qmin, qmax), ax1(n, pmin, pmax);
+    const float bl2phase = bl / phys::c * f_RF * kTwoPi;
+    const float syncphase = std::asin(V0 / V_RF);
+    const float phase = syncphase, ampl = 1;
+    for (uint32_t x = 0; x < n; x++) {
+        offset[x] = revolutionpart * (-ampl * V_RF * std::sin(ax0.at(x) * bl2phase + phase) + V0) /
+                    ax1.delta / dE;
+    }
+    return IVS_OK;
+}
+
+// src/SM/RFKickMap.cpp:15-83 from the ring parameters
 int ivs_rf_kick_offsets(const ivs_ring_params* o, const ivs_derived* d, float* offset) {
     if (!o || !d || !offset) return IVS_ERR_INVALID_ARGUMENT;
     const uint32_t n = o->grid_size;
-    const Axis ax0(n, d->qmin, d->qmax), ax1(n, d->pmin, d->pmax);
     const float f_RF = d->f_RF;
-    const float bl2phase = d->bl_f / phys::c * f_RF * kTwoPi;
-    if (o->linear_rf) {
-        const float angle = d->angle;
-        const float syncphase = 0, phase = 0, ampl = 1;
-        const float phaseoffs = syncphase - phase;
-        const float xcenter = ax0.zerobin;
-        for (uint32_t x = 0; x < n; x++) {
-            offset[x] = std::tan(angle) * (xcenter - x);
-            offset[x] += std::tan(angle) * phaseoffs / bl2phase / ax0.delta;
-            offset[x] *= ampl;
+    if (o->linear_rf) return ivs_rf_kick_linear(n, d->qmin, d->qmax, d->bl_f, d->angle, f_RF, offset);
+    // main() passes V_eff as V_RF (src/main.cpp:646)
+    return ivs_rf_kick_sine(n, d->qmin, d->qmax, d->pmin, d->pmax, d->bl_f, d->dE_f, (float)d->revolutionpart,
+                            (float)d->V_eff, f_RF, (float)d->V0, offset);
+}
+
+// DriftMap::DriftMap (src/SM/DriftMap.cpp:21-30) with the constructor's own arguments
+int ivs_drift_slip(uint32_t n, float qmin, float qmax, float pmin, float pmax, float dE, const float* slip,
+                   uint32_t nslip, float E0, float* offset) {
+    if (!offset || !slip || n < 2) return IVS_ERR_INVALID_ARGUMENT;
+    const Axis ax0(n, qmin, qmax), ax1(n, pmin, pmax);
+    for (uint32_t y = 0; y < n; y++) {
+        float acc = 0;
+        for (uint32_t i = 0; i < nslip; i++) {
+            acc += slip[i] * ax1.at(y) * std::pow(ax1.at(y) * dE / E0, static_cast<float>(i));
         }
-    } else {
-        const float revolutionpart = d->revolutionpart;
-        const float V_RF = d->V_eff, V0 = d->V0;  // main() passes V_eff as V_RF (src/main.cpp:646)
-        const float syncphase = std::asin(V0 / V_RF);
-        const float phase = syncphase, ampl = 1;
-        for (uint32_t x = 0; x < n; x++) {
-            offset[x] = revolutionpart * (-ampl * V_RF * std::sin(ax0.at(x) * bl2phase + phase) + V0) /
-                        ax1.delta / d->dE_f;
-        }
+        offset[y] = acc / ax0.delta;
     }
     return IVS_OK;
 }
@@ -323,17 +352,8 @@ int ivs_rf_kick_offsets(const ivs_ring_params* o, const ivs_derived* d, float* o
 // src/SM/DriftMap.cpp:21-30 with slip = {angle, a1/a0*angle, a2/a0*angle} (src/main.cpp:663-664)
 int ivs_drift_offsets(const ivs_ring_params* o, const ivs_derived* d, float* offset) {
     if (!o || !d || !offset) return IVS_ERR_INVALID_ARGUMENT;
-    const uint32_t n = o->grid_size;
-    const Axis ax0(n, d->qmin, d->qmax), ax1(n, d->pmin, d->pmax);
     const float E0 = o->E0;
-    for (uint32_t y = 0; y < n; y++) {
-        float acc = 0;
-        for (uint32_t i = 0; i < 3; i++) {
-            acc += d->slip[i] * ax1.at(y) * std::pow(ax1.at(y) * d->dE_f / E0, static_cast<float>(i));
-        }
-        offset[y] = acc / ax0.delta;
-    }
-    return IVS_OK;
+    return ivs_drift_slip(o->grid_size, d->qmin, d->qmax, d->pmin, d->pmax, d->dE_f, d->slip, 3, E0, offset);
 }
 
 // src/SM/FokkerPlanckMap.cpp:31-118, written out as 5 dense weights per row (y-2..y+2)
@@ -462,6 +482,16 @@ int ivs_radiation_impedance(const ivs_ring_params* o, const ivs_derived* d, floa
     if (!o || !d) return IVS_ERR_INVALID_ARGUMENT;
     return ivs_make_impedance(d->padded_bins, d->fmax, d->R_bend, d->f_rev, (o->gap > 0) ? o->gap : -1,
                               1, 0, 0, 0, z, nullptr);
+}
+
+// PhaseSpace::gaus (src/PS/PhaseSpace.cpp:471-484): one projection of the Gaussian start distribution
+int ivs_gaussian_projection(uint32_t n, float amin, float amax, double zoom, float* proj) {
+    if (!proj || n < 2 || !(amin < amax)) return IVS_ERR_INVALID_ARGUMENT;
+    const Axis ax(n, amin, amax);
+    const double zoom2 = zoom * zoom;
+    const float norm = 0.398942280401432677939946059934381868L;
+    for (uint32_t i = 0; i < n; i++) proj[i] = norm * std::exp((-0.5) * ax.at(i) * ax.at(i) / zoom2);
+    return IVS_OK;
 }
 
 // src/PS/PhaseSpace.cpp:52-65,457-484 (Gaussian start distribution, normalised), then the
