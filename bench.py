@@ -42,7 +42,7 @@ f32 = np.float32
 ALGO_BYTES_PER_CELL = 8.0  # one fp32 read + one fp32 write of the grid per step
 # dram__bytes_read.sum + dram__bytes_write.sum of one stream_step_kernel launch on the benchmark
 # batch (8 x 2048^2), from the ncu --set full capture summarised in profiles/ (updated per round)
-TRAFFIC_BYTES_PER_LAUNCH = 236951552  # r1: 141.5 MB read + 95.4 MB written (L2 still holds dirty lines at kernel end)
+TRAFFIC_BYTES_PER_LAUNCH = 236536832  # r1: 141.5 MB read + 95.0 MB written (L2 still holds dirty lines at kernel end)
 
 
 def workload_params(name):
@@ -224,6 +224,30 @@ def run_ours(args):
     e2e_value = cells_per_step * e2e_steps * world / e2e_s
     ctx.check(ctx.lib.ivs_host_free(ctx.h, host_ptr))
 
+    # the same ABI at the reference's out-step cadence (src/main.cpp:961-1033: the host looks at the
+    # simulation every `outstep` = 100 steps): 100 steps, then observables and profile to the host
+    out_steps, out_rounds = 100, max(1, min(5, args.steps // 100))
+    obs = np.zeros((members, 8), f32)
+
+    def outstep_loop(rounds):
+        for _ in range(rounds):
+            ctx.check(ctx.lib.ivs_sim_step(sim.h, out_steps))
+            ctx.check(ctx.lib.ivs_sim_observe(sim.h, obs.reshape(-1)))
+            ctx.check(ctx.lib.ivs_sim_download(sim.h, None, capi._ptr(prof), None, None))
+
+    sim.set_radiation()
+    outstep_loop(1)
+    barrier()
+    t0 = time.perf_counter()
+    outstep_loop(out_rounds)
+    barrier()
+    out_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([out_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out_s = float(t.item())
+    e2e_outstep = cells_per_step * out_steps * out_rounds * world / out_s
+
     single_run = None
     if single is not None:
         single.step(args.warmup)
@@ -253,7 +277,11 @@ def run_ours(args):
             "ensemble_steps_per_s": members * world * args.steps / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": int(prof.nbytes), "steps": e2e_steps,
-                    "what": "ivs_sim_upload_grid (pinned H2D) + ivs_sim_step(1) + profile D2H per step"},
+                    "what": "ivs_sim_upload_grid (pinned H2D) + ivs_sim_step(1) + profile D2H per step",
+                    "at_outstep_cadence": {"value": e2e_outstep, "unit": "cell-updates/s",
+                                           "what": "state resident; per 100 steps (the reference's out-step): "
+                                                   "ivs_sim_step(100) + ivs_sim_observe (sigma_z, sigma_E, CSR "
+                                                   "power) + profile D2H"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if not args.unfused and members == 8 and n == 2048 else None,

@@ -4,7 +4,11 @@
 //   (src/main.cpp:948-1053; maps src/SM/KickMap.cpp:221-266, src/SM/FokkerPlanckMap.cpp:197-211,
 //    projection src/PS/PhaseSpace.cpp:313-321, wake src/PS/ElectricField.cpp:186-253)
 //
-// Data flow per CTA (one tile = TX consecutive rows x of one ensemble member, all N columns y):
+// Three kernels live here: the streaming kernel (stream_step_kernel, further down: the default for
+// grid sizes 256 ... 2048 and what the benchmark runs) and two tile kernels, the first fused
+// versions, kept for other grid sizes and as independent implementations to test against.
+//
+// Data flow of the TILE kernels per CTA (one tile = TX consecutive rows x of one ensemble member, all N columns y):
 //   0. the tile plus the rows the drift will need from below/above (halo HL/HR, derived from
 //      the drift offsets) is staged in shared memory by the TMA engine: one cp.async.bulk per
 //      row (8 KB at N = 2048) completing on an mbarrier; every row keeps PAD zero columns on
@@ -576,10 +580,6 @@ __device__ __forceinline__ float4 lds128_volatile(uint32_t addr) {
                  : "r"(addr)
                  : "memory");
     return v;
-}
-__device__ __forceinline__ void sts128_volatile(uint32_t addr, const float4 v) {
-    asm volatile("st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
 }
 __device__ __forceinline__ int2 lds64i(uint32_t addr) {
     int2 v;
