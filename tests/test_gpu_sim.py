@@ -112,6 +112,8 @@ def _states(capi, ctx, p, flags, steps, members=1, currents=None, particles=None
     dict(grid_size=1024, steps_per_Ts=4000, gap=0.032, wall_conductivity=5.8e7, collimator=0.008),
     dict(grid_size=2048, steps_per_Ts=4000, linear_rf=0, alpha1=2e-4, alpha2=3e-3),
     dict(grid_size=2048, steps_per_Ts=1000),       # multi-cell displacements: wide halos
+    dict(grid_size=768, steps_per_Ts=2000),        # 6 warps per CTA: not a power of two
+    dict(grid_size=1536, steps_per_Ts=4000, linear_rf=0),
     dict(grid_size=128, interpolation=3, derivation=3),
     dict(grid_size=64, interpolation=2, gap=0.0),   # no wake map
     dict(grid_size=96, fp_type=0),

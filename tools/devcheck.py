@@ -35,6 +35,8 @@ CASES = {
     128: dict(grid_size=128),
     256: dict(grid_size=256),
     512: dict(grid_size=512, gap=0.032, bunch_current=300e-6, steps_per_Ts=2000),
+    768: dict(grid_size=768, steps_per_Ts=2000),
+    1536: dict(grid_size=1536, steps_per_Ts=4000, linear_rf=0),
     1024: dict(grid_size=1024, steps_per_Ts=4000, gap=0.032, wall_conductivity=5.8e7, collimator=0.008),
     2048: dict(grid_size=2048, steps_per_Ts=4000, linear_rf=0, alpha1=2e-4, alpha2=3e-3),
     2049: dict(grid_size=2048, steps_per_Ts=1000),
