@@ -135,3 +135,8 @@ IVS_HD ivs_taps ivs_kick_taps(float offset, uint32_t n_kd, uint32_t it) {
 }
 
 static inline uint32_t ivs_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// Opt-in limit of dynamic shared memory per CTA on sm_100 (227 KB).  Kernels that need more than
+// 48 KB are always opted in to this constant, never to the size one plan happens to need:
+// the attribute belongs to the kernel, and two live simulations of different grid sizes share it.
+constexpr int kIvsMaxOptinSmem = 227 * 1024 - 256;  // minus room for a kernel's few static bytes

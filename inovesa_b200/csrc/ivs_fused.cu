@@ -1140,11 +1140,11 @@ ivs_status launch_vec(ivs_ctx* ctx, const fused_args& a, dim3 grid, uint32_t thr
 template <int TX>
 ivs_status set_smem_attr(ivs_ctx* ctx, bool vec, size_t smem) {
     if (vec) {
-        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_kernel<TX, kRG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_kernel<TX, kRG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_kernel<TX, kRG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_kernel<TX, kRG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
     } else {
-        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_generic_kernel<TX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_generic_kernel<TX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_generic_kernel<TX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fused_step_generic_kernel<TX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
     }
     return IVS_OK;
 }
@@ -1280,7 +1280,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             plan->threads = threads_s;
             plan->smem = sb;
             plan->tx = 0;
-            IVS_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+            IVS_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
         }
     }
     // tile height: minimise (rounds of CTAs over the machine) x (rows staged per CTA)

@@ -192,8 +192,8 @@ ivs_status ivs_kick_y_batched(ivs_ctx* ctx, const float* in, float* out, uint32_
                               uint32_t it) {
     const size_t smem = n * sizeof(float);
     if (smem > 48 * 1024) {
-        IVS_CUDA(ctx, cudaFuncSetAttribute(kick_y_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(kick_y_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(kick_y_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(kick_y_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
     }
     return launch(ctx, kick_y_kernel<true>, kick_y_kernel<false>, dim3(n * members), dim3(kThreads),
                   smem, in, out, n, offset, offset_stride, it);
@@ -210,8 +210,8 @@ ivs_status ivs_fokker_planck_batched(ivs_ctx* ctx, const float* in, float* out, 
                                      uint32_t members, const float* w5) {
     const size_t smem = n * sizeof(float);
     if (smem > 48 * 1024) {
-        IVS_CUDA(ctx, cudaFuncSetAttribute(fokker_planck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(fokker_planck_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fokker_planck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(fokker_planck_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
     }
     return launch(ctx, fokker_planck_kernel<true>, fokker_planck_kernel<false>, dim3(n * members),
                   dim3(kThreads), smem, in, out, n, w5);

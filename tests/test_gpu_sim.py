@@ -221,6 +221,23 @@ def test_graph_and_direct_launch_agree(capi, ctx_strict):
         a.close(); b.close()
 
 
+def test_simulations_of_different_sizes_coexist(capi, ctx_strict):
+    """two live simulation objects of different grid sizes share the kernels (and their shared-memory
+    opt-in): stepping them alternately gives the same states as stepping each alone"""
+    pa, pb = kara_params(grid_size=2048, steps_per_Ts=4000), kara_params(grid_size=256)
+    a = capi.Simulation(ctx_strict, pa, 1)
+    b = capi.Simulation(ctx_strict, pb, 1)
+    for _ in range(3):
+        a.step(3)
+        b.step(5)
+    ga, gb = a.download()[0], b.download()[0]
+    a.close(); b.close()
+    a = capi.Simulation(ctx_strict, pa, 1); a.step(9)
+    b = capi.Simulation(ctx_strict, pb, 1); b.step(15)
+    assert np.array_equal(ga, a.download()[0]) and np.array_equal(gb, b.download()[0])
+    a.close(); b.close()
+
+
 def test_ensemble_members_are_independent(capi, ctx_strict):
     """config 4 in miniature: members differ only in bunch current (wake scaling)"""
     p = kara_params(grid_size=64)
