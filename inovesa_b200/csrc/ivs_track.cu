@@ -155,17 +155,21 @@ __device__ __forceinline__ void fp_track_one(float2& p, uint32_t n, const float*
     }
 }
 
-// One thread advances TWO particles (i and i + half) through the four maps: their dependent
-// table look-ups interleave, and in the stochastic mode one Box-Muller transform serves both.
+// One thread advances FOUR particles (i + k * quarter, k = 0..3) through the four maps: their
+// dependent table look-ups interleave (the kernel is latency bound: three gathers in a row per
+// particle), the launch is less than one wave of CTAs, and in the stochastic mode one Box-Muller
+// transform serves two particles.
 // The stochastic mode keys its generator on a step counter that lives on the DEVICE
 // (counter[0..1] = step as 64 bit, counter[2] = blocks finished), so that a replayed CUDA graph
 // still draws fresh numbers every step: every block reads the step when it starts, the last block
 // to finish advances it.
-__global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ particles, uint32_t np, uint32_t half,
+constexpr int kTrackPerThread = 4;
+__global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ particles, uint32_t np, uint32_t quarter,
                                   uint32_t n, const float* __restrict__ wake, const float* __restrict__ rf,
                                   const float* __restrict__ drift, const float* __restrict__ w5,
                                   const float* __restrict__ grid, uint32_t fptrack, float e1,
                                   float sigma, uint64_t seed, unsigned int* counter) {
+    constexpr int P = kTrackPerThread;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t member = blockIdx.y;
     const bool stochastic = w5 && fptrack == 3;
@@ -177,40 +181,48 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
         }
         __syncthreads();
     }
-    if (i < half) {
-        const uint32_t j = i + half;
-        const bool two = j < np;
+    if (i < quarter) {
         float2* base = particles + (size_t)member * np;
-        float2 p = base[i];
-        float2 q = two ? base[j] : p;
+        float2 p[P];
+        bool on[P];
+#pragma unroll
+        for (int k = 0; k < P; k++) {
+            const uint32_t j = i + k * quarter;
+            on[k] = j < np;
+            p[k] = base[on[k] ? j : i];
+        }
         if (wake) {
             const float* wm = wake + (size_t)member * n;
-            kick_one(p.y, p.x, wm, n);
-            kick_one(q.y, q.x, wm, n);
+#pragma unroll
+            for (int k = 0; k < P; k++) kick_one(p[k].y, p[k].x, wm, n);
         }
-        kick_one(p.y, p.x, rf, n);
-        kick_one(q.y, q.x, rf, n);
-        kick_one(p.x, p.y, drift, n);
-        kick_one(q.x, q.y, drift, n);
+#pragma unroll
+        for (int k = 0; k < P; k++) kick_one(p[k].y, p[k].x, rf, n);
+#pragma unroll
+        for (int k = 0; k < P; k++) kick_one(p[k].x, p[k].y, drift, n);
         if (w5 && (fptrack == 1 || fptrack == 2)) {
             const float* gm = grid ? grid + (size_t)member * n * n : nullptr;
-            fp_track_one(p, n, w5, gm, fptrack);
-            fp_track_one(q, n, w5, gm, fptrack);
+#pragma unroll
+            for (int k = 0; k < P; k++) fp_track_one(p[k], n, w5, gm, fptrack);
         } else if (stochastic) {
             // pos.y -= pos.y*e1 + N(0, sqrt(2 e1)/dp)   (src/SM/FokkerPlanckMap.cpp:264-266); the
             // reference draws from an unseeded mt19937, here a counter-based generator keyed on
-            // (seed, step, member, pair): reproducible run to run
-            const uint64_t h = mix64(skey + ((uint64_t)member << 32) + i);
-            const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
-            const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
-            const float r = sqrtf(-2.0f * __logf(u1));
-            float sn, cs;
-            __sincosf(6.2831853071795864f * u2, &sn, &cs);
-            p.y = IVS_SUB(p.y, IVS_ADD(IVS_MUL(p.y, e1), IVS_MUL(sigma, r * cs)));
-            q.y = IVS_SUB(q.y, IVS_ADD(IVS_MUL(q.y, e1), IVS_MUL(sigma, r * sn)));
+            // (seed, step, member, thread, pair): reproducible run to run
+#pragma unroll
+            for (int k = 0; k < P; k += 2) {
+                const uint64_t h = mix64(skey + ((uint64_t)member << 32) + ((uint64_t)k << 28) + i);
+                const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
+                const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+                const float r = sqrtf(-2.0f * __logf(u1));
+                float sn, cs;
+                __sincosf(6.2831853071795864f * u2, &sn, &cs);
+                p[k].y = IVS_SUB(p[k].y, IVS_ADD(IVS_MUL(p[k].y, e1), IVS_MUL(sigma, r * cs)));
+                p[k + 1].y = IVS_SUB(p[k + 1].y, IVS_ADD(IVS_MUL(p[k + 1].y, e1), IVS_MUL(sigma, r * sn)));
+            }
         }
-        base[i] = p;
-        if (two) base[j] = q;
+#pragma unroll
+        for (int k = 0; k < P; k++)
+            if (on[k]) base[i + k * quarter] = p[k];
     }
     if (stochastic) {
         __syncthreads();  // every thread of the block has used skey
@@ -232,10 +244,10 @@ ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, ui
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
                                  float dp, uint64_t seed, unsigned int* step_counter) {
     if (np == 0) return IVS_OK;
-    const uint32_t half = (np + 1) / 2;
+    const uint32_t quarter = ivs_div_up(np, kTrackPerThread);
     const float sigma = sqrtf(2.0f * e1) / dp;  // uniform, in the reference's fp32 operations
-    track_step_kernel<<<dim3(ivs_div_up(half, 256), members), 256, 0, ctx->stream>>>(
-        (float2*)particles, np, half, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, sigma, seed,
+    track_step_kernel<<<dim3(ivs_div_up(quarter, 256), members), 256, 0, ctx->stream>>>(
+        (float2*)particles, np, quarter, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, sigma, seed,
         step_counter);
     IVS_LAUNCHED(ctx);
     return IVS_OK;
