@@ -1219,49 +1219,53 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         const uint32_t H = plan->halo_lo + plan->halo_hi;
         const uint32_t threads_s = n / 4;
         const uint32_t pitch = n + 2 * kPadS;
-        const uint32_t max_strip = std::min<uint32_t>(n, 128);
-        const uint32_t max_rin = max_strip + H;
-        const uint32_t wcount = n + ((max_rin + 63) & ~63u);
-        const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
         auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-        const size_t fixed = a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) + a16((size_t)NW * max_rin * 8) +
-                             a16((size_t)max_strip * NW * 4) + a16((size_t)(max_rin + 1) * 48) +
-                             a16((size_t)NW * 2 * kMailSlots * 16);
         const bool fma = ctx->arith == IVS_ARITH_FMA;
         const void* kfn = fma ? (const void*)stream_step_kernel<true> : (const void*)stream_step_kernel<false>;
         cudaFuncAttributes fa;
         IVS_CUDA(ctx, cudaFuncGetAttributes(&fa, kfn));
         const uint32_t regs_thread = (std::max(fa.numRegs, 32) + 7) & ~7;
-        const uint32_t by_regs = std::max<uint32_t>(1, 65536u / (regs_thread * threads_s));
-        uint32_t want = std::min<uint32_t>(by_regs, 16);  // CTAs per SM the registers allow
-        uint32_t K = 0;
-        size_t sb = 0;
+        const uint32_t by_regs = std::max<uint32_t>(1, 65536u / (regs_thread * threads_s));  // CTAs per SM
         // ring depth: the warps' windows start up to H rows apart, plus rows in flight; the
         // mailboxes (kMailSlots deep) bound it from above
         const uint32_t kmin = H + 4, kmax = kMailSlots - 8;
-        for (; want >= 1 && kmin <= kmax; want--) {
-            const size_t budget = (size_t)227 * 1024 / want - 1024;  // 1 KB per CTA is reserved by the system
-            if (budget < fixed + (size_t)kmin * (pitch * 4 + 16)) continue;
-            K = (uint32_t)std::min<size_t>(std::min(kmin + 12, kmax), (budget - fixed) / ((size_t)pitch * 4 + 16));
-            sb = a16((size_t)K * pitch * 4) + fixed + 2 * a16((size_t)K * 8);
-            if (sb <= budget) break;
-            K = 0;
-        }
-        if (K >= kmin) {
-            const uint32_t per_sm = want;
-            // strips per member: minimise rounds x (rows through the pipeline per CTA + set-up)
-            uint64_t best = ~0ull;
-            uint32_t bestP = 1;
-            for (uint32_t P = 1; P <= n / 8; P++) {
-                const uint32_t S0 = ivs_div_up(n, P);
-                if ((uint64_t)S0 * (P - 1) >= n) continue;  // last strip would be empty
-                if (S0 > max_strip) continue;
-                const uint64_t units = (uint64_t)P * s->members;
-                const uint64_t slots = (uint64_t)ctx->sm_count * per_sm;
-                const uint64_t rounds = (units + slots - 1) / slots;
-                const uint64_t cost = rounds * (S0 + H + 16);  // set-up ~ 16 rows' worth of time
-                if (cost < best) { best = cost; bestP = P; }
+        // Search over the strip length S0 = ceil(n / P): the per-row tables in shared memory are sized
+        // for the strip, so shorter strips leave room for more CTAs per SM (small grids) while longer
+        // ones amortise the set-up and the halo rows.  Cost = rounds of CTAs over the machine x (rows
+        // through the pipeline per CTA + a set-up worth ~16 rows), scaled by how well the resident
+        // warps fill the four schedulers (16 warps per SM saturate this kernel).
+        double best = 1e300;
+        uint32_t bestP = 0, bestK = 0, best_rin = 0;
+        size_t best_sb = 0, best_wwin = 0;
+        for (uint32_t P = 1; P <= n / 8 && kmin <= kmax; P++) {
+            const uint32_t S0 = ivs_div_up(n, P);
+            if ((uint64_t)S0 * (P - 1) >= n || S0 > 128) continue;  // last strip empty / table cap
+            const uint32_t max_rin = S0 + H;
+            const uint32_t wcount = n + ((max_rin + 63) & ~63u);
+            const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
+            const size_t fixed = a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) + a16((size_t)NW * max_rin * 8) +
+                                 a16((size_t)S0 * NW * 4) + a16((size_t)(max_rin + 1) * 48) +
+                                 a16((size_t)NW * 2 * kMailSlots * 16);
+            uint32_t want = std::min<uint32_t>(by_regs, 16), K = 0;
+            size_t sb = 0;
+            for (; want >= 1; want--) {
+                const size_t budget = (size_t)227 * 1024 / want - 1024;  // 1 KB per CTA is reserved by the system
+                if (budget < fixed + (size_t)kmin * (pitch * 4 + 16)) continue;
+                K = (uint32_t)std::min<size_t>(std::min(kmin + 12, kmax), (budget - fixed) / ((size_t)pitch * 4 + 16));
+                sb = a16((size_t)K * pitch * 4) + fixed + 2 * a16((size_t)K * 8);
+                if (sb <= budget && K >= kmin) break;
+                K = 0;
             }
+            if (K < kmin) continue;
+            const uint64_t units = (uint64_t)P * s->members;
+            const uint64_t slots = (uint64_t)ctx->sm_count * want;
+            const uint64_t rounds = (units + slots - 1) / slots;
+            const uint32_t resident = (uint32_t)std::min<uint64_t>(want, ivs_div_up((uint32_t)units, ctx->sm_count));
+            const double fill = std::min(1.0, resident * (threads_s / 32) / 16.0);  // of 16 warps per SM
+            const double cost = (double)rounds * (S0 + H + 16) * resident / std::max(fill, 1.0 / 16);
+            if (cost < best) { best = cost; bestP = P; bestK = K; best_sb = sb; best_rin = max_rin; best_wwin = wwin_len; }
+        }
+        if (bestP) {
             // Fokker-Planck weights with the taps that fall outside the grid zeroed: the shuffles
             // deliver a lane's own value there instead of the tile kernels' zero pad
             std::vector<float> fps(fpw);
@@ -1273,12 +1277,12 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             IVS_CUDA(ctx, cudaMemcpy(plan->fp5, fps.data(), (size_t)n * 20, cudaMemcpyHostToDevice));
             plan->stream = true;
             plan->strip = ivs_div_up(n, bestP);
-            plan->kslots = K;
-            plan->max_strip = max_strip;
-            plan->max_rin = max_rin;
-            plan->wwin_len = wwin_len;
+            plan->kslots = bestK;
+            plan->max_strip = plan->strip;
+            plan->max_rin = best_rin;
+            plan->wwin_len = (uint32_t)best_wwin;
             plan->threads = threads_s;
-            plan->smem = sb;
+            plan->smem = best_sb;
             plan->tx = 0;
             IVS_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
         }
