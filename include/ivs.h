@@ -244,6 +244,12 @@ ivs_status ivs_sim_set_radiation(ivs_sim* sim, const float* rad_impedance, float
                                  float cutoff);
 /* PhaseSpace::integrateAndNormalize (main.cpp:953-956) on every member */
 ivs_status ivs_sim_renormalize(ivs_sim* sim);
+/* Replace the RF kick offsets (n floats) before the next step: the hook DynamicRFKickMap needs
+ * (src/SM/DynamicRFKickMap.cpp:80-109 re-draws phase and amplitude and recomputes KickMap::_offset
+ * on the host every apply()).  Takes effect for all following steps, also inside replayed graphs
+ * (the device tables are updated in place).  IVS_ERR_HALO if a displacement exceeds what the
+ * fused kernel stages. */
+ivs_status ivs_sim_set_rf_offset(ivs_sim* sim, const float* rf_offset);
 
 #ifdef __cplusplus
 }

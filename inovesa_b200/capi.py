@@ -72,6 +72,7 @@ SIGNATURES = {
     "ivs_sim_observe": (ci, [P, _fp]),
     "ivs_sim_set_radiation": (ci, [P, _fp, cf, cf]),
     "ivs_sim_renormalize": (ci, [P]),
+    "ivs_sim_set_rf_offset": (ci, [P, _fp]),
     # include/ivs_host.h
     "ivs_default_params": (None, [C.POINTER(RingParams)]),
     "ivs_derive": (ci, [C.POINTER(RingParams), C.POINTER(Derived)]),
@@ -518,6 +519,12 @@ class Simulation:
 
     def renormalize(self):
         self.ctx.check(self.lib.ivs_sim_renormalize(self.h))
+
+    def set_rf_offset(self, rf):
+        """new RF kick offsets for the following steps (the DynamicRFKickMap hook)"""
+        rf = np.ascontiguousarray(rf, f32)
+        assert rf.shape == (self.n,)
+        self.ctx.check(self.lib.ivs_sim_set_rf_offset(self.h, rf))
 
     @property
     def steps_done(self):

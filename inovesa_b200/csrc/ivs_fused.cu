@@ -1341,6 +1341,24 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
     return IVS_OK;
 }
 
+ivs_status ivs_fused_plan_set_rf(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s, const float* rf_offset) {
+    if (!plan->ready) return ivs_fail(ctx, IVS_ERR_UNSUPPORTED, "fused plan missing");
+    const uint32_t n = s->n;
+    std::vector<int> rf_first(n);
+    std::vector<float4> rf_w(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const ivs_taps t = ivs_kick_taps(rf_offset[i], n, s->it);  // KickMap::updateSM arithmetic
+        if (t.first < -kPad || t.first > kPad - 4)
+            return ivs_fail(ctx, IVS_ERR_HALO, "RF kick displacement exceeds the fused kernel's staged pad: pass IVS_SIM_UNFUSED");
+        rf_first[i] = t.first;
+        rf_w[i] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+    }
+    IVS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // steps in flight still read the old tables
+    IVS_CUDA(ctx, cudaMemcpy(plan->rf_first, rf_first.data(), n * 4, cudaMemcpyHostToDevice));
+    IVS_CUDA(ctx, cudaMemcpy(plan->rf_w, rf_w.data(), n * 16, cudaMemcpyHostToDevice));
+    return IVS_OK;
+}
+
 void ivs_fused_plan_destroy(ivs_fused_plan* plan) {
     void** bufs[] = {&plan->rf_first, &plan->rf_w, &plan->dr_first, &plan->dr_w, &plan->fp_base, &plan->fp_w, &plan->fp5};
     for (void** b : bufs) {

@@ -56,3 +56,5 @@ struct ivs_fused_plan {
 ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan);
 void ivs_fused_plan_destroy(ivs_fused_plan* plan);
 ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s);
+// new RF kick offsets: rebuild the fused kernels' tap tables in place (same device buffers)
+ivs_status ivs_fused_plan_set_rf(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s, const float* rf_offset);

@@ -400,4 +400,15 @@ ivs_status ivs_sim_renormalize(ivs_sim* s) {
     return ivs_normalize_batched(ctx, s->grid[s->cur], s->n, s->members, 1.0f, s->integral);
 }
 
+ivs_status ivs_sim_set_rf_offset(ivs_sim* s, const float* rf_offset) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_REQUIRE(ctx, rf_offset != nullptr, "ivs_sim_set_rf_offset: null pointer");
+    IVS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!(s->desc.flags & IVS_SIM_UNFUSED)) IVS_TRY(ivs_fused_plan_set_rf(ctx, &s->plan, s, rf_offset));
+    // the stream orders the copy after the steps already enqueued; the host array is consumed here
+    IVS_TRY(ivs_upload(ctx, s->rf, rf_offset, s->n * sizeof(float)));
+    return ivs_sync(ctx);
+}
+
 }  // extern "C"

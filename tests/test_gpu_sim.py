@@ -330,6 +330,39 @@ def test_above_threshold_statistics_match_oracle(capi, ctx_fma, oracle):
     osim.close()
 
 
+def test_rf_offsets_can_change_between_steps(capi, ctx_strict, oracle):
+    """the DynamicRFKickMap hook (src/SM/DynamicRFKickMap.cpp:80-109: new KickMap::_offset every
+    step): a simulation whose RF offsets are replaced half way equals the oracle run with the
+    first table followed by the oracle run with the second one, on all three step paths"""
+    p = kara_params(grid_size=256)
+    p2 = kara_params(grid_size=256, steps_per_Ts=800)  # a different rotation angle -> different RF table
+    o1 = oracle.sim(p)
+    t1 = o1.tables()
+    o1.step(12)
+    mid = o1.get()[0].copy()
+    o1.close()
+    o2 = oracle.sim(p2)
+    rf2 = o2.tables()["rf"].copy()
+    o2.close()
+    # reference continuation: same drift / FP / wake tables, new RF offsets, from the mid state
+    for flags in (0, capi.SIM_TILED, capi.SIM_UNFUSED):
+        tabs = dict(rf=t1["rf"], drift=t1["drift"], fp5=t1["fp5"], zwake=t1["zwake"])
+        a = capi.Simulation(ctx_strict, p, 1, flags=flags, tables=tabs)
+        a.step(12)
+        assert rel_l1(a.download()[0][0], mid) < 1e-6
+        a.set_rf_offset(rf2)
+        a.step(12)
+        b = capi.Simulation(ctx_strict, p, 1, flags=flags, tables=dict(rf=rf2, drift=t1["drift"], fp5=t1["fp5"], zwake=t1["zwake"]))
+        b.upload_grid(mid[None])
+        b.step(12)
+        assert rel_l1(a.download()[0][0], b.download()[0][0]) < 1e-6
+        a.close(); b.close()
+    with pytest.raises(capi.IvsError) as e:
+        c = capi.Simulation(ctx_strict, p, 1)
+        c.set_rf_offset(np.full(256, 40.0, f32))
+    assert e.value.code == capi.ERR_HALO
+
+
 def test_invalid_descriptors(capi, ctx_strict):
     p = kara_params(grid_size=4)
     with pytest.raises(capi.IvsError) as e:
