@@ -291,6 +291,11 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": cells_per_step * ALGO_BYTES_PER_CELL},
             "clocks": clocks,
         }
+        # BASELINE.json also asks for the reference's OpenCL path on the B200 "if an ICD is present":
+        # building it needs OpenCL headers and clFFT, neither of which exists in this image
+        icd = os.path.isdir("/etc/OpenCL/vendors") and bool(os.listdir("/etc/OpenCL/vendors"))
+        line["reference_opencl"] = ("not available: %s, and no OpenCL headers / clFFT to build the reference's "
+                                    "OpenCL path with" % ("an ICD is registered" if icd else "no OpenCL ICD registered"))
         if single_run:
             line["single_run"] = single_run
         if cpu:
