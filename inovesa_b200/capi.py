@@ -13,7 +13,8 @@ import numpy as np
 from .params import Derived, RingParams, SimDesc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libivs.so")
+# IVS_LIB: another build of the same library (A/B timing of kernel variants, tools/ab.sh)
+LIB_PATH = os.environ.get("IVS_LIB") or os.path.join(HERE, "lib", "libivs.so")
 f32 = np.float32
 
 IVS_OK = 0

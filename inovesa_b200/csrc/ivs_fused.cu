@@ -626,7 +626,8 @@ __device__ __forceinline__ void sts128_volatile_if(uint32_t addr, const float4 v
 // `p` is the shared address of in[y0 + a], a = (f1+f2) rounded down to a multiple of 4, RR the rest;
 // m0 = y0 + f2 is the first wake-kicked column the quad needs.
 template <bool FMA, int RR>
-__device__ __forceinline__ float4 kick_quad_rr(uint32_t p, int m0, uint32_t n, const float4 w1, const float4 w2) {
+__device__ __forceinline__ float4 kick_quad_rr(uint32_t p, int m0, uint32_t n, bool near_edge, const float4 w1,
+                                               const float4 w2) {
     float in[16];
     {
         const float4 A = lds128(p), B = lds128(p + 16), C = lds128(p + 32);
@@ -641,7 +642,9 @@ __device__ __forceinline__ float4 kick_quad_rr(uint32_t p, int m0, uint32_t n, c
     float k1[7];
 #pragma unroll
     for (int i = 0; i < 7; i++) k1[i] = tap4<FMA>(in[RR + i], in[RR + i + 1], in[RR + i + 2], in[RR + i + 3], w1);
-    if ((uint32_t)m0 > n - 7) {  // some of m0 .. m0+6 lie outside the grid: the wake-kicked grid is 0 there
+    // some of m0 .. m0+6 lie outside the grid: the wake-kicked grid is 0 there.  near_edge is a
+    // per-warp constant (only the first and the last warp of a row can get there)
+    if (near_edge && (uint32_t)m0 > n - 7) {
 #pragma unroll
         for (int i = 0; i < 7; i++)
             if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
@@ -654,14 +657,15 @@ __device__ __forceinline__ float4 kick_quad_rr(uint32_t p, int m0, uint32_t n, c
     return o;
 }
 template <bool FMA>
-__device__ __forceinline__ float4 kick_quad(uint32_t row_q, int fsum, int m0, uint32_t n, const float4 w1, const float4 w2) {
+__device__ __forceinline__ float4 kick_quad(uint32_t row_q, int fsum, int m0, uint32_t n, bool near_edge, const float4 w1,
+                                            const float4 w2) {
     const int a = fsum & ~3;  // floor to a multiple of 4 (two's complement: also for negatives)
     const uint32_t p = row_q + (uint32_t)(a * 4);
     switch (fsum - a) {
-    case 0: return kick_quad_rr<FMA, 0>(p, m0, n, w1, w2);
-    case 1: return kick_quad_rr<FMA, 1>(p, m0, n, w1, w2);
-    case 2: return kick_quad_rr<FMA, 2>(p, m0, n, w1, w2);
-    default: return kick_quad_rr<FMA, 3>(p, m0, n, w1, w2);
+    case 0: return kick_quad_rr<FMA, 0>(p, m0, n, near_edge, w1, w2);
+    case 1: return kick_quad_rr<FMA, 1>(p, m0, n, near_edge, w1, w2);
+    case 2: return kick_quad_rr<FMA, 2>(p, m0, n, near_edge, w1, w2);
+    default: return kick_quad_rr<FMA, 3>(p, m0, n, near_edge, w1, w2);
     }
 }
 
@@ -718,11 +722,10 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         }
     };
 
-    if (tid == 0) {
-        for (uint32_t s = 0; s < K; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NW);
-        }
+    if (tid < K) {  // one thread per slot; a single fence covers both initialisations
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_b + tid * 8), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_b + tid * 8), "r"(NW));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ---- per-thread constants, requested early: drift taps, Fokker-Planck and Simpson weights
     const uint32_t q = tid;  // this thread's quad of columns, y = 4q .. 4q+3
@@ -746,9 +749,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     }
     const float4 ws4 = __ldg(reinterpret_cast<const float4*>(g.ws) + q);
     __syncthreads();
-    if (tid == 0) {
-        for (uint32_t r = 0; r < min(K, RIN); r++) issue_row(r, r);  // the first ring-full flies during the set-up
-    }
+    if (tid < min(K, RIN)) issue_row(tid, tid);  // the first ring-full flies during the set-up
 
     // ---- set-up: zero pads (and slots of rows outside the grid, whose stale contents would
     // otherwise meet the zero weights as NaN * 0), mailboxes, last step's profile and the
@@ -762,6 +763,14 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         }
     }
     for (uint32_t i = tid; i < NW * 2 * kMailSlots; i += T) mail[i] = make_float4(0, 0, 0, 0);  // seq 0 = nothing posted
+    // static part of the per-row table (RF taps), requested before the wake potential is formed
+    for (uint32_t r = tid; r < RIN; r += T) {
+        const int x = xs + (int)r;
+        const bool valid = (uint32_t)x < n;
+        const int f2 = valid ? __ldg(&g.rf_first[x]) : -1;
+        tab[3 * r + 1] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
+        tab[3 * r + 2] = make_float4(0.0f, __int_as_float(f2), 0.0f, 0.0f);
+    }
     if (g.has_wake) {
         // all loads first, then the stores: one round trip to L2 instead of one per element
         // (T = n/4 threads: 4 profile entries and at most 5 window entries each)
@@ -851,10 +860,9 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
                 }
                 if (r >= hl && r < hl + S) g.wake_out[(size_t)member * n + x] = wk;
             }
-            const int f2 = valid ? __ldg(&g.rf_first[x]) : -1;
+            const int f2 = __float_as_int(tab[3 * r + 2].y);
             tab[3 * r] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
-            tab[3 * r + 1] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
-            tab[3 * r + 2] = make_float4(__int_as_float(t.first + f2), __int_as_float(f2), 0.0f, 0.0f);
+            tab[3 * r + 2].x = __int_as_float(t.first + f2);
         }
         if (tid == 0) tab[3 * RIN + 2] = make_float4(__int_as_float(-2), __int_as_float(-1), 0.0f, 0.0f);  // read ahead, never used
     }
@@ -942,9 +950,14 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         uint32_t aload = ring_q + (r0 % K) * pitchB;
         uint32_t tp = smem_u32(tab) + r0 * 48;
         int2 f = lds64i(tp + 32);
-        float4 A[NT];
+        // drift as running sums: P[j] is the output row that has taken j + 1 of its NT taps so far.
+        // A kicked row k feeds tap NT-1 of the oldest sum (which completes it), tap NT-2 of the next,
+        // ..., and starts a new one with tap 0 -- the same products added in the same order as a
+        // 4-tap sum over a window of rows, without the window (and its register moves).
+        float4 P[NT - 1];
 #pragma unroll
-        for (int t = 0; t < NT; t++) A[t] = make_float4(0, 0, 0, 0);
+        for (int t = 0; t < NT - 1; t++) P[t] = make_float4(0, 0, 0, 0);
+        const bool near_edge = __any_sync(0xffffffffu, y0 < 16 || y0 + 19 > (int)n);
         // cursor: full[] entry of the staged row the next kick reads and its phase; empty[] sits eoff behind
         uint32_t kbar = full_b + (r0 % K) * 8, kpar = (r0 / K) & 1;
         const uint32_t full_end = full_b + K * 8, eoff = empty_b - full_b;
@@ -972,19 +985,16 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             const bool duty = it >= pwin;
             if (duty) duty_probe();
             const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
-#pragma unroll
-            for (int t = 0; t + 1 < NT; t++) A[t] = A[t + 1];
-            A[NT - 1] = kick_quad<FMA>(aload, f.x, y0 + f.y, n, w1, w2);
+            const float4 kq = kick_quad<FMA>(aload, f.x, y0 + f.y, n, near_edge, w1, w2);
             tp += 48;
             f = lds64i(tp + 32);  // next row's entry, a row ahead of its use
             aload += pitchB;
             if (aload == ring_end) aload = ring_q;
             {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
-                float v;
-#define IVS_DRIFT_COL(c, m)                                                             \
-                v = __fmul_rn(A[0].m, dw[c][0]);                                        \
-                _Pragma("unroll") for (int t = 1; t < NT; t++) v = madd<FMA>(A[t].m, dw[c][t], v); \
-                d.m = v;
+#define IVS_DRIFT_COL(c, m)                                                                           \
+                d.m = madd<FMA>(kq.m, dw[c][NT - 1], P[NT - 2].m);                                    \
+                _Pragma("unroll") for (int t = NT - 2; t > 0; t--) P[t].m = madd<FMA>(kq.m, dw[c][t], P[t - 1].m); \
+                P[0].m = __fmul_rn(kq.m, dw[c][0]);
                 IVS_DRIFT_COL(0, x)
                 IVS_DRIFT_COL(1, y)
                 IVS_DRIFT_COL(2, z)
