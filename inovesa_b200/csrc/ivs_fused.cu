@@ -552,7 +552,12 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
 // (same taps, same order, same summation tree of the profile).
 
 constexpr int kPadS = 32;     // zero columns each side of a staged row: two kicks of up to 16 cells
-constexpr int kMailSlots = 32; // mailbox depth per warp edge (> ring slots + 6, see the hand-back rule)
+constexpr int kMailSlots = 32; // mailbox depth per warp edge (> ring slots + kLag + 5, see the hand-back rule)
+#ifndef IVS_LAG
+#define IVS_LAG 4
+#endif
+constexpr int kLag = IVS_LAG;        // drifted rows wait this many iterations (in a per-thread FIFO in shared memory)
+                               // for their Fokker-Planck step: the slack between neighbouring warps
 
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -703,6 +708,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     // per input row: wake taps, RF taps, (f1 + f2, f2, -, -)
     float4* tab = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 48));
     float4* mail = reinterpret_cast<float4*>(carve((size_t)NW * 2 * kMailSlots * 16)); // [warp][side][slot] = (a, b, seq, -)
+    float4* fifo = reinterpret_cast<float4*>(carve((size_t)kLag * T * 16));            // [slot][thread] drifted quads
     uint64_t* full = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
     uint64_t* empty = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
 
@@ -748,6 +754,29 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             for (int k = 0; k < 5; k++) w5[c][k] = t[c * 5 + k];
     }
     const float4 ws4 = __ldg(reinterpret_cast<const float4*>(g.ws) + q);
+    // last step's profile and the first batch of the wake-function window are requested in the same
+    // round trip (T = n/4 threads: 4 profile entries and 5 window entries each)
+    // w[x - x'] is stored at table index x - x' + n - 1; window entry t holds the table entry
+    // xs + t, so row r and x' meet at t = r - x' + n - 1
+    const int wtop = (int)(2 * n - 1);
+    const uint32_t tcount = n + ((RIN + 63) & ~63u);  // <= 5 T for n >= 1024
+    float rv[4];
+    double wv0[5];
+    // ... and so is the static part (RF taps) of this thread's first entry of the per-row table
+    int pre_f2 = -1;
+    float4 pre_w2 = make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
+    if (tid < RIN && (uint32_t)(xs + (int)tid) < n) {
+        pre_f2 = __ldg(&g.rf_first[xs + (int)tid]);
+        pre_w2 = __ldg(&g.rf_w[xs + (int)tid]);
+    }
+    if (g.has_wake) {
+        const float* rin = g.rho_in + (size_t)member * n;
+#pragma unroll
+        for (int k = 0; k < 4; k++) rv[k] = __ldg(rin + tid + k * T);
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+            wv0[k] = __ldg(g.wakefn + min(max(xs + (int)(tid + k * T), 0), wtop));  // clamped entries belong to rows outside the grid
+    }
     __syncthreads();
     if (tid < min(K, RIN)) issue_row(tid, tid);  // the first ring-full flies during the set-up
 
@@ -763,31 +792,30 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         }
     }
     for (uint32_t i = tid; i < NW * 2 * kMailSlots; i += T) mail[i] = make_float4(0, 0, 0, 0);  // seq 0 = nothing posted
-    // static part of the per-row table (RF taps), requested before the wake potential is formed
-    for (uint32_t r = tid; r < RIN; r += T) {
+    // static part of the per-row table (RF taps), in place before the wake potential is formed
+    if (tid < RIN) {
+        tab[3 * tid + 1] = pre_w2;
+        tab[3 * tid + 2] = make_float4(0.0f, __int_as_float(pre_f2), 0.0f, 0.0f);
+    }
+    for (uint32_t r = tid + T; r < RIN; r += T) {  // small grids: strips longer than the block
         const int x = xs + (int)r;
         const bool valid = (uint32_t)x < n;
         const int f2 = valid ? __ldg(&g.rf_first[x]) : -1;
-        tab[3 * r + 1] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
+        tab[3 * r + 1] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);
         tab[3 * r + 2] = make_float4(0.0f, __int_as_float(f2), 0.0f, 0.0f);
     }
     if (g.has_wake) {
-        // all loads first, then the stores: one round trip to L2 instead of one per element
-        // (T = n/4 threads: 4 profile entries and at most 5 window entries each)
-        const float* rin = g.rho_in + (size_t)member * n;
-        float rv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) rv[k] = __ldg(rin + tid + k * T);
-        // w[x - x'] is stored at table index x - x' + n - 1; window entry t holds the table
-        // entry xs + t, so row r and x' meet at t = r - x' + n - 1
-        const int wtop = (int)(2 * n - 1);
-        const uint32_t tcount = n + ((RIN + 63) & ~63u);  // <= 5 T for n >= 1024
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t i = tid + k * T;
             rho[i + (i >> 5)] = (double)rv[k];
         }
-        for (uint32_t t0 = tid; t0 < tcount; t0 += 5 * T) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const uint32_t t = tid + k * T;
+            if (t < tcount) wwin[wwin_pos(t)] = wv0[k];
+        }
+        for (uint32_t t0 = tid + 5 * T; t0 < tcount; t0 += 5 * T) {  // small grids: the rest of the window
             double wv[5];
 #pragma unroll
             for (int k = 0; k < 5; k++)
@@ -887,6 +915,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     const uint32_t mail_b = smem_u32(mail);
     const uint32_t post_l = mail_b + (warp * 2 + 0) * kMailSlots * 16;   // written by lane 0
     const uint32_t post_r = mail_b + (warp * 2 + 1) * kMailSlots * 16;   // written by lane 31
+    const uint32_t post_me = lane == 0 ? post_l : post_r;
     const bool edge_l = lane == 0 && warp > 0, edge_r = lane == 31 && warp + 1 < NW;
     // lane 0 reads the left neighbour's right post, lane 31 the right neighbour's left post
     const uint32_t peek = edge_l ? mail_b + ((warp - 1) * 2 + 1) * kMailSlots * 16
@@ -968,7 +997,8 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         }
         wait_row(kbar, kpar, 0);  // the first kick's row
 
-        float4 d = make_float4(0, 0, 0, 0), dprev = d;  // drifted rows of the last two iterations
+        float4 d = make_float4(0, 0, 0, 0);  // the drifted row of this iteration
+        const uint32_t fifo_t = smem_u32(fifo) + tid * 16;  // this thread's entry of FIFO slot 0
         float pprev = 0.0f;   // this lane's part of a finished row's sum (reduced an iteration later)
         uint32_t redp = smem_u32(red) + warp * 4 - NW * 4;  // where the row sum reduced next goes
         const size_t gstride = (size_t)nq;
@@ -977,7 +1007,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         // ---- one kick step: staged row r0 + it -> wake kick + RF kick -> window -> drifted row d
         // (output row it - NT + 1 once the window is full).  POST: d is a real output row whose edge
         // values the neighbour warps need.  MORE: another kick follows, its row has to have landed.
-        auto kick_step = [&](const int it, const bool POST, const bool MORE) {
+        auto kick_step = [&](const int it, const uint32_t fa, const bool POST, const bool MORE) {
             // probes whose answers are needed at the end of the step
             uint32_t nbar = kbar + 8, npar = kpar;
             if (nbar == full_end) { nbar = full_b; npar ^= 1; }
@@ -1001,12 +1031,14 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
                 IVS_DRIFT_COL(3, w)
 #undef IVS_DRIFT_COL
             }
+            // parked in this thread's FIFO entry until its stencil step kLag iterations later
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(fa), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w) : "memory");
             if (POST) {
                 const uint32_t orow = (uint32_t)(it - NT + 1);
                 const uint32_t ms = (orow & (kMailSlots - 1)) * 16;
                 // lane 0 posts (x, y) for the left neighbour, lane 31 (z, w) for the right one
                 const bool l0 = lane == 0;
-                sts128_volatile_if((l0 ? post_l : post_r) + ms,
+                sts128_volatile_if(post_me + ms,
                                    make_float4(l0 ? d.x : d.z, l0 ? d.y : d.w, __uint_as_float(orow + 1), 0.0f),
                                    l0 || lane == 31);
             }
@@ -1014,12 +1046,15 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             mbar_arrive_if(kbar + eoff, lane == 0);
             kbar = nbar;
             kpar = npar;
-            if (duty) duty_issue();
-            if (!landed) wait_row(nbar, npar, it);
+            if (duty || !landed) {  // one rarely taken region for both slow paths
+                if (duty) duty_issue();
+                if (!landed) wait_row(nbar, npar, it);
+            }
         };
-        // ---- one stencil step on dprev = drifted output row `orow`: neighbours, Fokker-Planck, store,
-        // partial row sum; the warp sum of the row before is reduced on the side
-        auto fp_step = [&](const int it, const uint32_t orow) {
+        // ---- one stencil step on drifted output row `orow` (out of the FIFO): neighbours,
+        // Fokker-Planck, store, partial row sum; the warp sum of the row before is reduced on the side
+        auto fp_step = [&](const int it, const uint32_t fa, const uint32_t orow) {
+            const float4 dprev = lds128(fa);
             float4 m = make_float4(0, 0, 0, 0);
             const uint32_t pa = peek + (orow & (kMailSlots - 1)) * 16;
             if (edge) m = lds128_volatile(pa);
@@ -1077,23 +1112,24 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         };
 
         // Iteration `it` kicks row r0 + it; from it = NT-1 on a drifted output row (it - NT + 1) comes
-        // out; the stencil handles the drifted row of two iterations before (output row it - NT - 1),
-        // which gives the neighbour warps a row of slack.
+        // out and is parked in FIFO slot it mod kLag; the stencil handles the row parked kLag
+        // iterations before (output row it - NT + 1 - kLag, read from the same slot before this
+        // iteration's kick overwrites it), so a warp only waits for a neighbour that is more than
+        // kLag - 1 rows late.
+        auto fifo_at = [&](int i) { return fifo_t + (uint32_t)(i & (kLag - 1)) * (T * 16); };
         int it = 0;
-        for (; it <= NT; it++) {  // fill the window, the first two drifted rows
-            if (it < (int)nkicks) kick_step(it, it + 1 >= NT, it + 1 < (int)nkicks);
-            dprev = (it == NT - 1) ? d : dprev;
+        for (; it < NT - 1 + kLag; it++) {  // fill the drift sums and the FIFO
+            if (it < (int)nkicks) kick_step(it, fifo_at(it), it + 1 >= NT, it + 1 < (int)nkicks);
         }
-        // here d = output row 1, dprev = output row 0
         for (; it + 1 < (int)nkicks; it++) {  // steady state
-            fp_step(it, (uint32_t)(it - NT - 1));
-            dprev = d;
-            kick_step(it, true, true);
+            const uint32_t fa = fifo_at(it);
+            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
+            kick_step(it, fa, true, true);
         }
-        for (; it <= (int)nkicks + 1; it++) {  // the last kick and the two rows still in flight
-            fp_step(it, (uint32_t)(it - NT - 1));
-            dprev = d;
-            if (it < (int)nkicks) kick_step(it, true, false);
+        for (; it < (int)nkicks + kLag; it++) {  // the last kick and the rows still parked
+            const uint32_t fa = fifo_at(it);
+            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
+            if (it < (int)nkicks) kick_step(it, fa, true, false);
         }
         // the last row's sum
         {
@@ -1238,7 +1274,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         const uint32_t by_regs = std::max<uint32_t>(1, 65536u / (regs_thread * threads_s));  // CTAs per SM
         // ring depth: the warps' windows start up to H rows apart, plus rows in flight; the
         // mailboxes (kMailSlots deep) bound it from above
-        const uint32_t kmin = H + 4, kmax = kMailSlots - 8;
+        const uint32_t kmin = H + 4, kmax = kMailSlots - kLag - 6;
         // Search over the strip length S0 = ceil(n / P): the per-row tables in shared memory are sized
         // for the strip, so shorter strips leave room for more CTAs per SM (small grids) while longer
         // ones amortise the set-up and the halo rows.  Cost = rounds of CTAs over the machine x (rows
@@ -1255,7 +1291,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
             const size_t fixed = a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) + a16((size_t)NW * max_rin * 8) +
                                  a16((size_t)S0 * NW * 4) + a16((size_t)(max_rin + 1) * 48) +
-                                 a16((size_t)NW * 2 * kMailSlots * 16);
+                                 a16((size_t)NW * 2 * kMailSlots * 16) + a16((size_t)kLag * threads_s * 16);
             uint32_t want = std::min<uint32_t>(by_regs, 16), K = 0;
             size_t sb = 0;
             for (; want >= 1; want--) {
