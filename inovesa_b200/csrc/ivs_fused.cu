@@ -906,7 +906,6 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     const int spread = wfmax - wfmin;  // <= 2 (checked when the plan was made)
 
     const uint32_t ring_q = smem_u32(ring + kPadS) + q * 16;  // this quad in slot 0
-    const uint32_t ring_end = ring_q + K * pitchB;
     const int y0 = (int)(q << 2);
     float* redw = red + warp;  // row i's partial at redw[i * NW]
     float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + q;
@@ -1010,16 +1009,14 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         auto kick_step = [&](const int it, const uint32_t fa, const bool POST, const bool MORE) {
             // probes whose answers are needed at the end of the step
             uint32_t nbar = kbar + 8, npar = kpar;
-            if (nbar == full_end) { nbar = full_b; npar ^= 1; }
+            const bool wrap = nbar == full_end;  // the next row sits in slot 0
+            if (wrap) { nbar = full_b; npar ^= 1; }
             const uint32_t landed = mbar_test(MORE ? nbar : kbar, MORE ? npar : kpar);
-            const bool duty = it >= pwin;
-            if (duty) duty_probe();
             const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
             const float4 kq = kick_quad<FMA>(aload, f.x, y0 + f.y, n, near_edge, w1, w2);
             tp += 48;
             f = lds64i(tp + 32);  // next row's entry, a row ahead of its use
-            aload += pitchB;
-            if (aload == ring_end) aload = ring_q;
+            aload = wrap ? ring_q : aload + pitchB;
             {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
 #define IVS_DRIFT_COL(c, m)                                                                           \
                 d.m = madd<FMA>(kq.m, dw[c][NT - 1], P[NT - 2].m);                                    \
@@ -1046,8 +1043,11 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             mbar_arrive_if(kbar + eoff, lane == 0);
             kbar = nbar;
             kpar = npar;
-            if (duty || !landed) {  // one rarely taken region for both slow paths
-                if (duty) duty_issue();
+            if (it >= pwin || !landed) {  // one rarely taken region for both slow paths
+                if (it >= pwin) {  // this warp's turn to stage a row (one in NW iterations)
+                    duty_probe();
+                    duty_issue();
+                }
                 if (!landed) wait_row(nbar, npar, it);
             }
         };
