@@ -8,8 +8,9 @@ metric : phase-space cell-updates/s  (N^2 * members * steps / time of the step l
 workload (config.workload): BASELINE.json configs[4] -- 2048x2048 grid, sin RF (RFKickMap) +
   DriftMap with alpha1/alpha2, free-space CSR wake, cubic interpolation, 4000 steps/T_s -- run
   as a batch of `members` independent simulations per GPU (a bunch-current scan, the ensemble
-  partitioning of SURVEY.md section 8e) so that the state streamed per step (2 x members x 16 MiB)
-  exceeds the 126 MB L2: the timing rule "inputs larger than L2" instead of an L2 flush.
+  partitioning of SURVEY.md section 8e; default 26: 17 strips each = 442 CTAs, three full rounds
+  over the 148 SMs) so that the state streamed per step (2 x members x 16 MiB) exceeds the 126 MB
+  L2: the timing rule "inputs larger than L2" instead of an L2 flush.
   A single L2-resident 2048^2 run is reported next to it as `single_run`.
 One "step" = one simulation step of every member (wake potential, wake kick, RF kick, drift,
 Fokker-Planck, X projection, tracking of the passive particles): two launches, the fused step
@@ -41,8 +42,9 @@ from inovesa_b200.params import kara_params  # noqa: E402
 f32 = np.float32
 ALGO_BYTES_PER_CELL = 8.0  # one fp32 read + one fp32 write of the grid per step
 # dram__bytes_read.sum + dram__bytes_write.sum of one stream_step_kernel launch on the benchmark
-# batch (8 x 2048^2), from the ncu --set full capture summarised in profiles/ (updated per round)
-TRAFFIC_BYTES_PER_LAUNCH = 236536832  # r1: 141.5 MB read + 95.0 MB written (L2 still holds dirty lines at kernel end)
+# batch (26 x 2048^2), from the ncu --set full capture summarised in profiles/ (updated per round)
+TRAFFIC_MEMBERS = 26
+TRAFFIC_BYTES_PER_LAUNCH = 865476608  # r1: 457.5 MB read + 408.0 MB written; algorithmic 872.4 MB
 
 
 def workload_params(name):
@@ -284,7 +286,7 @@ def run_ours(args):
                                                    "power) + profile D2H"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if not args.unfused and members == 8 and n == 2048 else None,
+                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if not args.unfused and members == TRAFFIC_MEMBERS and n == 2048 else None,
                          "peak_source": peak_src,
                          "kernel": "stream_step_kernel" if not args.unfused else "kick/drift/fokker_planck/project sequence",
                          "us_per_launch": ms_kernel * 1e3 / args.steps,
@@ -388,7 +390,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config5")
-    ap.add_argument("--members", type=int, default=8)
+    ap.add_argument("--members", type=int, default=26)
     ap.add_argument("--particles", type=int, default=100000)
     ap.add_argument("--arith", default="fma", choices=["fma", "strict"])
     ap.add_argument("--unfused", action="store_true")

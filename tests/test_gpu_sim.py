@@ -158,6 +158,22 @@ def test_fused_properties_at_full_size(capi, ctx_fma):
     assert np.all(np.isfinite(g)) and g.min() > -1e-3
 
 
+@pytest.mark.parametrize("members", [9, 26])
+def test_strip_length_does_not_change_results(capi, ctx_fma, members):
+    """The planner cuts a member into strips by how many members there are (147 strips of 14 rows
+    for one 2048^2 run, 16 of 128 for a batch of 9, 17 of 121 for the benchmark's batch of 26: one,
+    one and three rounds of CTAs over the machine).  Strips, halos, ring depth and the order in
+    which CTAs run must not show in the results: every member of a batch of identical members
+    equals the single run bit for bit."""
+    p = kara_params(grid_size=2048, steps_per_Ts=4000, linear_rf=0, alpha1=2e-4, alpha2=3e-3)
+    (g1, p1, w1, _), = _states(capi, ctx_fma, p, 0, [10])
+    (g, pr, w, _), = _states(capi, ctx_fma, p, 0, [10], members=members)
+    for m in (0, members // 2, members - 1):
+        assert np.array_equal(g[m], g1[0])
+        assert np.array_equal(pr[m], p1[0])
+        assert np.array_equal(w[m], w1[0])
+
+
 def test_fused_tracking_matches_unfused(capi, ctx_strict, rng):
     p = kara_params(grid_size=256)
     p.fp_track = 1
