@@ -976,6 +976,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         };
 
         uint32_t aload = ring_q + (r0 % K) * pitchB;
+        const uint32_t ring_back = pitchB - K * pitchB;
         uint32_t tp = smem_u32(tab) + r0 * 48;
         int2 f = lds64i(tp + 32);
         // drift as running sums: P[j] is the output row that has taken j + 1 of its NT taps so far.
@@ -1016,7 +1017,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             const float4 kq = kick_quad<FMA>(aload, f.x, y0 + f.y, n, near_edge, w1, w2);
             tp += 48;
             f = lds64i(tp + 32);  // next row's entry, a row ahead of its use
-            aload = wrap ? ring_q : aload + pitchB;
+            aload += wrap ? ring_back : pitchB;  // ring_back = pitchB - K * pitchB: back to slot 0
             {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
 #define IVS_DRIFT_COL(c, m)                                                                           \
                 d.m = madd<FMA>(kq.m, dw[c][NT - 1], P[NT - 2].m);                                    \
@@ -1053,8 +1054,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         };
         // ---- one stencil step on drifted output row `orow` (out of the FIFO): neighbours,
         // Fokker-Planck, store, partial row sum; the warp sum of the row before is reduced on the side
-        auto fp_step = [&](const int it, const uint32_t fa, const uint32_t orow) {
-            const float4 dprev = lds128(fa);
+        auto fp_step = [&](const int it, const float4 dprev, const uint32_t orow) {
             float4 m = make_float4(0, 0, 0, 0);
             const uint32_t pa = peek + (orow & (kMailSlots - 1)) * 16;
             if (edge) m = lds128_volatile(pa);
@@ -1123,12 +1123,12 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         }
         for (; it + 1 < (int)nkicks; it++) {  // steady state
             const uint32_t fa = fifo_at(it);
-            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
+            fp_step(it, lds128(fa), (uint32_t)(it - (NT - 1 + kLag)));
             kick_step(it, fa, true, true);
         }
         for (; it < (int)nkicks + kLag; it++) {  // the last kick and the rows still parked
             const uint32_t fa = fifo_at(it);
-            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
+            fp_step(it, lds128(fa), (uint32_t)(it - (NT - 1 + kLag)));
             if (it < (int)nkicks) kick_step(it, fa, true, false);
         }
         // the last row's sum
