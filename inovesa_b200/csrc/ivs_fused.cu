@@ -27,6 +27,7 @@
 // Every tap accumulation is madd<FMA>() in the reference's order, so the result is bit-identical
 // to the unfused kernel sequence (ivs_maps.cu) -- tested.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -1283,7 +1284,13 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         double best = 1e300;
         uint32_t bestP = 0, bestK = 0, best_rin = 0;
         size_t best_sb = 0, best_wwin = 0;
+        // development aids: IVS_FORCE_STRIPS=<P> pins the number of strips per member,
+        // IVS_PLAN_DEBUG=1 prints the plan that was chosen
+        const char* force_env = getenv("IVS_FORCE_STRIPS");
+        const uint32_t forceP = force_env ? (uint32_t)atoi(force_env) : 0;
+        uint32_t best_want = 0;
         for (uint32_t P = 1; P <= n / 8 && kmin <= kmax; P++) {
+            if (forceP && P != forceP) continue;
             const uint32_t S0 = ivs_div_up(n, P);
             if ((uint64_t)S0 * (P - 1) >= n || S0 > 128) continue;  // last strip empty / table cap
             const uint32_t max_rin = S0 + H;
@@ -1309,8 +1316,11 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             const uint32_t resident = (uint32_t)std::min<uint64_t>(want, ivs_div_up((uint32_t)units, ctx->sm_count));
             const double fill = std::min(1.0, resident * (threads_s / 32) / 16.0);  // of 16 warps per SM
             const double cost = (double)rounds * (S0 + H + 16) * resident / std::max(fill, 1.0 / 16);
-            if (cost < best) { best = cost; bestP = P; bestK = K; best_sb = sb; best_rin = max_rin; best_wwin = wwin_len; }
+            if (cost < best) { best = cost; bestP = P; bestK = K; best_sb = sb; best_rin = max_rin; best_wwin = wwin_len; best_want = want; }
         }
+        if (bestP && getenv("IVS_PLAN_DEBUG"))
+            fprintf(stderr, "[ivs plan] n %u members %u: %u strips of %u rows, halo %u, ring %u slots, %zu B shared memory, %u CTAs/SM, %u CTAs\n",
+                    n, s->members, bestP, ivs_div_up(n, bestP), H, bestK, best_sb, best_want, bestP * s->members);
         if (bestP) {
             // Fokker-Planck weights with the taps that fall outside the grid zeroed: the shuffles
             // deliver a lane's own value there instead of the tile kernels' zero pad
