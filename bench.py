@@ -44,7 +44,7 @@ ALGO_BYTES_PER_CELL = 8.0  # one fp32 read + one fp32 write of the grid per step
 # dram__bytes_read.sum + dram__bytes_write.sum of one stream_step_kernel launch on the benchmark
 # batch (26 x 2048^2), from the ncu --set full capture summarised in profiles/ (updated per round)
 TRAFFIC_MEMBERS = 26
-TRAFFIC_BYTES_PER_LAUNCH = 865476608  # r1: 457.5 MB read + 408.0 MB written; algorithmic 872.4 MB
+TRAFFIC_BYTES_PER_LAUNCH = 865557760  # r1: 457.5 MB read + 408.0 MB written; algorithmic 872.4 MB
 
 
 def workload_params(name):
