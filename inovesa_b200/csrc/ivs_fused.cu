@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
 // (same taps, same order, same summation tree of the profile).
 
 constexpr int kPadS = 32;     // zero columns each side of a staged row: two kicks of up to 16 cells
+constexpr uint32_t kMinStrip = 2;  // shortest strip the planner considers (rows), see ivs_fused_plan_create
 constexpr int kMailSlots = 32; // mailbox depth per warp edge (> ring slots + kLag + 5, see the hand-back rule)
 #ifndef IVS_LAG
 #define IVS_LAG 4
@@ -1293,10 +1294,14 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         const char* force_env = getenv("IVS_FORCE_STRIPS");
         const uint32_t forceP = force_env ? (uint32_t)atoi(force_env) : 0;
         uint32_t best_want = 0;
-        for (uint32_t P = 1; P <= n / 8 && kmin <= kmax; P++) {
+        for (uint32_t P = 1; P <= n / kMinStrip && kmin <= kmax; P++) {
             if (forceP && P != forceP) continue;
             const uint32_t S0 = ivs_div_up(n, P);
             if ((uint64_t)S0 * (P - 1) >= n || S0 > 128) continue;  // last strip empty / table cap
+            // Strips shorter than 8 rows only pay when every strip gets an SM of its own (a single
+            // small run: a step is then the latency of set-up + S0 + halo rows; measured 7.4 vs 9.9 us
+            // per step at 256^2, 8.2 vs 9.8 at 512^2), not when CTAs share SMs (12.9 vs 11.5 us at 1024^2)
+            if (S0 < 8 && (uint64_t)P * s->members > (uint64_t)ctx->sm_count) continue;
             const uint32_t max_rin = S0 + H;
             const uint32_t wcount = n + ((max_rin + 63) & ~63u);
             const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
