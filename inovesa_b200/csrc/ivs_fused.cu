@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include <vector>
 
@@ -555,6 +556,12 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
 constexpr int kPadS = 32;     // zero columns each side of a staged row: two kicks of up to 16 cells
 constexpr uint32_t kMinStrip = 2;  // shortest strip the planner considers (rows), see ivs_fused_plan_create
 constexpr int kMailSlots = 32; // mailbox depth per warp edge (> ring slots + kLag + 5, see the hand-back rule)
+#ifndef IVS_WARP_CLOCKS
+#define IVS_WARP_CLOCKS 0  // development aid: per-warp-index totals of loop time and poll counts (stderr at plan destroy)
+#endif
+#if IVS_WARP_CLOCKS
+__device__ unsigned long long g_wstat[4][32];  // [loop-end clock, mailbox polls, row waits, strips][warp]
+#endif
 #ifndef IVS_LAG
 #define IVS_LAG 4
 #endif
@@ -926,6 +933,10 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     const uint32_t peek = edge_l ? mail_b + ((warp - 1) * 2 + 1) * kMailSlots * 16
                                  : mail_b + ((warp + 1) * 2 + 0) * kMailSlots * 16;
 
+#if IVS_WARP_CLOCKS
+    const long long wclk0 = clock64();
+    unsigned long long n_mpoll = 0, n_rwait = 0;
+#endif
     auto run = [&](auto nt_tag) {
         constexpr int NT = decltype(nt_tag)::value;
         float dw[4][NT];
@@ -973,6 +984,9 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         auto wait_row = [&](uint32_t bar, uint32_t ph, int it) {
             uint32_t tries = 0;
             while (!mbar_try(bar, ph)) {
+#if IVS_WARP_CLOCKS
+                n_rwait++;
+#endif
                 if (it >= pwin) {
                     duty_probe();
                     duty_issue();
@@ -1080,6 +1094,9 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
                         duty_issue();
                     }
                     if (edge) m = lds128_volatile(pa);
+#if IVS_WARP_CLOCKS
+                    n_mpoll++;
+#endif
                     if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
                 } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1));
             }
@@ -1137,6 +1154,14 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             fp_step(it, lds128(fa), (uint32_t)(it - (NT - 1 + kLag)));
             if (it < (int)nkicks) kick_step(it, fa, true, false);
         }
+#if IVS_WARP_CLOCKS
+        if (lane == 0) {
+            atomicAdd(&g_wstat[0][warp], (unsigned long long)(clock64() - wclk0));
+            atomicAdd(&g_wstat[1][warp], n_mpoll);
+            atomicAdd(&g_wstat[2][warp], n_rwait);
+            atomicAdd(&g_wstat[3][warp], 1ull);
+        }
+#endif
         // the last row's sum
         {
             float p = pprev;
@@ -1425,6 +1450,19 @@ ivs_status ivs_fused_plan_set_rf(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s,
 }
 
 void ivs_fused_plan_destroy(ivs_fused_plan* plan) {
+#if IVS_WARP_CLOCKS
+    if (plan->stream) {
+        unsigned long long h[4][32];
+        if (cudaMemcpyFromSymbol(h, g_wstat, sizeof(h)) == cudaSuccess) {
+            for (int w = 0; w < 32; w++)
+                if (h[3][w])
+                    fprintf(stderr, "[ivs warp %2d] strips %llu: loop end at %.0f clocks, %.1f mailbox polls, %.1f row waits per strip\n", w,
+                            h[3][w], (double)h[0][w] / h[3][w], (double)h[1][w] / h[3][w], (double)h[2][w] / h[3][w]);
+            memset(h, 0, sizeof(h));
+            cudaMemcpyToSymbol(g_wstat, h, sizeof(h));
+        }
+    }
+#endif
     void** bufs[] = {&plan->rf_first, &plan->rf_w, &plan->dr_first, &plan->dr_w, &plan->fp_base, &plan->fp_w, &plan->fp5};
     for (void** b : bufs) {
         if (*b) cudaFree(*b);
