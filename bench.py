@@ -88,9 +88,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi takes a while to produce its first line on a fresh box: do not time before it"""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
+        """statistics of the samples taken in [t_begin, t_end] (the timed region); if the region was
+        shorter than the sampling interval, of the samples up to 0.25 s around it"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -99,9 +107,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        rows = [r for _, r in self.rows]
+        if t_begin is not None and t_end is not None:
+            inside = [r for t, r in self.rows if t_begin <= t <= t_end]
+            near = [r for t, r in self.rows if t_begin - 0.25 <= t <= t_end + 0.25]
+            rows = inside if len(inside) >= 3 else (near or rows)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -171,14 +184,18 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    sim.step(args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    sim.step(args.warmup)
+    if rank == 0:
+        sampler.wait_first()
     launches0 = ctx.launches
+    t_begin = time.perf_counter()
     ms = timed(sim.step, args.steps)
+    t_end = time.perf_counter()
     launches = ctx.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     cells_per_step = float(n) * n * members
     value = cells_per_step * args.steps * world / (ms * 1e-3)
 
@@ -386,8 +403,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config5")
     ap.add_argument("--members", type=int, default=26)
