@@ -53,6 +53,11 @@ def workload_params(name):
                            gap=-1.0, bunch_current=50e-6, fp_track=3)
     if name == "config1":
         return kara_params(grid_size=256, steps_per_Ts=1000, gap=-1.0, bunch_current=50e-6)
+    if name == "config2":
+        return kara_params(grid_size=512, steps_per_Ts=1000, gap=0.032, bunch_current=300e-6)
+    if name == "config3":
+        return kara_params(grid_size=1024, steps_per_Ts=4000, gap=0.032, wall_conductivity=5.8e7,
+                           collimator=0.008, bunch_current=200e-6)
     if name == "config4":
         return kara_params(grid_size=256, steps_per_Ts=1000, gap=-1.0, bunch_current=50e-6)
     raise SystemExit("unknown workload " + name)
@@ -147,6 +152,7 @@ def run_ours(args):
     members = args.members
     arith = capi.ARITH_STRICT if args.arith == "strict" else capi.ARITH_FMA
     flags = capi.SIM_UNFUSED if args.unfused else 0
+    flags |= {0: 0, 1: capi.SIM_QPT1, 2: capi.SIM_QPT2}[args.qpt]
     ctx = capi.Context(local_rank, arith)
     stream = torch.cuda.ExternalStream(ctx.lib.ivs_ctx_stream(ctx.h), device=local_rank)
     d = capi.derive(p)
@@ -161,8 +167,7 @@ def run_ours(args):
     if args.particles:
         parts = (rng.random((args.particles, 2)) * (n / 2) + n / 4).astype(f32)  # q,p in [-3,3]
     sim = capi.Simulation(ctx, p, members, particles=parts, flags=flags, bunch_currents=currents,
-                          seed=rank)
-    single = capi.Simulation(ctx, p, 1, flags=flags) if args.single_run else None
+                          seed=rank, strips=args.strips)
 
     def barrier():
         ctx.sync()
@@ -184,17 +189,26 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    def timed_median(fn, steps, repeats):
+        """`repeats` timed blocks of exactly `steps` steps each (CUDA events on the launching stream,
+        barrier + synchronize on both sides, max over ranks); the median block is the result"""
+        blocks = sorted(timed(fn, steps) for _ in range(repeats))
+        return blocks[len(blocks) // 2], blocks
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # warm-up: W steps as asked, then one untimed rehearsal of the timed block itself (the step
+    # graphs were captured and instantiated when the simulation was created)
     sim.step(args.warmup)
+    sim.step(args.steps)
     if rank == 0:
         sampler.wait_first()
     launches0 = ctx.launches
     t_begin = time.perf_counter()
-    ms = timed(sim.step, args.steps)
+    ms, ms_blocks = timed_median(sim.step, args.steps, args.repeats)
     t_end = time.perf_counter()
-    launches = ctx.launches - launches0
+    launches = (ctx.launches - launches0) // args.repeats
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     cells_per_step = float(n) * n * members
     value = cells_per_step * args.steps * world / (ms * 1e-3)
@@ -204,11 +218,13 @@ def run_ours(args):
     # duration is measured on the same batch without particles, where a step is exactly that one
     # launch (CUDA events on the launching stream, same warm-up, same number of steps).
     peak, peak_src = measured_peak()
-    ms_kernel = ms
+    ms_kernel, ms_kernel_blocks = ms, ms_blocks
     if args.particles and not args.unfused:
-        simk = capi.Simulation(ctx, p, members, flags=flags, bunch_currents=currents, seed=rank)
+        simk = capi.Simulation(ctx, p, members, flags=flags, bunch_currents=currents, seed=rank,
+                               strips=args.strips)
         simk.step(args.warmup)
-        ms_kernel = timed(simk.step, args.steps)
+        simk.step(args.steps)
+        ms_kernel, ms_kernel_blocks = timed_median(simk.step, args.steps, args.repeats)
         simk.close()
     achieved = cells_per_step * ALGO_BYTES_PER_CELL / (ms_kernel * 1e-3 / args.steps) / 1e9
 
@@ -267,13 +283,42 @@ def run_ours(args):
         out_s = float(t.item())
     e2e_outstep = cells_per_step * out_steps * out_rounds * world / out_s
 
+    # single runs (no ensemble: the state is L2-resident, a step is latency-bound) at the grid sizes
+    # of BASELINE.json's configs 1, 2, 3 and 5
     single_run = None
-    if single is not None:
-        single.step(args.warmup)
-        ms1 = timed(single.step, args.steps)
-        single_run = {"cell_updates_per_s": float(n) * n * args.steps / (ms1 * 1e-3),
-                      "steps_per_s": args.steps / (ms1 * 1e-3), "us_per_step": ms1 * 1e3 / args.steps,
-                      "note": "one 2048^2 simulation, state L2-resident (no flush): latency-bound view"}
+    if args.single_run:
+        single_run = {}
+        for key, wl in (("256", "config1"), ("512", "config2"), ("1024", "config3"), ("2048", "config5")):
+            p1 = workload_params(wl)
+            one = capi.Simulation(ctx, p1, 1, flags=flags)
+            k1 = max(args.steps, 256)
+            one.step(64)
+            ms1, _ = timed_median(one.step, k1, 3)
+            one.close()
+            n1 = p1.grid_size
+            single_run[key] = {"us_per_step": ms1 * 1e3 / k1, "steps_per_s": k1 / (ms1 * 1e-3),
+                               "cell_updates_per_s": float(n1) * n1 * k1 / (ms1 * 1e-3)}
+        single_run["note"] = ("one simulation per grid size (BASELINE configs 1, 2, 3, 5), state L2-resident "
+                              "(no flush): the latency-bound view")
+
+    # BASELINE.json configs[3]: the bunch-current scan of 256 independent 256^2 runs, 256 / N per GPU
+    scan = None
+    if args.scan:
+        ps = workload_params("config4")
+        total = 256
+        lo4, hi4 = member_block(total, world, rank)
+        cur4 = [float(c) for c in scan_currents(0.05e-3, 3e-3, total)[lo4:hi4]]
+        ens = capi.Simulation(ctx, ps, hi4 - lo4, flags=flags, bunch_currents=cur4)
+        k4 = max(args.steps, 256)
+        ens.step(64)
+        ms4, blocks4 = timed_median(ens.step, k4, 5)
+        fb = ens.fallback_steps
+        ens.close()
+        scan = {"workload": "configs[3]: 256 independent 256^2 runs (bunch currents 0.05 ... 3 mA), %d per GPU" % (hi4 - lo4),
+                "ensemble_steps_per_s": total * k4 / (ms4 * 1e-3),
+                "cell_updates_per_s": 256.0 * 256 * total * k4 / (ms4 * 1e-3),
+                "us_per_step": ms4 * 1e3 / k4, "steps": k4, "fallback_steps": fb,
+                "frac_of_hbm_peak": 256.0 * 256 * (hi4 - lo4) * ALGO_BYTES_PER_CELL / (ms4 * 1e-3 / k4) / 1e9 / peak}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -292,6 +337,7 @@ def run_ours(args):
                        "grid": n, "members_per_gpu": members, "particles_per_member": args.particles,
                        "arith": args.arith, "step_path": "unfused" if args.unfused else "fused",
                        "l2": "inputs larger than L2 (state %d MiB/GPU)" % (2 * nbytes // 2**20),
+                       "timing": "median of %d timed blocks of %d steps each" % (args.repeats, args.steps),
                        "parallelism": "replicas x%d (no collective on the step path)" % world},
             "ensemble_steps_per_s": members * world * args.steps / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
@@ -302,6 +348,9 @@ def run_ours(args):
                                                    "ivs_sim_step(100) + ivs_sim_observe (sigma_z, sigma_E, CSR "
                                                    "power) + profile D2H"}},
             "gpu_launches": int(launches),
+            "repeats": {"n": args.repeats, "ms_blocks": ms_blocks, "kernel_ms_blocks": ms_kernel_blocks,
+                        "spread": (ms_blocks[-1] - ms_blocks[0]) / ms},
+            "fallback_steps": sim.fallback_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if not args.unfused and members == TRAFFIC_MEMBERS and n == 2048 else None,
                          "peak_source": peak_src,
@@ -317,12 +366,12 @@ def run_ours(args):
                                     "OpenCL path with" % ("an ICD is registered" if icd else "no OpenCL ICD registered"))
         if single_run:
             line["single_run"] = single_run
+        if scan:
+            line["scan_256x256"] = scan
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     sim.close()
-    if single is not None:
-        single.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -413,6 +462,12 @@ def main():
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--single-run", dest="single_run", action="store_true", default=True)
     ap.add_argument("--no-single-run", dest="single_run", action="store_false")
+    ap.add_argument("--scan", dest="scan", action="store_true", default=True,
+                    help="also time BASELINE configs[3] (256 x 256^2 scan, 256/N members per GPU)")
+    ap.add_argument("--no-scan", dest="scan", action="store_false")
+    ap.add_argument("--repeats", type=int, default=7, help="timed blocks of --steps steps; the median counts")
+    ap.add_argument("--qpt", type=int, default=0, choices=[0, 1, 2], help="tuning: quads of columns per thread")
+    ap.add_argument("--strips", type=int, default=0, help="tuning: strips per member (0 = planner)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

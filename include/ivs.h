@@ -193,7 +193,7 @@ typedef struct ivs_sim_desc {
     uint32_t n_particles;  /* tracked particles per member (0 = none) */
     uint32_t fptrack;      /* FPTracking for the particles */
     uint32_t flags;        /* IVS_SIM_* */
-    uint32_t reserved;
+    uint32_t strips;       /* tuning: strips per member of the streaming step kernel (0 = planner's choice) */
     float dq;              /* axis 0 delta (Simpson weights are built from it, as the reference) */
     float dp;              /* axis 1 delta */
     float e1;              /* damping decrement (tracking only; the stencil is in fp_weights) */
@@ -215,7 +215,9 @@ enum {
                                    Toeplitz product (same operator) */
     IVS_SIM_UNFUSED = 2u,       /* run the step as the reference's kernel sequence (debug / parity) */
     IVS_SIM_NO_GRAPH = 4u,      /* launch kernels directly instead of replaying a CUDA graph */
-    IVS_SIM_TILED = 8u          /* fused step as the tile kernel instead of the streaming pipeline */
+    IVS_SIM_TILED = 8u,         /* fused step as the tile kernel instead of the streaming pipeline */
+    IVS_SIM_QPT1 = 16u,         /* tuning: streaming kernel with one quad of columns per thread ... */
+    IVS_SIM_QPT2 = 32u          /* ... or two (default: two from 1024 columns on) */
 };
 
 ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* desc, ivs_sim** out);
@@ -224,6 +226,12 @@ ivs_status ivs_sim_destroy(ivs_sim* sim);
 ivs_status ivs_sim_step(ivs_sim* sim, uint32_t nsteps);
 /* steps taken so far */
 uint64_t ivs_sim_steps_done(const ivs_sim* sim);
+/* The fused step kernel stages 32 zero columns beside every row, which bounds the wake kick's
+ * first tap to [-16, 8] cells; KickMap::updateSM (src/SM/KickMap.cpp:339-389) has no such limit.
+ * A step that exceeds it is detected on the device, redone through the unfused kernel sequence
+ * (any displacement) and the steps after it are re-enqueued -- at the next call that touches the
+ * simulation, transparently.  This counts the steps that were redone that way. */
+uint64_t ivs_sim_fallback_steps(const ivs_sim* sim);
 /* device pointers to the current state (valid until the next ivs_sim_step):
  * grid [members][n][n], x-projection [members][n], wake potential [members][n]
  * (the offsets the last step applied), particles [members][np][2] */

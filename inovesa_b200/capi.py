@@ -20,7 +20,7 @@ f32 = np.float32
 IVS_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_HALO, ERR_NO_DEVICE = 1, 2, 3, 4, 5
 ARITH_FMA, ARITH_STRICT = 0, 1
-SIM_WAKE_FFT, SIM_UNFUSED, SIM_NO_GRAPH, SIM_TILED = 1, 2, 4, 8
+SIM_WAKE_FFT, SIM_UNFUSED, SIM_NO_GRAPH, SIM_TILED, SIM_QPT1, SIM_QPT2 = 1, 2, 4, 8, 16, 32
 
 P, u32, u64, cf, cd, ci, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_int, C.c_size_t
 _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -67,6 +67,7 @@ SIGNATURES = {
     "ivs_sim_destroy": (ci, [P]),
     "ivs_sim_step": (ci, [P, u32]),
     "ivs_sim_steps_done": (u64, [P]),
+    "ivs_sim_fallback_steps": (u64, [P]),
     "ivs_sim_state": (ci, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "ivs_sim_download": (ci, [P, P, P, P, P]),
     "ivs_sim_upload_grid": (ci, [P, _fp]),
@@ -434,7 +435,7 @@ class Simulation:
     """
 
     def __init__(self, ctx, params, members=1, grid=None, particles=None, flags=0, tables=None,
-                 bunch_currents=None, seed=0):
+                 bunch_currents=None, seed=0, strips=0):
         self.ctx, self.lib = ctx, ctx.lib
         self.params = params
         self.d = d = derive(params)
@@ -480,7 +481,7 @@ class Simulation:
             self.np = parts.shape[1]
         desc = SimDesc(n=n, members=members, it=params.interpolation,
                        nmax=self.nmax, n_particles=self.np,
-                       fptrack=params.fp_track, flags=flags, reserved=0, dq=d.dq, dp=d.dp, e1=d.e1,
+                       fptrack=params.fp_track, flags=flags, strips=strips, dq=d.dq, dp=d.dp, e1=d.e1,
                        qmin=d.qmin, pmin=d.pmin, reserved_f=0.0,
                        rf_offset=_ptr(rf), drift_offset=_ptr(drift), fp_weights=_ptr(fp5),
                        impedance=_ptr(zw), wakescaling=_ptr(scal), grid=_ptr(grid),
@@ -530,6 +531,11 @@ class Simulation:
     @property
     def steps_done(self):
         return int(self.lib.ivs_sim_steps_done(self.h))
+
+    @property
+    def fallback_steps(self):
+        """steps redone through the kernel sequence because a wake kick left the fused kernel's pad"""
+        return int(self.lib.ivs_sim_fallback_steps(self.h))
 
     def close(self):
         if getattr(self, "h", None):

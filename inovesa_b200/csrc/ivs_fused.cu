@@ -57,7 +57,8 @@ struct fused_args {
     const float4* fp_w;
     const float* fp_w5;
     const float* ws;
-    int* status;
+    int* status;     // [0] ordinal of the first step that left the staged pad (kStatusClean: none), [1] CTA tickets
+    int* host_flag;  // host-mapped copy of "status[0] is set" (read by the host without a sync)
     uint32_t n, it, hl, hr, pitch;
     int has_wake;
 };
@@ -90,6 +91,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
             : "r"(smem_u32(bar)), "r"(phase)
             : "memory");
     } while (!ok);
+}
+
+
+// ---- step bookkeeping shared by the three fused kernels.  status[0] = ordinal (counted from the
+// host's last reset of the two words) of the first step in which a wake kick left the staged pad,
+// status[1] = CTA ticket counter (ticket / CTAs per step = this step's ordinal).  Once status[0] is
+// set every later step exits without writing, so the input of the offending step stays intact
+// in the ping-pong buffer and the host can redo it through the kernel sequence (ivs_step.cu).
+constexpr int kStatusClean = 0x7fffffff;
+__device__ __forceinline__ void step_ctl_begin(const fused_args& g, int* ctl) {
+    ctl[0] = *reinterpret_cast<volatile int*>(g.status);
+    ctl[1] = (int)atomicAdd(reinterpret_cast<unsigned int*>(g.status) + 1, 1u);
+}
+__device__ __forceinline__ void step_ctl_overflow(const fused_args& g, const int* ctl) {
+    const unsigned int ord = (unsigned int)ctl[1] / (gridDim.x * gridDim.y);
+    atomicMin(g.status, (int)ord);
+    *reinterpret_cast<volatile int*>(g.host_flag) = 1;
+    __threadfence_system();
 }
 
 template <bool FMA>
@@ -140,6 +159,7 @@ template <int TX, bool FMA>
 __global__ void __launch_bounds__(1024, 1) fused_step_generic_kernel(const fused_args g) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int ctl[2];
     const uint32_t n = g.n, pitch = g.pitch, hl = g.hl;
     const uint32_t R = TX + g.hl + g.hr;
     const uint32_t T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
@@ -158,12 +178,14 @@ __global__ void __launch_bounds__(1024, 1) fused_step_generic_kernel(const fused
 
     // ---- 0. stage the rows through the TMA engine
     if (tid == 0) {
+        step_ctl_begin(g, ctl);
         mbar_init(&bar, 1);
         uint32_t valid = 0;
         for (uint32_t r = 0; r < R; r++) valid += ((uint32_t)(xs + (int)r) < n);
-        mbar_expect_tx(&bar, valid * n * (uint32_t)sizeof(float));
+        if (ctl[0] == kStatusClean) mbar_expect_tx(&bar, valid * n * (uint32_t)sizeof(float));
     }
     __syncthreads();
+    if (ctl[0] != kStatusClean) return;  // an earlier step overflowed: see step_ctl_begin
     if (warp == 0) {
         for (uint32_t r = lane; r < R; r += 32) {
             const int x = xs + (int)r;
@@ -200,7 +222,7 @@ __global__ void __launch_bounds__(1024, 1) fused_step_generic_kernel(const fused
                 const float wk = __fmul_rn(scal, (float)acc);
                 ivs_taps t = ivs_kick_taps(wk, n, g.it);
                 if (t.first < -kPad || t.first > kPad - 4) {  // beyond the staged pad: flag, neutralise
-                    atomicExch(g.status, 1);
+                    step_ctl_overflow(g, ctl);
                     t.first = -1;
                     t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.0f;
                 }
@@ -363,6 +385,7 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
     constexpr int NV = TX / RG;  // rows per thread in the last stage
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int ctl[2];
     const uint32_t n = g.n, nq = g.n >> 2, pitch = g.pitch, hl = g.hl;
     const uint32_t R = TX + g.hl + g.hr;
     const uint32_t T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
@@ -381,12 +404,14 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
 
     // ---- 0. stage the rows through the TMA engine (one bulk copy per row)
     if (tid == 0) {
+        step_ctl_begin(g, ctl);
         mbar_init(&bar, 1);
         uint32_t valid = 0;
         for (uint32_t r = 0; r < R; r++) valid += ((uint32_t)(xs + (int)r) < n);
-        mbar_expect_tx(&bar, valid * n * (uint32_t)sizeof(float));
+        if (ctl[0] == kStatusClean) mbar_expect_tx(&bar, valid * n * (uint32_t)sizeof(float));
     }
     __syncthreads();
+    if (ctl[0] != kStatusClean) return;  // an earlier step overflowed: see step_ctl_begin
     if (warp == 0) {
         for (uint32_t r = lane; r < R; r += 32) {
             const int x = xs + (int)r;
@@ -426,7 +451,7 @@ __global__ void __launch_bounds__(1024, 1) fused_step_kernel(const fused_args g)
                 const float wk = __fmul_rn(scal, (float)acc);  // src/PS/ElectricField.cpp:236-241
                 ivs_taps t = ivs_kick_taps(wk, n, g.it);
                 if (t.first < -kPad || t.first > kPad - 4) {
-                    atomicExch(g.status, 1);
+                    step_ctl_overflow(g, ctl);
                     t.first = -1;
                     t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.0f;
                 }
@@ -691,15 +716,52 @@ __device__ __forceinline__ float4 kick_quad(uint32_t row_q, int fsum, int m0, ui
 // on different banks
 __device__ __forceinline__ uint32_t wwin_pos(uint32_t t) { return t + (t >> 3); }
 
-template <bool FMA>
-__global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args sa) {
+// wake kick + RF kick of the QPT quads a thread owns in one staged row (quad j sits 32 quads =
+// 512 bytes after quad j-1).  The alignment of the first tap is the same for all of them, so one
+// warp-uniform switch serves QPT independent chains of arithmetic.
+template <bool FMA, int QPT>
+__device__ __forceinline__ void kick_quads(uint32_t row_q, int fsum, int m0, uint32_t n, const bool (&near_edge)[QPT],
+                                           const float4 w1, const float4 w2, float4 (&kq)[QPT]) {
+    const int a = fsum & ~3;  // floor to a multiple of 4 (two's complement: also for negatives)
+    const uint32_t p = row_q + (uint32_t)(a * 4);
+    // the three staged quads every alignment needs are requested before the switch (their latency
+    // then overlaps the branch); only the shift by 3 needs a fourth
+    float4 A[QPT], B[QPT], C[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; j++) {
+        A[j] = lds128(p + j * 512);
+        B[j] = lds128(p + j * 512 + 16);
+        C[j] = lds128(p + j * 512 + 32);
+    }
+#define IVS_KICK_CASE(RR)                                                                                       \
+    _Pragma("unroll") for (int j = 0; j < QPT; j++)                                                             \
+        kq[j] = kick_quad_rr<FMA, RR>(p + j * 512, A[j], B[j], C[j], m0 + j * 128, n, near_edge[j], w1, w2);
+    switch (fsum - a) {
+    case 0: IVS_KICK_CASE(0) break;
+    case 1: IVS_KICK_CASE(1) break;
+    case 2: IVS_KICK_CASE(2) break;
+    default: IVS_KICK_CASE(3) break;
+    }
+#undef IVS_KICK_CASE
+}
+
+// A thread owns QPT quads of columns (QPT float4 per row) for the whole strip: quad j of the thread
+// is quad (warp * QPT + j) * 32 + lane of the row, i.e. a warp covers QPT adjacent segments of 128
+// columns and a lane's quads are 128 columns apart (conflict-free LDS.128, coalesced STG.128).
+// QPT = 2 halves the warps per row (8 warps of up to 255 registers at n = 2048 instead of 16 of
+// 128): the per-row control (barrier probes, tap tables, cursors, staging duty, mailboxes) is paid
+// once for twice the columns and every dependent chain has an independent twin to interleave with.
+template <bool FMA, int QPT>
+__global__ void __launch_bounds__(512 / QPT, 1) stream_step_kernel(const stream_args sa) {
     const fused_args& g = sa.f;
     extern __shared__ __align__(128) float smem[];
+    __shared__ int ctl[2];
     const uint32_t n = g.n, nq = g.n >> 2, pitch = g.pitch, hl = g.hl;
     const uint32_t H = g.hl + g.hr;
     const uint32_t K = sa.kslots;
-    const uint32_t T = blockDim.x;             // == nq: one quad of columns per thread
+    const uint32_t T = blockDim.x;             // == nq / QPT
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+    const uint32_t NSEG = NW * QPT;            // segments of 128 columns in a row
     const uint32_t member = blockIdx.y;
     const uint32_t xa = blockIdx.x * sa.strip;
     const uint32_t S = min(sa.strip, n - xa);  // output rows of this strip
@@ -716,12 +778,12 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     float* ring = reinterpret_cast<float*>(carve((size_t)K * pitch * 4));        // K row slots
     double* rho = reinterpret_cast<double*>(carve((size_t)(n + (n >> 5)) * 8));  // last step's profile (skewed)
     double* wwin = reinterpret_cast<double*>(carve((size_t)sa.wwin_len * 8));    // wake function window
-    double* partial = reinterpret_cast<double*>(carve((size_t)NW * sa.max_rin * 8));  // wake partial sums
-    float* red = reinterpret_cast<float*>(carve((size_t)sa.max_strip * NW * 4));       // row-sum partials
+    double* partial = reinterpret_cast<double*>(carve((size_t)NSEG * sa.max_rin * 8));  // wake partial sums
+    float* red = reinterpret_cast<float*>(carve((size_t)sa.max_strip * NSEG * 4));       // row-sum partials
     // per input row: wake taps, RF taps, (f1 + f2, f2, -, -)
     float4* tab = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 48));
     float4* mail = reinterpret_cast<float4*>(carve((size_t)NW * 2 * kMailSlots * 16)); // [warp][side][slot] = (a, b, seq, -)
-    float4* fifo = reinterpret_cast<float4*>(carve((size_t)kLag * T * 16));            // [slot][thread] drifted quads
+    float4* fifo = reinterpret_cast<float4*>(carve((size_t)kLag * QPT * T * 16));      // [slot][quad j][thread] drifted quads
     uint64_t* full = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
     uint64_t* empty = reinterpret_cast<uint64_t*>(carve((size_t)K * 8));
 
@@ -741,20 +803,26 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         }
     };
 
+    if (tid == 0) step_ctl_begin(g, ctl);
     if (tid < K) {  // one thread per slot; a single fence covers both initialisations
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_b + tid * 8), "r"(1u));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_b + tid * 8), "r"(NW));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ---- per-thread constants, requested early: drift taps, Fokker-Planck and Simpson weights
-    const uint32_t q = tid;  // this thread's quad of columns, y = 4q .. 4q+3
-    const int4 df = __ldg(reinterpret_cast<const int4*>(g.dr_first) + q);
-    float4 dwl[4];
+    uint32_t q[QPT];  // this thread's quads of columns, y = 4q .. 4q+3
 #pragma unroll
-    for (int c = 0; c < 4; c++) dwl[c] = __ldg(&g.dr_w[4 * q + c]);
-    float w5[4][5];
-    {
-        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)q * 20);
+    for (int j = 0; j < QPT; j++) q[j] = (warp * QPT + j) * 32 + lane;
+    int4 df[QPT];
+    float4 dwl[QPT][4];
+    float w5[QPT][4][5];
+    float4 ws4[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; j++) {
+        df[j] = __ldg(reinterpret_cast<const int4*>(g.dr_first) + q[j]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) dwl[j][c] = __ldg(&g.dr_w[4 * q[j] + c]);
+        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)q[j] * 20);
         float t[20];
 #pragma unroll
         for (int k = 0; k < 5; k++) {
@@ -764,17 +832,18 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
 #pragma unroll
         for (int c = 0; c < 4; c++)
 #pragma unroll
-            for (int k = 0; k < 5; k++) w5[c][k] = t[c * 5 + k];
+            for (int k = 0; k < 5; k++) w5[j][c][k] = t[c * 5 + k];
+        ws4[j] = __ldg(reinterpret_cast<const float4*>(g.ws) + q[j]);
     }
-    const float4 ws4 = __ldg(reinterpret_cast<const float4*>(g.ws) + q);
     // last step's profile and the first batch of the wake-function window are requested in the same
-    // round trip (T = n/4 threads: 4 profile entries and 5 window entries each)
+    // round trip (T = n / (4 QPT) threads: 4 QPT profile entries and 5 QPT window entries each)
     // w[x - x'] is stored at table index x - x' + n - 1; window entry t holds the table entry
     // xs + t, so row r and x' meet at t = r - x' + n - 1
+    constexpr int NRV = 4 * QPT, NWV = 5 * QPT;
     const int wtop = (int)(2 * n - 1);
-    const uint32_t tcount = n + ((RIN + 63) & ~63u);  // <= 5 T for n >= 1024
-    float rv[4];
-    double wv0[5];
+    const uint32_t tcount = n + ((RIN + 63) & ~63u);  // <= NWV T for n >= 1024
+    float rv[NRV];
+    double wv0[NWV];
     // ... and so is the static part (RF taps) of this thread's first entry of the per-row table
     int pre_f2 = -1;
     float4 pre_w2 = make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
@@ -785,12 +854,15 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     if (g.has_wake) {
         const float* rin = g.rho_in + (size_t)member * n;
 #pragma unroll
-        for (int k = 0; k < 4; k++) rv[k] = __ldg(rin + tid + k * T);
+        for (int k = 0; k < NRV; k++) rv[k] = __ldg(rin + tid + k * T);
 #pragma unroll
-        for (int k = 0; k < 5; k++)
+        for (int k = 0; k < NWV; k++)
             wv0[k] = __ldg(g.wakefn + min(max(xs + (int)(tid + k * T), 0), wtop));  // clamped entries belong to rows outside the grid
     }
     __syncthreads();
+    // an earlier step of this run left the staged pad (the host redoes it on another path and
+    // re-enqueues what follows): nothing may be written any more
+    if (ctl[0] != kStatusClean) return;
     if (tid < min(K, RIN)) issue_row(tid, tid);  // the first ring-full flies during the set-up
 
     // ---- set-up: zero pads (and slots of rows outside the grid, whose stale contents would
@@ -819,22 +891,22 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     }
     if (g.has_wake) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < NRV; k++) {
             const uint32_t i = tid + k * T;
             rho[i + (i >> 5)] = (double)rv[k];
         }
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < NWV; k++) {
             const uint32_t t = tid + k * T;
             if (t < tcount) wwin[wwin_pos(t)] = wv0[k];
         }
-        for (uint32_t t0 = tid + 5 * T; t0 < tcount; t0 += 5 * T) {  // small grids: the rest of the window
-            double wv[5];
+        for (uint32_t t0 = tid + NWV * T; t0 < tcount; t0 += NWV * T) {  // small grids: the rest of the window
+            double wv[NWV];
 #pragma unroll
-            for (int k = 0; k < 5; k++)
+            for (int k = 0; k < NWV; k++)
                 wv[k] = __ldg(g.wakefn + min(max(xs + (int)(t0 + k * T), 0), wtop));  // clamped entries belong to rows outside the grid
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
+            for (int k = 0; k < NWV; k++) {
                 const uint32_t t = t0 + k * T;
                 if (t < tcount) wwin[wwin_pos(t)] = wv[k];
             }
@@ -843,39 +915,42 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     __syncthreads();
     if (g.has_wake) {
         // W[x] = scaling * sum_x' rho[x'] w[x-x']  (src/PS/ElectricField.cpp:186-253 as a Toeplitz
-        // product).  Warp w sums x' in [128 w, 128 w + 128); a lane owns 8 consecutive rows and 32
+        // product).  Segment s sums x' in [128 s, 128 s + 128); a lane owns 8 consecutive rows and 32
         // consecutive x', so the 8 wake-function values it needs slide through registers: one
         // window load and one profile load per 8 multiply-adds.
         const uint32_t rbk = lane & 7, sub = lane >> 3;
-        const uint32_t xb = warp * 128 + sub * 32;
-        const double* rp = rho + xb + (xb >> 5);
-        for (uint32_t pass = 0; pass * 64 < RIN; pass++) {  // warp-uniform trip count
-            const uint32_t r0 = pass * 64 + rbk * 8;
-            const uint32_t t0 = r0 + n - 1 - xb;
-            double wv[8], acc[8];
+#pragma unroll 1
+        for (uint32_t seg = warp * QPT; seg < (warp + 1) * QPT; seg++) {
+            const uint32_t xb = seg * 128 + sub * 32;
+            const double* rp = rho + xb + (xb >> 5);
+            for (uint32_t pass = 0; pass * 64 < RIN; pass++) {  // warp-uniform trip count
+                const uint32_t r0 = pass * 64 + rbk * 8;
+                const uint32_t t0 = r0 + n - 1 - xb;
+                double wv[8], acc[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                wv[j] = wwin[wwin_pos(t0 + j)];
-                acc[j] = 0.0;
-            }
+                for (int j = 0; j < 8; j++) {
+                    wv[j] = wwin[wwin_pos(t0 + j)];
+                    acc[j] = 0.0;
+                }
 #pragma unroll 8
-            for (uint32_t k = 0; k < 32; k++) {
-                const double rh = rp[k];
+                for (uint32_t k = 0; k < 32; k++) {
+                    const double rh = rp[k];
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc[j] = __fma_rn(rh, wv[j], acc[j]);
+                    for (int j = 0; j < 8; j++) acc[j] = __fma_rn(rh, wv[j], acc[j]);
 #pragma unroll
-                for (int j = 7; j > 0; j--) wv[j] = wv[j - 1];
-                wv[0] = wwin[wwin_pos(max((int)(t0 - k) - 1, 0))];
-            }
+                    for (int j = 7; j > 0; j--) wv[j] = wv[j - 1];
+                    wv[0] = wwin[wwin_pos(max((int)(t0 - k) - 1, 0))];
+                }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-            }
-            if (sub == 0) {
+                for (int j = 0; j < 8; j++) {
+                    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+                    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+                }
+                if (sub == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (r0 + j < RIN) partial[(size_t)warp * sa.max_rin + r0 + j] = acc[j];
+                    for (int j = 0; j < 8; j++)
+                        if (r0 + j < RIN) partial[(size_t)seg * sa.max_rin + r0 + j] = acc[j];
+                }
             }
         }
     }
@@ -891,11 +966,13 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             t.w[0] = 0.0f; t.w[1] = 1.0f; t.w[2] = 0.0f; t.w[3] = 0.0f;
             if (valid && g.has_wake) {
                 double acc = 0.0;
-                for (uint32_t k = 0; k < NW; k++) acc += partial[(size_t)k * sa.max_rin + r];
+                for (uint32_t k = 0; k < NSEG; k++) acc += partial[(size_t)k * sa.max_rin + r];
                 const float wk = __fmul_rn(scal, (float)acc);  // src/PS/ElectricField.cpp:236-241
                 t = ivs_kick_taps(wk, n, g.it);
-                if (t.first < -16 || t.first > 8) {  // beyond the staged pad: flag, neutralise
-                    atomicExch(g.status, 1);
+                if (t.first < -16 || t.first > 8) {
+                    // beyond the staged pad: record the step (the host redoes it through the kernel
+                    // sequence, which has no such limit) and keep the addresses in range
+                    step_ctl_overflow(g, ctl);
                     t.first = -1;
                     t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.0f;
                 }
@@ -910,7 +987,12 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     __syncthreads();  // tables, pads and mailboxes visible to everybody
 
     // =============================== the row loop ==============================================
-    int wfmin = min(min(df.x, df.y), min(df.z, df.w)), wfmax = max(max(df.x, df.y), max(df.z, df.w));
+    int wfmin = 0x7fffffff, wfmax = -0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < QPT; j++) {
+        wfmin = min(wfmin, min(min(df[j].x, df[j].y), min(df[j].z, df[j].w)));
+        wfmax = max(wfmax, max(max(df[j].x, df[j].y), max(df[j].z, df[j].w)));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         wfmin = min(wfmin, __shfl_xor_sync(0xffffffffu, wfmin, o));
@@ -918,10 +1000,9 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     }
     const int spread = wfmax - wfmin;  // <= 2 (checked when the plan was made)
 
-    const uint32_t ring_q = smem_u32(ring + kPadS) + q * 16;  // this quad in slot 0
-    const int y0 = (int)(q << 2);
-    float* redw = red + warp;  // row i's partial at redw[i * NW]
-    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + q;
+    const uint32_t ring_q = smem_u32(ring + kPadS) + q[0] * 16;  // this thread's first quad in slot 0
+    const int y0 = (int)(q[0] << 2);
+    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + q[0];
     // mailboxes: this warp posts the drifted x,y of its first quad (for the left neighbour) and
     // the z,w of its last quad (for the right neighbour); lane 0 / lane 31 read the neighbours'
     const uint32_t mail_b = smem_u32(mail);
@@ -939,12 +1020,13 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
 #endif
     auto run = [&](auto nt_tag) {
         constexpr int NT = decltype(nt_tag)::value;
-        float dw[4][NT];
-        {
-            const int fs[4] = {df.x, df.y, df.z, df.w};
+        float dw[QPT][4][NT];
+#pragma unroll
+        for (int j = 0; j < QPT; j++) {
+            const int fs[4] = {df[j].x, df[j].y, df[j].z, df[j].w};
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const float wv[4] = {dwl[c].x, dwl[c].y, dwl[c].z, dwl[c].w};
+                const float wv[4] = {dwl[j][c].x, dwl[j][c].y, dwl[j][c].z, dwl[j][c].w};
                 const int off = fs[c] - wfmin;  // 0 .. NT-4
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
@@ -952,7 +1034,7 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
 #pragma unroll
                     for (int u = 0; u < 4; u++)
                         if (t - u >= 0 && t - u <= NT - 4) v = (off == t - u) ? wv[u] : v;
-                    dw[c][t] = v;
+                    dw[j][c][t] = v;
                 }
             }
         }
@@ -1003,10 +1085,17 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         // A kicked row k feeds tap NT-1 of the oldest sum (which completes it), tap NT-2 of the next,
         // ..., and starts a new one with tap 0 -- the same products added in the same order as a
         // 4-tap sum over a window of rows, without the window (and its register moves).
-        float4 P[NT - 1];
+        float4 P[QPT][NT - 1];
 #pragma unroll
-        for (int t = 0; t < NT - 1; t++) P[t] = make_float4(0, 0, 0, 0);
-        const bool near_edge = __any_sync(0xffffffffu, y0 < 16 || y0 + 19 > (int)n);
+        for (int j = 0; j < QPT; j++)
+#pragma unroll
+            for (int t = 0; t < NT - 1; t++) P[j][t] = make_float4(0, 0, 0, 0);
+        bool near_edge[QPT];
+#pragma unroll
+        for (int j = 0; j < QPT; j++) {
+            const int yj = y0 + j * 128;
+            near_edge[j] = __any_sync(0xffffffffu, yj < 16 || yj + 19 > (int)n);
+        }
         // cursor: full[] entry of the staged row the next kick reads and its phase; empty[] sits eoff behind
         uint32_t kbar = full_b + (r0 % K) * 8, kpar = (r0 / K) & 1;
         const uint32_t full_end = full_b + K * 8, eoff = empty_b - full_b;
@@ -1017,12 +1106,20 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         }
         wait_row(kbar, kpar, 0);  // the first kick's row
 
-        float4 d = make_float4(0, 0, 0, 0);  // the drifted row of this iteration
-        const uint32_t fifo_t = smem_u32(fifo) + tid * 16;  // this thread's entry of FIFO slot 0
-        float pprev = 0.0f;   // this lane's part of a finished row's sum (reduced an iteration later)
-        uint32_t redp = smem_u32(red) + warp * 4 - NW * 4;  // where the row sum reduced next goes
+        float4 d[QPT];  // the drifted row of this iteration
+#pragma unroll
+        for (int j = 0; j < QPT; j++) d[j] = make_float4(0, 0, 0, 0);
+        const uint32_t fifo_t = smem_u32(fifo) + tid * 16;  // this thread's entry (quad 0) of FIFO slot 0
+        const uint32_t fifo_j = T * 16;                     // from quad j to quad j+1 inside a FIFO slot
+        float pprev[QPT];  // this lane's part of a finished row's sum (reduced an iteration later)
+#pragma unroll
+        for (int j = 0; j < QPT; j++) pprev[j] = 0.0f;
+        // where the row sums reduced next go: lane 0 holds segment warp*QPT's, lane 16 the next one's (QPT = 2)
+        uint32_t redp = smem_u32(red) + (warp * QPT + (QPT == 2 && lane >= 16 ? 1 : 0)) * 4 - NSEG * 4;
         const size_t gstride = (size_t)nq;
         const bool edge = edge_l || edge_r;
+        const bool red_lane = QPT == 2 ? (lane & 15) == 0 : lane == 0;
+        const uint32_t lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
 
         // ---- one kick step: staged row r0 + it -> wake kick + RF kick -> window -> drifted row d
         // (output row it - NT + 1 once the window is full).  POST: d is a real output row whose edge
@@ -1034,30 +1131,32 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             if (wrap) { nbar = full_b; npar ^= 1; }
             const uint32_t landed = mbar_test(MORE ? nbar : kbar, MORE ? npar : kpar);
             const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
-            const float4 kq = kick_quad<FMA>(aload, f.x, y0 + f.y, n, near_edge, w1, w2);
+            float4 kq[QPT];
+            kick_quads<FMA, QPT>(aload, f.x, y0 + f.y, n, near_edge, w1, w2, kq);
             tp += 48;
             f = lds64i(tp + 32);  // next row's entry, a row ahead of its use
             aload += wrap ? ring_back : pitchB;  // ring_back = pitchB - K * pitchB: back to slot 0
-            {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
 #define IVS_DRIFT_COL(c, m)                                                                           \
-                d.m = madd<FMA>(kq.m, dw[c][NT - 1], P[NT - 2].m);                                    \
-                _Pragma("unroll") for (int t = NT - 2; t > 0; t--) P[t].m = madd<FMA>(kq.m, dw[c][t], P[t - 1].m); \
-                P[0].m = __fmul_rn(kq.m, dw[c][0]);
+                d[j].m = madd<FMA>(kq[j].m, dw[j][c][NT - 1], P[j][NT - 2].m);                        \
+                _Pragma("unroll") for (int t = NT - 2; t > 0; t--) P[j][t].m = madd<FMA>(kq[j].m, dw[j][c][t], P[j][t - 1].m); \
+                P[j][0].m = __fmul_rn(kq[j].m, dw[j][c][0]);
                 IVS_DRIFT_COL(0, x)
                 IVS_DRIFT_COL(1, y)
                 IVS_DRIFT_COL(2, z)
                 IVS_DRIFT_COL(3, w)
 #undef IVS_DRIFT_COL
+                // parked in this thread's FIFO entry until its stencil step kLag iterations later
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(fa + j * fifo_j), "f"(d[j].x), "f"(d[j].y), "f"(d[j].z), "f"(d[j].w) : "memory");
             }
-            // parked in this thread's FIFO entry until its stencil step kLag iterations later
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(fa), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w) : "memory");
             if (POST) {
                 const uint32_t orow = (uint32_t)(it - NT + 1);
                 const uint32_t ms = (orow & (kMailSlots - 1)) * 16;
-                // lane 0 posts (x, y) for the left neighbour, lane 31 (z, w) for the right one
+                // lane 0 posts (x, y) of its first quad for the left neighbour, lane 31 (z, w) of its last for the right one
                 const bool l0 = lane == 0;
                 sts128_volatile_if(post_me + ms,
-                                   make_float4(l0 ? d.x : d.z, l0 ? d.y : d.w, __uint_as_float(orow + 1), 0.0f),
+                                   make_float4(l0 ? d[0].x : d[QPT - 1].z, l0 ? d[0].y : d[QPT - 1].w, __uint_as_float(orow + 1), 0.0f),
                                    l0 || lane == 31);
             }
             // the staged row is in registers everywhere (its drift has been computed): hand it back
@@ -1074,16 +1173,39 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         };
         // ---- one stencil step on drifted output row `orow` (out of the FIFO): neighbours,
         // Fokker-Planck, store, partial row sum; the warp sum of the row before is reduced on the side
-        auto fp_step = [&](const int it, const float4 dprev, const uint32_t orow) {
+        auto fp_step = [&](const int it, const uint32_t fa, const uint32_t orow) {
+            float4 dp[QPT];
+#pragma unroll
+            for (int j = 0; j < QPT; j++) dp[j] = lds128(fa + j * fifo_j);
             float4 m = make_float4(0, 0, 0, 0);
             const uint32_t pa = peek + (orow & (kMailSlots - 1)) * 16;
             if (edge) m = lds128_volatile(pa);
-            float Lz = __shfl_up_sync(0xffffffffu, dprev.z, 1);
-            float Lw = __shfl_up_sync(0xffffffffu, dprev.w, 1);
-            float Rx = __shfl_down_sync(0xffffffffu, dprev.x, 1);
-            float Ry = __shfl_down_sync(0xffffffffu, dprev.y, 1);
-            float ps = pprev;
-            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 16));
+            // neighbours inside the warp: quad j of lane l sits between quad j of lanes l-1 and l+1;
+            // lane 0's left neighbour is lane 31's quad j-1, lane 31's right one lane 0's quad j+1
+            float Lz[QPT], Lw[QPT], Rx[QPT], Ry[QPT];
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                const float sz = (j > 0 && lane == 31) ? dp[j - 1].z : dp[j].z;
+                const float sw = (j > 0 && lane == 31) ? dp[j - 1].w : dp[j].w;
+                const float sx = (j + 1 < QPT && lane == 0) ? dp[j + 1].x : dp[j].x;
+                const float sy = (j + 1 < QPT && lane == 0) ? dp[j + 1].y : dp[j].y;
+                Lz[j] = __shfl_sync(0xffffffffu, sz, lane_up);
+                Lw[j] = __shfl_sync(0xffffffffu, sw, lane_up);
+                Rx[j] = __shfl_sync(0xffffffffu, sx, lane_dn);
+                Ry[j] = __shfl_sync(0xffffffffu, sy, lane_dn);
+            }
+            // the row sums of the row before: first level of the butterfly (QPT = 2: the two segments'
+            // sums are transposed into the two half-warps, same tree per segment as with one quad)
+            float ps;
+            if (QPT == 2) {
+                const bool upper = (lane & 16) != 0;
+                const float send = upper ? pprev[0] : pprev[QPT - 1];
+                const float keep = upper ? pprev[QPT - 1] : pprev[0];
+                ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+            } else {
+                ps = pprev[0];
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 16));
+            }
             if (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1)) {
                 // the neighbour is more than a row behind: poll (warp-uniformly, so that lane 0
                 // keeps serving the staging duty)
@@ -1100,38 +1222,44 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
                     if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
                 } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1));
             }
-            if (edge_l) { Lz = m.x; Lw = m.y; }
-            if (edge_r) { Rx = m.x; Ry = m.y; }
+            if (edge_l) { Lz[0] = m.x; Lw[0] = m.y; }
+            if (edge_r) { Rx[QPT - 1] = m.x; Ry[QPT - 1] = m.y; }
             // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
-            const float in[8] = {Lz, Lw, dprev.x, dprev.y, dprev.z, dprev.w, Rx, Ry};
-            float o[4];
-#define IVS_FP_COL(c)                                                   \
-            {                                                           \
-                float v = __fmul_rn(in[c], w5[c][0]);                   \
-                v = madd<FMA>(in[1 + c], w5[c][1], v);                  \
-                v = madd<FMA>(in[2 + c], w5[c][2], v);                  \
-                v = madd<FMA>(in[3 + c], w5[c][3], v);                  \
-                v = madd<FMA>(in[4 + c], w5[c][4], v);                  \
-                o[c] = v;                                               \
+            float o[QPT][4];
+#define IVS_FP_COL(j, c)                                                 \
+            {                                                            \
+                float v = __fmul_rn(in[c], w5[j][c][0]);                 \
+                v = madd<FMA>(in[1 + c], w5[j][c][1], v);                \
+                v = madd<FMA>(in[2 + c], w5[j][c][2], v);                \
+                v = madd<FMA>(in[3 + c], w5[j][c][3], v);                \
+                v = madd<FMA>(in[4 + c], w5[j][c][4], v);                \
+                o[j][c] = v;                                             \
             }
-            IVS_FP_COL(0)
-            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
-            IVS_FP_COL(1)
-            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
-            IVS_FP_COL(2)
-            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
-            IVS_FP_COL(3)
-            ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                const float in[8] = {Lz[j], Lw[j], dp[j].x, dp[j].y, dp[j].z, dp[j].w, Rx[j], Ry[j]};
+                IVS_FP_COL(j, 0)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
+                IVS_FP_COL(j, 1)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
+                IVS_FP_COL(j, 2)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
+                IVS_FP_COL(j, 3)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
+                gout[j * 32] = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
+            }
 #undef IVS_FP_COL
-            *gout = make_float4(o[0], o[1], o[2], o[3]);
             gout += gstride;
-            if (lane == 0 && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
-            redp += NW * 4;
-            float p = __fmul_rn(o[0], ws4.x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
-            p = __fadd_rn(p, __fmul_rn(o[1], ws4.y));
-            p = __fadd_rn(p, __fmul_rn(o[2], ws4.z));
-            p = __fadd_rn(p, __fmul_rn(o[3], ws4.w));
-            pprev = p;
+            if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
+            redp += NSEG * 4;
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                float p = __fmul_rn(o[j][0], ws4[j].x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
+                p = __fadd_rn(p, __fmul_rn(o[j][1], ws4[j].y));
+                p = __fadd_rn(p, __fmul_rn(o[j][2], ws4[j].z));
+                p = __fadd_rn(p, __fmul_rn(o[j][3], ws4[j].w));
+                pprev[j] = p;
+            }
         };
 
         // Iteration `it` kicks row r0 + it; from it = NT-1 on a drifted output row (it - NT + 1) comes
@@ -1139,19 +1267,19 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
         // iterations before (output row it - NT + 1 - kLag, read from the same slot before this
         // iteration's kick overwrites it), so a warp only waits for a neighbour that is more than
         // kLag - 1 rows late.
-        auto fifo_at = [&](int i) { return fifo_t + (uint32_t)(i & (kLag - 1)) * (T * 16); };
+        auto fifo_at = [&](int i) { return fifo_t + (uint32_t)(i & (kLag - 1)) * (QPT * T * 16); };
         int it = 0;
         for (; it < NT - 1 + kLag; it++) {  // fill the drift sums and the FIFO
             if (it < (int)nkicks) kick_step(it, fifo_at(it), it + 1 >= NT, it + 1 < (int)nkicks);
         }
         for (; it + 1 < (int)nkicks; it++) {  // steady state
             const uint32_t fa = fifo_at(it);
-            fp_step(it, lds128(fa), (uint32_t)(it - (NT - 1 + kLag)));
+            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
             kick_step(it, fa, true, true);
         }
         for (; it < (int)nkicks + kLag; it++) {  // the last kick and the rows still parked
             const uint32_t fa = fifo_at(it);
-            fp_step(it, lds128(fa), (uint32_t)(it - (NT - 1 + kLag)));
+            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
             if (it < (int)nkicks) kick_step(it, fa, true, false);
         }
 #if IVS_WARP_CLOCKS
@@ -1162,12 +1290,13 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
             atomicAdd(&g_wstat[3][warp], 1ull);
         }
 #endif
-        // the last row's sum
-        {
-            float p = pprev;
+        // the last row's sums
+#pragma unroll
+        for (int j = 0; j < QPT; j++) {
+            float p = pprev[j];
 #pragma unroll
             for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
-            if (lane == 0) redw[(S - 1) * NW] = p;
+            if (lane == 0) red[(S - 1) * NSEG + warp * QPT + j] = p;
         }
         // rows this warp still has to issue (its probe may have failed on the last iterations)
         {
@@ -1183,11 +1312,11 @@ __global__ void __launch_bounds__(512, 1) stream_step_kernel(const stream_args s
     else if (spread == 1) run(std::integral_constant<int, 5>{});
     else run(std::integral_constant<int, 6>{});
 
-    // the strip's row sums: one thread per row adds the warps' partials in fixed order
+    // the strip's row sums: one thread per row adds the segments' partials in fixed order
     __syncthreads();
     for (uint32_t i = tid; i < S; i += T) {
         float v = 0.0f;
-        for (uint32_t k = 0; k < NW; k++) v = __fadd_rn(v, red[i * NW + k]);
+        for (uint32_t k = 0; k < NSEG; k++) v = __fadd_rn(v, red[i * NSEG + k]);
         g.rho_out[(size_t)member * n + xa + i] = v;
     }
 }
@@ -1285,20 +1414,31 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
     plan->pad_y = kPad;
     // ---- streaming kernel (default for grid sizes that are multiples of 256, up to 2048)
     plan->stream = false;
-    const uint32_t NW = n / 128;  // warps: one quad of columns per thread
+    // quads of columns per thread: 2 (half the warps, twice the registers each) from 1024 columns on,
+    // where a row still gives a CTA at least 4 warps; IVS_SIM_QPT1 / IVS_SIM_QPT2 override
+    uint32_t qpt = n >= 1024 ? 2 : 1;
+    if (s->desc.flags & IVS_SIM_QPT1) qpt = 1;
+    if ((s->desc.flags & IVS_SIM_QPT2) && n >= 256) qpt = 2;
     bool quads_ok = n % 256 == 0 && n <= 2048;
-    // over a warp's 128 columns the first drift tap may vary by at most 2 rows (window of up to 6 rows)
-    for (uint32_t w = 0; quads_ok && w < NW; w++) {
-        const auto mm = std::minmax_element(dr_first.begin() + 128 * w, dr_first.begin() + 128 * (w + 1));
-        quads_ok = *mm.second - *mm.first <= 2;
-    }
+    // over a warp's 128 * qpt columns the first drift tap may vary by at most 2 rows (window of up to 6 rows)
+    auto spread_ok = [&](uint32_t cols) {
+        for (uint32_t w = 0; w < n / cols; w++) {
+            const auto mm = std::minmax_element(dr_first.begin() + cols * w, dr_first.begin() + cols * (w + 1));
+            if (*mm.second - *mm.first > 2) return false;
+        }
+        return true;
+    };
+    if (quads_ok && qpt == 2 && !spread_ok(256)) qpt = 1;
+    quads_ok = quads_ok && spread_ok(128 * qpt);
     if (quads_ok && !(s->desc.flags & IVS_SIM_TILED)) {
         const uint32_t H = plan->halo_lo + plan->halo_hi;
-        const uint32_t threads_s = n / 4;
+        const uint32_t threads_s = n / 4 / qpt;
+        const uint32_t NW = threads_s / 32;  // warps of a CTA
         const uint32_t pitch = n + 2 * kPadS;
         auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
         const bool fma = ctx->arith == IVS_ARITH_FMA;
-        const void* kfn = fma ? (const void*)stream_step_kernel<true> : (const void*)stream_step_kernel<false>;
+        const void* kfn = qpt == 2 ? (fma ? (const void*)stream_step_kernel<true, 2> : (const void*)stream_step_kernel<false, 2>)
+                                   : (fma ? (const void*)stream_step_kernel<true, 1> : (const void*)stream_step_kernel<false, 1>);
         cudaFuncAttributes fa;
         IVS_CUDA(ctx, cudaFuncGetAttributes(&fa, kfn));
         const uint32_t regs_thread = (std::max(fa.numRegs, 32) + 7) & ~7;
@@ -1310,15 +1450,11 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         // for the strip, so shorter strips leave room for more CTAs per SM (small grids) while longer
         // ones amortise the set-up and the halo rows.  Cost = rounds of CTAs over the machine x (rows
         // through the pipeline per CTA + a set-up worth ~16 rows), scaled by how well the resident
-        // warps fill the four schedulers (16 warps per SM saturate this kernel).
+        // warps fill the four schedulers (16 quads per lane and SM saturate this kernel).
         double best = 1e300;
         uint32_t bestP = 0, bestK = 0, best_rin = 0;
         size_t best_sb = 0, best_wwin = 0;
-        // development aids: IVS_FORCE_STRIPS=<P> pins the number of strips per member,
-        // IVS_PLAN_DEBUG=1 prints the plan that was chosen
-        const char* force_env = getenv("IVS_FORCE_STRIPS");
-        const uint32_t forceP = force_env ? (uint32_t)atoi(force_env) : 0;
-        uint32_t best_want = 0;
+        const uint32_t forceP = s->desc.strips;  // 0: the planner's choice
         for (uint32_t P = 1; P <= n / kMinStrip && kmin <= kmax; P++) {
             if (forceP && P != forceP) continue;
             const uint32_t S0 = ivs_div_up(n, P);
@@ -1330,9 +1466,9 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             const uint32_t max_rin = S0 + H;
             const uint32_t wcount = n + ((max_rin + 63) & ~63u);
             const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
-            const size_t fixed = a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) + a16((size_t)NW * max_rin * 8) +
-                                 a16((size_t)S0 * NW * 4) + a16((size_t)(max_rin + 1) * 48) +
-                                 a16((size_t)NW * 2 * kMailSlots * 16) + a16((size_t)kLag * threads_s * 16);
+            const size_t fixed = a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) + a16((size_t)(n / 128) * max_rin * 8) +
+                                 a16((size_t)S0 * (n / 128) * 4) + a16((size_t)(max_rin + 1) * 48) +
+                                 a16((size_t)NW * 2 * kMailSlots * 16) + a16((size_t)kLag * (n / 4) * 16);
             uint32_t want = std::min<uint32_t>(by_regs, 16), K = 0;
             size_t sb = 0;
             for (; want >= 1; want--) {
@@ -1348,16 +1484,13 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             const uint64_t slots = (uint64_t)ctx->sm_count * want;
             const uint64_t rounds = (units + slots - 1) / slots;
             const uint32_t resident = (uint32_t)std::min<uint64_t>(want, ivs_div_up((uint32_t)units, ctx->sm_count));
-            const double fill = std::min(1.0, resident * (threads_s / 32) / 16.0);  // of 16 warps per SM
+            const double fill = std::min(1.0, resident * (n / 128) / 16.0);  // of 16 segments in flight per SM
             const double cost = (double)rounds * (S0 + H + 16) * resident / std::max(fill, 1.0 / 16);
-            if (cost < best) { best = cost; bestP = P; bestK = K; best_sb = sb; best_rin = max_rin; best_wwin = wwin_len; best_want = want; }
+            if (cost < best) { best = cost; bestP = P; bestK = K; best_sb = sb; best_rin = max_rin; best_wwin = wwin_len; }
         }
-        if (bestP && getenv("IVS_PLAN_DEBUG"))
-            fprintf(stderr, "[ivs plan] n %u members %u: %u strips of %u rows, halo %u, ring %u slots, %zu B shared memory, %u CTAs/SM, %u CTAs\n",
-                    n, s->members, bestP, ivs_div_up(n, bestP), H, bestK, best_sb, best_want, bestP * s->members);
         if (bestP) {
             // Fokker-Planck weights with the taps that fall outside the grid zeroed: the shuffles
-            // deliver a lane's own value there instead of the tile kernels' zero pad
+            // deliver another lane's value there instead of the tile kernels' zero pad
             std::vector<float> fps(fpw);
             fps[0] = fps[1] = 0.0f;
             fps[5] = 0.0f;
@@ -1366,6 +1499,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             IVS_CUDA(ctx, cudaMalloc(&plan->fp5, (size_t)n * 20));
             IVS_CUDA(ctx, cudaMemcpy(plan->fp5, fps.data(), (size_t)n * 20, cudaMemcpyHostToDevice));
             plan->stream = true;
+            plan->qpt = qpt;
             plan->strip = ivs_div_up(n, bestP);
             plan->kslots = bestK;
             plan->max_strip = plan->strip;
@@ -1487,6 +1621,7 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
     a.fp_w5 = s->fpw;
     a.ws = s->ws;
     a.status = s->status;
+    a.host_flag = s->host_flag;
     a.n = s->n; a.it = s->it; a.hl = plan->halo_lo; a.hr = plan->halo_hi; a.pitch = s->n + 2 * kPad;
     a.has_wake = s->has_wake ? 1 : 0;
     ivs_status st;
@@ -1498,8 +1633,14 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
         sa.strip = plan->strip; sa.kslots = plan->kslots;
         sa.max_strip = plan->max_strip; sa.max_rin = plan->max_rin; sa.wwin_len = plan->wwin_len;
         const dim3 sgrid(ivs_div_up(s->n, plan->strip), s->members);
-        if (ctx->arith == IVS_ARITH_FMA) stream_step_kernel<true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
-        else stream_step_kernel<false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+        const bool fma = ctx->arith == IVS_ARITH_FMA;
+        if (plan->qpt == 2) {
+            if (fma) stream_step_kernel<true, 2><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+            else stream_step_kernel<false, 2><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+        } else {
+            if (fma) stream_step_kernel<true, 1><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+            else stream_step_kernel<false, 1><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+        }
         IVS_LAUNCHED(ctx);
         st = IVS_OK;
         goto launched;
@@ -1527,7 +1668,7 @@ launched:
     if (s->np) {
         st = ivs_track_step_launch(ctx, s->particles, s->np, s->members, s->n, s->has_wake ? s->wake : nullptr,
                                    s->rf, s->drift, s->has_fp ? s->fpw : nullptr, nullptr, s->desc.fptrack,
-                                   s->desc.e1, s->desc.dp, s->desc.seed, s->track_counter);
+                                   s->desc.e1, s->desc.dp, s->desc.seed, s->track_counter, s->status);
     }
     return st;
 }

@@ -33,7 +33,8 @@ ivs_status ivs_field_prepare(ivs_ctx* ctx, uint32_t nmax);
 ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
                                  uint32_t n, const float* wake, const float* rf, const float* drift,
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
-                                 float dp, uint64_t seed, unsigned int* step_counter);
+                                 float dp, uint64_t seed, unsigned int* step_counter,
+                                 const int* sim_status = nullptr);
 
 // the fused step kernel (ivs_fused.cu)
 struct ivs_fused_plan {
@@ -48,7 +49,8 @@ struct ivs_fused_plan {
     void* dr_first = nullptr; void* dr_w = nullptr;
     void* fp_base = nullptr; void* fp_w = nullptr;
     bool vec = false;   // float4-per-lane kernel (grid size multiple of 256)
-    bool stream = false;  // streaming kernel (independent warps, one quad of columns per thread)
+    bool stream = false;  // streaming kernel (independent warps, qpt quads of columns per thread)
+    uint32_t qpt = 1;
     uint32_t strip = 0, kslots = 0, max_strip = 0, max_rin = 0, wwin_len = 0;
     void* fp5 = nullptr;  // Fokker-Planck weights, out-of-grid taps zeroed (streaming kernel)
     bool ready = false;

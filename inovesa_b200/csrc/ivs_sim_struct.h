@@ -26,14 +26,20 @@ struct ivs_sim {
     float* integral = nullptr;    // [members]
     float* moments = nullptr;     // [members][2][3]
     float* power = nullptr;       // [members]
-    int* status = nullptr;        // device error flag of the fused kernel
+    // bookkeeping of the fused kernels (ivs_fused.cu, step_ctl_begin): status[0] = ordinal of the first
+    // step whose wake kick left the staged pad (0x7fffffff: none), status[1] = CTA tickets
+    int* status = nullptr;
+    int* host_flag = nullptr;     // host-mapped word, set together with status[0]: peeked without a sync
+    uint64_t fused_enqueued = 0;  // fused steps enqueued since the status words were last reset ...
+    int cur_at_reset = 0;         // ... and the buffer parity at that moment
+    uint64_t fallback_steps = 0;  // steps redone through the kernel sequence after an overflow
     unsigned int* track_counter = nullptr;  // device step counter of the stochastic tracking mode (+ block ticket)
     float f_scale = 0, cutoff = 0;
     uint64_t steps_done = 0;
     ivs_fused_plan plan{};
-    cudaGraphExec_t graph1 = nullptr;   // one step
-    cudaGraphExec_t graphK = nullptr;   // kGraphSteps steps
-    int graph_cur = -1;                 // buffer parity the graphs were captured for
+    // fused steps ping-pong two buffers: one graph per buffer parity (captured at creation)
+    cudaGraphExec_t graph1[2] = {nullptr, nullptr};   // one step (unfused sequence only)
+    cudaGraphExec_t graphK[2] = {nullptr, nullptr};   // kGraphSteps steps
     static constexpr uint32_t kGraphSteps = 16;
 };
 

@@ -32,12 +32,13 @@ ivs_status dalloc(ivs_ctx* ctx, T** p, size_t count) {
     } while (0)
 
 // one step as the reference's kernel sequence (src/main.cpp:948-1053), grids wired
-// wm: t1->t2, rfm: t2->t1, drm: t1->t3, fpm: t3->t1 (:593-763)
+// wm: t1->t2, rfm: t2->t1, drm: t1->t3, fpm: t3->t1 (:593-763); t1 = the current buffer (it stays
+// the current one), t2 = the other ping-pong buffer, t3 = the third grid
 ivs_status enqueue_unfused_step(ivs_sim* s) {
     ivs_ctx* ctx = s->ctx;
     const uint32_t n = s->n, m = s->members;
-    float *t1 = s->grid[0], *t2 = s->grid[1], *t3 = s->grid[2];
-    float* prof = s->profile[0];
+    float *t1 = s->grid[s->cur], *t2 = s->grid[s->cur ^ 1], *t3 = s->grid[2];
+    float* prof = s->profile[s->pcur];
     const size_t bytes = (size_t)m * n * n * sizeof(float);
     if (s->has_wake) {
         // wkm->update(): ElectricField::wakePotential -> offsets (src/SM/WakePotentialMap.cpp:34-50)
@@ -69,17 +70,18 @@ ivs_status enqueue_step(ivs_sim* s) {
 }
 
 void drop_graphs(ivs_sim* s) {
-    if (s->graph1) cudaGraphExecDestroy(s->graph1);
-    if (s->graphK) cudaGraphExecDestroy(s->graphK);
-    s->graph1 = s->graphK = nullptr;
-    s->graph_cur = -1;
+    for (int k = 0; k < 2; k++) {
+        if (s->graph1[k]) cudaGraphExecDestroy(s->graph1[k]);
+        if (s->graphK[k]) cudaGraphExecDestroy(s->graphK[k]);
+        s->graph1[k] = s->graphK[k] = nullptr;
+    }
 }
 
 ivs_status capture(ivs_sim* s, uint32_t steps, cudaGraphExec_t* out) {
     ivs_ctx* ctx = s->ctx;
     cudaGraph_t g = nullptr;
     const int cur0 = s->cur, pcur0 = s->pcur;
-    const uint64_t launches0 = ctx->launches, done0 = s->steps_done;
+    const uint64_t launches0 = ctx->launches, done0 = s->steps_done, enq0 = s->fused_enqueued;
     IVS_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     ivs_status st = IVS_OK;
     for (uint32_t i = 0; i < steps && st == IVS_OK; i++) {
@@ -88,7 +90,7 @@ ivs_status capture(ivs_sim* s, uint32_t steps, cudaGraphExec_t* out) {
     }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
     // capture only records; restore the bookkeeping it advanced
-    s->cur = cur0; s->pcur = pcur0; ctx->launches = launches0; s->steps_done = done0;
+    s->cur = cur0; s->pcur = pcur0; ctx->launches = launches0; s->steps_done = done0; s->fused_enqueued = enq0;
     if (st != IVS_OK) { if (g) cudaGraphDestroy(g); return st; }
     if (e != cudaSuccess) return ivs_check_cuda(ctx, e, "cudaStreamEndCapture");
     e = cudaGraphInstantiate(out, g, 0);
@@ -145,6 +147,8 @@ std::vector<double> wake_function_host(const float* z, uint32_t nmax, uint32_t n
 }  // namespace
 
 extern "C" {
+
+static ivs_status reset_status(ivs_sim* s);
 
 ivs_status ivs_wake_function(ivs_ctx* ctx, const void* d_impedance, uint32_t nmax,
                              float wakescaling, uint32_t n, void* d_wakefunction) {
@@ -203,7 +207,13 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
     S_TRY(dalloc(ctx, &s->moments, (size_t)m * 6));
     S_TRY(dalloc(ctx, &s->power, m));
     S_TRY(dalloc(ctx, &s->status, 4));
-    S_TRY(ivs_memset_zero(ctx, s->status, 4 * sizeof(int)));
+    {
+        void* hf = nullptr;
+        cudaError_t e = cudaHostAlloc(&hf, 64, cudaHostAllocMapped);
+        if (e != cudaSuccess) return fail(ivs_check_cuda(ctx, e, "cudaHostAlloc"));
+        s->host_flag = (int*)hf;
+    }
+    S_TRY(reset_status(s));
     S_TRY(dalloc(ctx, &s->track_counter, 4));
     S_TRY(ivs_memset_zero(ctx, s->track_counter, 4 * sizeof(unsigned int)));
     S_TRY(ivs_memset_zero(ctx, s->wake, (size_t)m * n * sizeof(float)));
@@ -241,6 +251,19 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
     S_TRY(ivs_project_x_batched(ctx, s->grid[0], n, m, s->ws, s->profile[0]));
     if (!unfused) S_TRY(ivs_fused_plan_create(ctx, s, &s->plan));
     S_TRY(ivs_sync(ctx));
+    // the step graphs are captured and instantiated here, one per buffer parity, so that no
+    // ivs_sim_step ever pays for it
+    if (!(d->flags & IVS_SIM_NO_GRAPH)) {
+        S_TRY(capture(s, ivs_sim::kGraphSteps, &s->graphK[0]));
+        if (unfused) {
+            S_TRY(capture(s, 1, &s->graph1[0]));
+        } else {
+            s->cur = s->pcur = 1;
+            st = capture(s, ivs_sim::kGraphSteps, &s->graphK[1]);
+            s->cur = s->pcur = 0;
+            if (st != IVS_OK) return fail(st);
+        }
+    }
 #undef S_TRY
     // the descriptor's host pointers are not retained
     s->desc.rf_offset = s->desc.drift_offset = s->desc.fp_weights = s->desc.impedance = nullptr;
@@ -261,37 +284,35 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
                      (float*)s->track_counter};
     for (float* b : bufs) if (b) cudaFree(b);
     if (s->status) cudaFree(s->status);
+    if (s->host_flag) cudaFreeHost(s->host_flag);
     delete s;
     return IVS_OK;
 }
 
-ivs_status ivs_sim_step(ivs_sim* s, uint32_t nsteps) {
-    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+// enqueue nsteps steps: replays of the kGraphSteps-step graph of the current buffer parity plus
+// direct launches for the remainder
+static ivs_status enqueue_steps(ivs_sim* s, uint32_t nsteps) {
     ivs_ctx* ctx = s->ctx;
-    IVS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool use_graph = !(s->desc.flags & IVS_SIM_NO_GRAPH);
     const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
-    // (tracking with the stochastic Fokker-Planck mode keys its generator on a step counter the
-    // tracking kernel keeps on the device, so a replayed graph draws fresh numbers every step)
-    const bool graph_ok = use_graph;
-    // fused steps ping-pong two buffers: a graph is valid for an even number of steps only,
-    // or for the parity it was captured at
     const uint32_t lps = launches_per_step(s);
     uint32_t left = nsteps;
-    if (graph_ok) {
-        const uint32_t K = ivs_sim::kGraphSteps;  // even
-        if (s->graph_cur != s->cur) drop_graphs(s);
+    if (use_graph) {
+        const uint32_t K = ivs_sim::kGraphSteps;  // even: a replay leaves the parity as it was
         while (left >= K) {
-            if (!s->graphK) { IVS_TRY(capture(s, K, &s->graphK)); s->graph_cur = s->cur; }
-            IVS_CUDA(ctx, cudaGraphLaunch(s->graphK, ctx->stream));
+            cudaGraphExec_t& gk = s->graphK[s->cur];
+            if (!gk) IVS_TRY(capture(s, K, &gk));
+            IVS_CUDA(ctx, cudaGraphLaunch(gk, ctx->stream));
             ctx->launches += (uint64_t)lps * K;
             s->steps_done += K;
+            if (!unfused) s->fused_enqueued += K;
             left -= K;
         }
         if (unfused) {
             while (left > 0) {
-                if (!s->graph1) { IVS_TRY(capture(s, 1, &s->graph1)); s->graph_cur = s->cur; }
-                IVS_CUDA(ctx, cudaGraphLaunch(s->graph1, ctx->stream));
+                cudaGraphExec_t& g1 = s->graph1[s->cur];
+                if (!g1) IVS_TRY(capture(s, 1, &g1));
+                IVS_CUDA(ctx, cudaGraphLaunch(g1, ctx->stream));
                 ctx->launches += lps;
                 s->steps_done++;
                 left--;
@@ -306,11 +327,66 @@ ivs_status ivs_sim_step(ivs_sim* s, uint32_t nsteps) {
     return IVS_OK;
 }
 
+static ivs_status reset_status(ivs_sim* s) {
+    ivs_ctx* ctx = s->ctx;
+    const int words[4] = {0x7fffffff, 0, 0, 0};
+    IVS_CUDA(ctx, cudaMemcpyAsync(s->status, words, sizeof(words), cudaMemcpyHostToDevice, ctx->stream));
+    IVS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *reinterpret_cast<volatile int*>(s->host_flag) = 0;
+    s->fused_enqueued = 0;
+    s->cur_at_reset = s->cur;
+    return IVS_OK;
+}
+
+// Wait for the stream; if a fused step left the staged pad (see ivs_fused.cu, step_ctl_begin), rewind
+// to the input of that step -- intact in the ping-pong buffer, since every later step exited without
+// writing --, redo it through the kernel sequence and re-enqueue the steps after it.  On return
+// the state is what `steps_done` steps of the reference's loop produce.
+static ivs_status settle(ivs_sim* s) {
+    ivs_ctx* ctx = s->ctx;
+    for (;;) {
+        IVS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((s->desc.flags & IVS_SIM_UNFUSED) || s->fused_enqueued == 0) return IVS_OK;
+        if (*reinterpret_cast<volatile int*>(s->host_flag) == 0) {
+            // clean; keep the 32-bit ticket counter far from wrapping
+            if (s->fused_enqueued > (1u << 20)) IVS_TRY(reset_status(s));
+            return IVS_OK;
+        }
+        int words[4];
+        IVS_CUDA(ctx, cudaMemcpy(words, s->status, sizeof(words), cudaMemcpyDeviceToHost));
+        const uint64_t good = (uint64_t)words[0];  // fused steps since the reset that are valid
+        if (words[0] < 0 || good >= s->fused_enqueued)
+            return ivs_fail(ctx, IVS_ERR_HALO, "inconsistent overflow bookkeeping of the fused step kernel");
+        const uint64_t redo = s->fused_enqueued - good;  // the offending step and those after it
+        s->cur = s->pcur = s->cur_at_reset ^ (int)(good & 1);
+        s->steps_done -= redo;
+        IVS_TRY(reset_status(s));
+        if (!s->grid[2]) IVS_TRY(dalloc(ctx, &s->grid[2], (size_t)s->members * s->n * s->n));
+        IVS_TRY(enqueue_unfused_step(s));
+        s->steps_done++;
+        s->fallback_steps++;
+        if (redo > 1) IVS_TRY(enqueue_steps(s, (uint32_t)(redo - 1)));
+    }
+}
+
+ivs_status ivs_sim_step(ivs_sim* s, uint32_t nsteps) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_CUDA(ctx, cudaSetDevice(ctx->device));
+    // an overflow seen so far (no sync: the flag is host-mapped) is repaired before more is enqueued
+    if (s->host_flag && (*reinterpret_cast<volatile int*>(s->host_flag) != 0 ||
+                         s->fused_enqueued + nsteps > (1u << 21)))
+        IVS_TRY(settle(s));
+    return enqueue_steps(s, nsteps);
+}
+
 uint64_t ivs_sim_steps_done(const ivs_sim* s) { return s ? s->steps_done : 0; }
+uint64_t ivs_sim_fallback_steps(const ivs_sim* s) { return s ? s->fallback_steps : 0; }
 
 ivs_status ivs_sim_state(ivs_sim* s, void** d_grid, void** d_profile, void** d_wake,
                          void** d_particles) {
     if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    IVS_TRY(settle(s));
     if (d_grid) *d_grid = s->grid[s->cur];
     if (d_profile) *d_profile = s->profile[s->pcur];
     if (d_wake) *d_wake = s->wake;
@@ -322,17 +398,12 @@ ivs_status ivs_sim_download(ivs_sim* s, float* grid, float* profile, float* wake
     if (!s) return IVS_ERR_INVALID_ARGUMENT;
     ivs_ctx* ctx = s->ctx;
     const size_t n = s->n, m = s->members;
+    IVS_TRY(settle(s));
     if (grid) IVS_CUDA(ctx, cudaMemcpyAsync(grid, s->grid[s->cur], m * n * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (profile) IVS_CUDA(ctx, cudaMemcpyAsync(profile, s->profile[s->pcur], m * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (wake) IVS_CUDA(ctx, cudaMemcpyAsync(wake, s->wake, m * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (particles && s->np) IVS_CUDA(ctx, cudaMemcpyAsync(particles, s->particles, m * s->np * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     IVS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    int status[4] = {0, 0, 0, 0};
-    IVS_CUDA(ctx, cudaMemcpy(status, s->status, sizeof(status), cudaMemcpyDeviceToHost));
-    if (status[0] != 0)
-        return ivs_fail(ctx, IVS_ERR_HALO,
-                        "a kick displacement exceeded the halo staged by the fused step kernel; "
-                        "re-create the simulation with IVS_SIM_UNFUSED");
     return IVS_OK;
 }
 
@@ -341,6 +412,7 @@ ivs_status ivs_sim_upload_grid(ivs_sim* s, const float* grid) {
     ivs_ctx* ctx = s->ctx;
     IVS_REQUIRE(ctx, grid != nullptr, "ivs_sim_upload_grid: null pointer");
     const size_t n = s->n, m = s->members;
+    if (s->host_flag && *reinterpret_cast<volatile int*>(s->host_flag) != 0) IVS_TRY(settle(s));
     IVS_CUDA(ctx, cudaMemcpyAsync(s->grid[s->cur], grid, m * n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     return ivs_project_x_batched(ctx, s->grid[s->cur], s->n, s->members, s->ws, s->profile[s->pcur]);
 }
@@ -368,6 +440,7 @@ ivs_status ivs_sim_observe(ivs_sim* s, float* obs) {
     ivs_ctx* ctx = s->ctx;
     IVS_REQUIRE(ctx, obs != nullptr, "ivs_sim_observe: null pointer");
     const uint32_t n = s->n, m = s->members;
+    IVS_TRY(settle(s));
     const float* g = s->grid[s->cur];
     const float* prof = s->profile[s->pcur];
     IVS_TRY(ivs_integrate_batched(ctx, prof, n, m, s->ws, s->integral));
@@ -396,6 +469,7 @@ ivs_status ivs_sim_observe(ivs_sim* s, float* obs) {
 ivs_status ivs_sim_renormalize(ivs_sim* s) {
     if (!s) return IVS_ERR_INVALID_ARGUMENT;
     ivs_ctx* ctx = s->ctx;
+    IVS_TRY(settle(s));
     IVS_TRY(ivs_integrate_batched(ctx, s->profile[s->pcur], s->n, s->members, s->ws, s->integral));
     return ivs_normalize_batched(ctx, s->grid[s->cur], s->n, s->members, 1.0f, s->integral);
 }
@@ -405,6 +479,7 @@ ivs_status ivs_sim_set_rf_offset(ivs_sim* s, const float* rf_offset) {
     ivs_ctx* ctx = s->ctx;
     IVS_REQUIRE(ctx, rf_offset != nullptr, "ivs_sim_set_rf_offset: null pointer");
     IVS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IVS_TRY(settle(s));
     if (!(s->desc.flags & IVS_SIM_UNFUSED)) IVS_TRY(ivs_fused_plan_set_rf(ctx, &s->plan, s, rf_offset));
     // the stream orders the copy after the steps already enqueued; the host array is consumed here
     IVS_TRY(ivs_upload(ctx, s->rf, rf_offset, s->n * sizeof(float)));

@@ -168,8 +168,12 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
                                   uint32_t n, const float* __restrict__ wake, const float* __restrict__ rf,
                                   const float* __restrict__ drift, const float* __restrict__ w5,
                                   const float* __restrict__ grid, uint32_t fptrack, float e1,
-                                  float sigma, uint64_t seed, unsigned int* counter) {
+                                  float sigma, uint64_t seed, unsigned int* counter,
+                                  const int* __restrict__ sim_status) {
     constexpr int P = kTrackPerThread;
+    // the fused step this launch belongs to (or an earlier one) left its staged pad and will be
+    // redone by the host: the particles stay where they are (ivs_fused.cu, step_ctl_begin)
+    if (sim_status && *sim_status != 0x7fffffff) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t member = blockIdx.y;
     const bool stochastic = w5 && fptrack == 3;
@@ -213,9 +217,11 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
                 const uint64_t h = mix64(skey + ((uint64_t)member << 32) + ((uint64_t)k << 28) + i);
                 const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0,1)
                 const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
-                const float r = sqrtf(-2.0f * __logf(u1));
+                // logf (not __logf: its absolute error exceeds |log u1| for u1 next to 1 and could
+                // make the radicand negative) and sincospif, the same functions as track_fp_kernel
+                const float r = sqrtf(fmaxf(-2.0f * logf(u1), 0.0f));
                 float sn, cs;
-                __sincosf(6.2831853071795864f * u2, &sn, &cs);
+                sincospif(2.0f * u2, &sn, &cs);
                 p[k].y = IVS_SUB(p[k].y, IVS_ADD(IVS_MUL(p[k].y, e1), IVS_MUL(sigma, r * cs)));
                 p[k + 1].y = IVS_SUB(p[k + 1].y, IVS_ADD(IVS_MUL(p[k + 1].y, e1), IVS_MUL(sigma, r * sn)));
             }
@@ -242,13 +248,13 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
 ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
                                  uint32_t n, const float* wake, const float* rf, const float* drift,
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
-                                 float dp, uint64_t seed, unsigned int* step_counter) {
+                                 float dp, uint64_t seed, unsigned int* step_counter, const int* sim_status) {
     if (np == 0) return IVS_OK;
     const uint32_t quarter = ivs_div_up(np, kTrackPerThread);
     const float sigma = sqrtf(2.0f * e1) / dp;  // uniform, in the reference's fp32 operations
     track_step_kernel<<<dim3(ivs_div_up(quarter, 256), members), 256, 0, ctx->stream>>>(
         (float2*)particles, np, quarter, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, sigma, seed,
-        step_counter);
+        step_counter, sim_status);
     IVS_LAUNCHED(ctx);
     return IVS_OK;
 }

@@ -108,7 +108,7 @@ class SimDesc(C.Structure):
     _fields_ = [
         ("n", C.c_uint32), ("members", C.c_uint32), ("it", C.c_uint32), ("nmax", C.c_uint32),
         ("n_particles", C.c_uint32), ("fptrack", C.c_uint32), ("flags", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("strips", C.c_uint32),
         ("dq", C.c_float), ("dp", C.c_float), ("e1", C.c_float), ("qmin", C.c_float),
         ("pmin", C.c_float), ("reserved_f", C.c_float),
         ("rf_offset", C.c_void_p), ("drift_offset", C.c_void_p), ("fp_weights", C.c_void_p),

@@ -83,6 +83,8 @@ class Oracle:
         L.orc_derive.argtypes = [C.POINTER(RingParams), C.POINTER(Derived)]
         L.orc_sim_create.restype = P
         L.orc_sim_create.argtypes = [C.POINTER(RingParams), P, P, u32]
+        L.orc_sim_create_z.restype = P
+        L.orc_sim_create_z.argtypes = [C.POINTER(RingParams), P, P, u32, P, P]
         L.orc_sim_destroy.argtypes = [P]
         L.orc_sim_step.argtypes = [P, u32]
         L.orc_sim_derived.argtypes = [P, C.POINTER(Derived)]
@@ -210,8 +212,10 @@ class Oracle:
         self.lib.orc_derive(C.byref(params), C.byref(d))
         return d
 
-    def sim(self, params, grid=None, particles=None):
-        return _Sim(self.lib, "orc", params, grid, particles)
+    def sim(self, params, grid=None, particles=None, zwake=None, zrad=None):
+        """zwake / zrad: impedance tables made earlier by make_impedance with the same parameters
+        (tests/golden/impedance_tables.npz for the parallel-plates configs)"""
+        return _Sim(self.lib, "orc", params, grid, particles, zwake, zrad)
 
 
 class Ref:
@@ -357,13 +361,19 @@ class Ref:
 class _Sim:
     """whole-simulation handle with the same surface for Oracle and Ref"""
 
-    def __init__(self, lib, prefix, params, grid, particles):
+    def __init__(self, lib, prefix, params, grid, particles, zwake=None, zrad=None):
         self.lib, self.px = lib, prefix
         self.n = params.grid_size
         g = None if grid is None else np.ascontiguousarray(grid, f32)
         p = None if particles is None else np.ascontiguousarray(particles, f32)
         self.np = 0 if p is None else len(p)
-        self.h = getattr(lib, prefix + "_sim_create")(C.byref(params), _opt(g), _opt(p), self.np)
+        if zwake is not None or zrad is not None:
+            assert prefix == "orc"
+            zw = None if zwake is None else np.ascontiguousarray(zwake, f32)
+            zr = None if zrad is None else np.ascontiguousarray(zrad, f32)
+            self.h = lib.orc_sim_create_z(C.byref(params), _opt(g), _opt(p), self.np, _opt(zw), _opt(zr))
+        else:
+            self.h = getattr(lib, prefix + "_sim_create")(C.byref(params), _opt(g), _opt(p), self.np)
         if not self.h:
             raise RuntimeError("sim_create failed")
         self.derived = Derived()

@@ -980,9 +980,11 @@ static void sim_rebuild_tables(orc_sim* s) {
     orc_kick_update_sm(s->drift, s->n, s->n, s->it, s->dr_idx, s->dr_w);
 }
 
-/* object wiring of src/main.cpp:478-763 */
-orc_sim* orc_sim_create(const ivs_ring_params* p, const float* grid, const float* particles,
-                        uint32_t np) {
+/* object wiring of src/main.cpp:478-763.  zwake / zrad: impedance tables computed earlier by
+ * orc_make_impedance with the same parameters (the Airy quadrature of the parallel-plates model
+ * takes minutes; tests keep the tables in tests/golden/), NULL = compute them here */
+orc_sim* orc_sim_create_z(const ivs_ring_params* p, const float* grid, const float* particles,
+                          uint32_t np, const float* zwake, const float* zrad) {
     orc_sim* s = (orc_sim*)calloc(1, sizeof(orc_sim));
     s->p = *p;
     orc_derive(p, &s->d);
@@ -1042,11 +1044,17 @@ orc_sim* orc_sim_create(const ivs_ring_params* p, const float* grid, const float
         for (uint32_t y = 0; y < n; y++) for (int k = 0; k < 5; k++) s->fp5[y * 5 + k] = (k == 2);
     }
     /* impedances, :717-727 */
-    s->has_wake = orc_make_impedance(s->nmax, d->fmax, d->R_bend, d->f_rev, p->gap, p->use_csr,
-                                     p->wall_conductivity, p->wall_susceptibility, p->collimator,
-                                     s->zwake);
-    orc_make_impedance(s->nmax, d->fmax, d->R_bend, d->f_rev, (p->gap > 0) ? p->gap : -1, 1, 0, 0,
-                       0, s->zrad);
+    if (zwake) {
+        memcpy(s->zwake, zwake, sizeof(float) * 2 * s->nmax);
+        s->has_wake = 1;
+    } else {
+        s->has_wake = orc_make_impedance(s->nmax, d->fmax, d->R_bend, d->f_rev, p->gap, p->use_csr,
+                                         p->wall_conductivity, p->wall_susceptibility, p->collimator,
+                                         s->zwake);
+    }
+    if (zrad) memcpy(s->zrad, zrad, sizeof(float) * 2 * s->nmax);
+    else orc_make_impedance(s->nmax, d->fmax, d->R_bend, d->f_rev, (p->gap > 0) ? p->gap : -1, 1, 0, 0,
+                            0, s->zrad);
     s->np = np;
     if (np) {
         s->particles = (float*)malloc(sizeof(float) * 2 * np);
@@ -1055,6 +1063,11 @@ orc_sim* orc_sim_create(const ivs_ring_params* p, const float* grid, const float
     orc_project_x(n, s->t1, s->ws, s->proj); /* :893-894 */
     s->filling = orc_integrate(n, s->proj, s->ws);
     return s;
+}
+
+orc_sim* orc_sim_create(const ivs_ring_params* p, const float* grid, const float* particles,
+                        uint32_t np) {
+    return orc_sim_create_z(p, grid, particles, np, NULL, NULL);
 }
 
 void orc_sim_destroy(orc_sim* s) {

@@ -123,6 +123,9 @@ void orc_derive(const ivs_ring_params* p, ivs_derived* d);
 typedef struct orc_sim orc_sim;
 orc_sim* orc_sim_create(const ivs_ring_params* p, const float* grid, const float* particles,
                         uint32_t np);
+/* the same with impedance tables made earlier by orc_make_impedance (NULL = compute here) */
+orc_sim* orc_sim_create_z(const ivs_ring_params* p, const float* grid, const float* particles,
+                          uint32_t np, const float* zwake, const float* zrad);
 void orc_sim_destroy(orc_sim* s);
 void orc_sim_step(orc_sim* s, uint32_t nsteps);
 void orc_sim_derived(const orc_sim* s, ivs_derived* d);

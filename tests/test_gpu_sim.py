@@ -214,15 +214,54 @@ def test_stochastic_tracking_is_reproducible_and_graph_safe(capi, ctx_fma, rng):
     assert 0.9 < spread < 1.1
 
 
-def test_fused_flags_displacements_beyond_its_halo(capi, ctx_strict):
-    """a wake kick of many cells cannot be served from the staged pad: the step must say so"""
-    p = kara_params(grid_size=128, bunch_current=5.0)  # absurd current -> huge wake offsets
-    sim = capi.Simulation(ctx_strict, p, 1)
-    sim.step(2)
-    with pytest.raises(capi.IvsError) as e:
-        sim.download()
-    assert e.value.code == capi.ERR_HALO
-    sim.close()
+@pytest.mark.parametrize("flags", ["stream", "tiled", "nograph"])
+def test_fused_recovers_from_displacements_beyond_its_pad(capi, ctx_strict, oracle, rng, flags):
+    """KickMap::updateSM (src/SM/KickMap.cpp:339-389) takes any displacement; the fused kernels stage
+    32 zero columns per row, so a wake kick whose first tap leaves [-16, 8] cells cannot be served
+    by them.  At 10 mA in a 128^2 grid the first steps kick by 16 cells, later ones by 2-3: the
+    overflowing steps must be detected on the device, redone through the kernel sequence and the
+    steps after them re-enqueued, without the caller noticing anything but `fallback_steps`."""
+    p = kara_params(grid_size=128, bunch_current=10e-3)
+    p.fp_track = 1
+    parts = (rng.random((300, 2)) * 100 + 14).astype(f32)
+    f = {"stream": 0, "tiled": capi.SIM_TILED, "nograph": capi.SIM_NO_GRAPH}[flags]
+    osim = oracle.sim(p, None, parts)
+    sim = capi.Simulation(ctx_strict, p, 1, flags=f, particles=parts)
+    uns = capi.Simulation(ctx_strict, p, 1, flags=capi.SIM_UNFUSED, particles=parts)
+    done = 0
+    for k in (3, 16, 21):  # direct launches, one graph replay, both
+        sim.step(k); uns.step(k); osim.step(k)
+        done += k
+        g, pr, w, pt = sim.download()
+        gu, pru, wu, ptu = uns.download()
+        og, opr, ow, opt = osim.get()
+        assert sim.steps_done == done
+        assert rel_l1(g[0], og) <= L1_TOL and rel_l1(pr[0], opr) <= L1_TOL
+        assert rel_l1(g[0], gu[0]) <= 3e-6
+        assert np.abs(pt[0] - opt).max() < 1e-3 and np.abs(pt[0] - ptu[0]).max() < 1e-3
+    assert 0 < sim.fallback_steps < done, sim.fallback_steps  # some steps overflowed, later ones did not
+    assert uns.fallback_steps == 0
+    # observe() and renormalize() settle as well
+    sim.step(5); uns.step(5)
+    assert np.allclose(sim.observe()[0][:7], uns.observe()[0][:7], rtol=1e-5, atol=1e-6)
+    sim.close(); uns.close(); osim.close()
+
+
+def test_fused_recovery_in_an_ensemble(capi, ctx_fma):
+    """one member of a batch overflows, the others do not: all members are redone together and
+    still equal their single runs"""
+    p = kara_params(grid_size=256)
+    currents = [50e-6, 10e-3, 100e-6]
+    ens = capi.Simulation(ctx_fma, p, 3, bunch_currents=currents)
+    ens.step(20)
+    g = ens.download()[0]
+    assert ens.fallback_steps > 0
+    for i, ib in enumerate(currents):
+        one = capi.Simulation(ctx_fma, kara_params(grid_size=256, bunch_current=ib), 1, flags=capi.SIM_UNFUSED)
+        one.step(20)
+        assert rel_l1(g[i], one.download()[0][0]) < 3e-6, i
+        one.close()
+    ens.close()
 
 
 def test_graph_and_direct_launch_agree(capi, ctx_strict):
