@@ -250,6 +250,11 @@ ivs_status ivs_sim_upload_grid(ivs_sim* sim, const float* grid);
 ivs_status ivs_sim_observe(ivs_sim* sim, float* obs);
 ivs_status ivs_sim_set_radiation(ivs_sim* sim, const float* rad_impedance, float f_scale,
                                  float cutoff);
+/* the field rows main() appends at an out-step (src/main.cpp:949-952,1000-1001; HDF5File::append(ef)
+ * src/IO/HDF5File.cpp:360-423), for the CURRENT bunch profile of every member, to HOST arrays:
+ * csr_spectrum [members][nmax] = ElectricField::updateCSR's spectrum (src/PS/ElectricField.cpp:133-184),
+ * wake [members][n] = ElectricField::wakePotential (:186-253).  Either may be NULL. */
+ivs_status ivs_sim_fields(ivs_sim* sim, float* csr_spectrum, float* wake);
 /* PhaseSpace::integrateAndNormalize (main.cpp:953-956) on every member */
 ivs_status ivs_sim_renormalize(ivs_sim* sim);
 /* Replace the RF kick offsets (n floats) before the next step: the hook DynamicRFKickMap needs

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ivs_sim_upload_grid": (ci, [P, _fp]),
     "ivs_sim_observe": (ci, [P, _fp]),
     "ivs_sim_set_radiation": (ci, [P, _fp, cf, cf]),
+    "ivs_sim_fields": (ci, [P, P, P]),
     "ivs_sim_renormalize": (ci, [P]),
     "ivs_sim_set_rf_offset": (ci, [P, _fp]),
     # include/ivs_host.h
@@ -518,6 +519,13 @@ class Simulation:
         obs = np.zeros((self.members, 8), f32)
         self.ctx.check(self.lib.ivs_sim_observe(self.h, obs.reshape(-1)))
         return obs
+
+    def fields(self, spectrum=True, wake=True):
+        """CSR spectrum [members][nmax] and wake potential [members][n] of the current profile"""
+        sp = np.zeros((self.members, self.nmax), f32) if spectrum else None
+        w = np.zeros((self.members, self.n), f32) if wake else None
+        self.ctx.check(self.lib.ivs_sim_fields(self.h, _ptr(sp), _ptr(w)))
+        return sp, w
 
     def renormalize(self):
         self.ctx.check(self.lib.ivs_sim_renormalize(self.h))

@@ -22,10 +22,19 @@ ivs_status ivs_normalize_batched(ivs_ctx* ctx, float* grid, uint32_t n, uint32_t
                                  float filling_set, const float* integral);
 ivs_status ivs_moments_batched(ivs_ctx* ctx, const float* proj, uint32_t n, uint32_t members,
                                float amin, float delta, const float* integral, float* out3);
+// out-step observables formed by the field kernel in CSR mode: obs[member*8 + {integral, mean_q,
+// var_q, sigma_q, mean_p, var_p, sigma_p, csr_power}] from the X profile and projy
+struct ivs_field_obs {
+    float* obs;
+    const float* projy;
+    const float* ws;
+    float qmin, pmin, dp;
+};
 ivs_status ivs_field_launch(ivs_ctx* ctx, const float* profile, uint32_t n, uint32_t members,
                             const float* impedance, uint32_t nmax, const float* d_scaling,
                             float scaling, float* wake, float* formfactor, float* spectrum,
-                            float* power, float dq, float f_scale, float cutoff, int mode);
+                            float* power, float dq, float f_scale, float cutoff, int mode,
+                            const ivs_field_obs* obs = nullptr);
 // allocates the twiddle table for an FFT length (must not happen inside a graph capture)
 ivs_status ivs_field_prepare(ivs_ctx* ctx, uint32_t nmax);
 // all four maps' applyTo for every tracked particle of every member, one launch per step;

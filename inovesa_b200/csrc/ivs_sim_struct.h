@@ -26,6 +26,8 @@ struct ivs_sim {
     float* integral = nullptr;    // [members]
     float* moments = nullptr;     // [members][2][3]
     float* power = nullptr;       // [members]
+    float* spectrum = nullptr;    // [members][nmax] CSR spectrum (ivs_sim_fields, allocated on first use)
+    float* wake_now = nullptr;    // [members][n] wake potential of the current profile (ivs_sim_fields)
     // bookkeeping of the fused kernels (ivs_fused.cu, step_ctl_begin): status[0] = ordinal of the first
     // step whose wake kick left the staged pad (0x7fffffff: none), status[1] = CTA tickets
     int* status = nullptr;

@@ -281,7 +281,7 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
     float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
                      s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
                      (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power,
-                     (float*)s->track_counter};
+                     (float*)s->track_counter, s->spectrum, s->wake_now};
     for (float* b : bufs) if (b) cudaFree(b);
     if (s->status) cudaFree(s->status);
     if (s->host_flag) cudaFreeHost(s->host_flag);
@@ -322,6 +322,7 @@ static ivs_status enqueue_steps(ivs_sim* s, uint32_t nsteps) {
     while (left > 0) {
         IVS_TRY(enqueue_step(s));
         s->steps_done++;
+        if (!unfused) s->fused_enqueued++;
         left--;
     }
     return IVS_OK;
@@ -443,25 +444,57 @@ ivs_status ivs_sim_observe(ivs_sim* s, float* obs) {
     IVS_TRY(settle(s));
     const float* g = s->grid[s->cur];
     const float* prof = s->profile[s->pcur];
+    IVS_TRY(ivs_project_y_batched(ctx, g, n, m, s->ws, s->projy));
+    if (s->has_rad) {
+        // one launch: CSR spectrum + power of the radiation impedance, integral and the moments of
+        // both projections, 8 floats per member
+        ivs_field_obs o{s->obs, s->projy, s->ws, s->desc.qmin, s->desc.pmin, s->desc.dp};
+        IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->rad_impedance, s->nmax, nullptr, 0, nullptr, nullptr,
+                                 nullptr, s->power, s->desc.dq, s->f_scale, s->cutoff, 1, &o));
+        return ivs_download(ctx, obs, s->obs, (size_t)8 * m * sizeof(float));
+    }
     IVS_TRY(ivs_integrate_batched(ctx, prof, n, m, s->ws, s->integral));
     IVS_TRY(ivs_moments_batched(ctx, prof, n, m, s->desc.qmin, s->desc.dq, s->integral, s->moments));
-    IVS_TRY(ivs_project_y_batched(ctx, g, n, m, s->ws, s->projy));
     IVS_TRY(ivs_moments_batched(ctx, s->projy, n, m, s->desc.pmin, s->desc.dp, s->integral, s->moments + (size_t)3 * m));
-    if (s->has_rad) {
-        IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->rad_impedance, s->nmax, nullptr, 0, nullptr, nullptr,
-                                 nullptr, s->power, s->desc.dq, s->f_scale, s->cutoff, 1));
-    }
-    std::vector<float> integral(m), mom((size_t)6 * m), power(m, 0.0f);
+    std::vector<float> integral(m), mom((size_t)6 * m);
     IVS_TRY(ivs_download(ctx, integral.data(), s->integral, m * sizeof(float)));
     IVS_TRY(ivs_download(ctx, mom.data(), s->moments, (size_t)6 * m * sizeof(float)));
-    IVS_TRY(ivs_download(ctx, power.data(), s->power, m * sizeof(float)));
     for (uint32_t i = 0; i < m; i++) {
         obs[i * 8 + 0] = integral[i];
         for (int k = 0; k < 3; k++) {
             obs[i * 8 + 1 + k] = mom[(size_t)i * 3 + k];
             obs[i * 8 + 4 + k] = mom[(size_t)3 * m + (size_t)i * 3 + k];
         }
-        obs[i * 8 + 7] = power[i];
+        obs[i * 8 + 7] = 0.0f;
+    }
+    return IVS_OK;
+}
+
+// ElectricField::updateCSR's spectrum (src/PS/ElectricField.cpp:133-184) and
+// ElectricField::wakePotential (:186-253) of the CURRENT bunch profile -- what main() appends to
+// /CSR/Spectrum/data and /WakePotential/data at an out-step (src/main.cpp:949-952,1000-1001)
+ivs_status ivs_sim_fields(ivs_sim* s, float* csr_spectrum, float* wake) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    const uint32_t n = s->n, m = s->members;
+    IVS_TRY(settle(s));
+    const float* prof = s->profile[s->pcur];
+    if (csr_spectrum) {
+        IVS_REQUIRE(ctx, s->has_rad, "ivs_sim_fields: the CSR spectrum needs ivs_sim_set_radiation");
+        if (!s->spectrum) IVS_TRY(dalloc(ctx, &s->spectrum, (size_t)m * s->nmax));
+        IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->rad_impedance, s->nmax, nullptr, 0, nullptr, nullptr,
+                                 s->spectrum, s->power, s->desc.dq, s->f_scale, s->cutoff, 1));
+        IVS_TRY(ivs_download(ctx, csr_spectrum, s->spectrum, (size_t)m * s->nmax * sizeof(float)));
+    }
+    if (wake) {
+        if (s->has_wake) {
+            if (!s->wake_now) IVS_TRY(dalloc(ctx, &s->wake_now, (size_t)m * n));
+            IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->impedance, s->nmax, s->wakescaling, 0, s->wake_now,
+                                     nullptr, nullptr, nullptr, 0, 0, 0, 0));
+            IVS_TRY(ivs_download(ctx, wake, s->wake_now, (size_t)m * n * sizeof(float)));
+        } else {
+            for (size_t i = 0; i < (size_t)m * n; i++) wake[i] = 0.0f;
+        }
     }
     return IVS_OK;
 }
