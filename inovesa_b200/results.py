@@ -183,6 +183,17 @@ class ResultFile:
                 f[link] = h5py.SoftLink(target)
 
 
+def unit_factors(derived):
+    """(Volt, WattPerHertz, Watt): ElectricField::volts = delta(1) * scale(1, "ElectronVolt") /
+    revolutionpart (src/PS/ElectricField.cpp:23, revolutionpart a float), factor4WattPerHertz =
+    2 * factor4Ohms * Ib^2 / f_rev with factor4Ohms = 1 (:39, inc/Z/Impedance.hpp:91) and factor4Watts =
+    factor4WattPerHertz * c / bl, the "Hertz" scale of the frequency axis (:28-31,40)"""
+    d = derived
+    volts = float(f32(f32(d.dp) * f32(d.dE_f)) / f32(d.revolutionpart))  # float * float / float, then widened
+    wph = 2.0 * d.Ib * d.Ib / d.f_rev
+    return volts, wph, wph * float(f32(2.99792458e8 / float(f32(d.bl_f))))
+
+
 def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0, wake_impedance=None):
     """main()'s loop with its out-step cadence (src/main.cpp:948-1053) on a `capi.Simulation`
     with one member: returns the filled ResultFile.  Time axis in synchrotron periods."""
@@ -193,7 +204,8 @@ def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0,
     axis_f = np.arange(nmax, dtype=f32) * f32(1.0 / d.dq / (nmax - 1))
     rf = ResultFile(n, nmax, sim.np, axis_q=axis_q, axis_p=axis_p, axis_f=axis_f, bl=d.bl, dE=d.dE,
                     f_scale=2.99792458e8 / d.bl, Ib=d.Ib, Qb=d.Qb, t_sync=1.0 / d.fs, f_rev=d.f_rev,
-                    volts=d.dp * d.dE, impedance=wake_impedance)
+                    volts=unit_factors(d)[0], watt_per_hertz=unit_factors(d)[1], watts=unit_factors(d)[2],
+                    impedance=wake_impedance)
     for name, _ in params._fields_:
         if not name.startswith("reserved"):
             rf.add_parameter(name, getattr(params, name))
@@ -201,11 +213,14 @@ def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0,
     done, k = 0, 0
     while True:
         obs = sim.observe()[0]  # [integral, mean_q, var_q, sigma_q, mean_p, var_p, sigma_p, P_csr]
-        grid, prof, wake, parts = sim.download()
+        grid, prof, _, parts = sim.download()
+        # the CSR spectrum and the wake potential of THIS profile: main() refreshes the wake before
+        # the out-step block (src/main.cpp:949-952) and appends updateCSR's spectrum (:1000-1001)
+        spectrum, wake = sim.fields()
         t = done / float(d.steps)
         projy = (grid[0].astype(np.float64) * _simpson(n, d.dq)[:, None]).sum(0).astype(f32)
         rf.append_time_step(t, prof[0], obs[3], obs[1], projy, obs[6], obs[4], obs[0])
-        rf.append_csr(np.zeros(nmax // 2, f32), obs[7])
+        rf.append_csr(spectrum[0], obs[7])
         rf.append_wake(wake[0])
         if parts is not None:
             rf.append_tracks(parts[0])

@@ -246,6 +246,7 @@ class Ref:
         L.ref_sim_get.argtypes = [P, P, P, P, P]
         L.ref_sim_tables.argtypes = [P, P, P, P, P, P]
         L.ref_sim_observe.argtypes = [P, _fp, P, P]
+        L.ref_sim_units.argtypes = [P, C.POINTER(cd * 3)]
 
     def _check(self, rc):
         if rc == 1:
@@ -411,6 +412,13 @@ class _Sim:
         projy = np.zeros(self.n, f32)
         getattr(self.lib, self.px + "_sim_observe")(self.h, obs, _opt(spec), _opt(projy))
         return obs, spec, projy
+
+    def units(self):
+        """(Volt, WattPerHertz, Watt) factors of the reference's ElectricField objects"""
+        assert self.px == "ref"
+        out = (cd * 3)()
+        self.lib.ref_sim_units(self.h, C.byref(out))
+        return tuple(out)
 
     def close(self):
         if self.h:

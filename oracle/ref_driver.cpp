@@ -627,4 +627,17 @@ int ref_sim_observe(void* h, float* obs, float* csr_spectrum, float* projy) {
     });
 }
 
+// unit factors the reference writes beside /WakePotential/data, /CSR/Spectrum/data and
+// /CSR/Intensity/data (src/IO/HDF5File.cpp:259-276): ElectricField::volts (src/PS/ElectricField.cpp:23),
+// factor4WattPerHertz and factor4Watts (:39-40)
+int ref_sim_units(void* h, double* out3) {
+    ref_sim* s = static_cast<ref_sim*>(h);
+    return guarded([&] {
+        const ElectricField* f = s->wake_field ? s->wake_field.get() : s->rdtn_field.get();
+        out3[0] = f->volts;
+        out3[1] = s->rdtn_field->factor4WattPerHertz;
+        out3[2] = s->rdtn_field->factor4Watts;
+    });
+}
+
 }  // extern "C"

@@ -69,6 +69,20 @@ def test_save_round_trip_and_hdf5_gate(tmp_path):
         assert os.path.getsize(base + ".h5") > 0
 
 
+def test_unit_factors_equal_the_reference_objects(ref, capi):
+    """the Volt / WattPerHertz / Watt attributes (src/IO/HDF5File.cpp:259-276) against the values the
+    reference's own ElectricField objects hold (oracle/_ref, src/PS/ElectricField.cpp:23,39-40)"""
+    from inovesa_b200.params import kara_params
+    from inovesa_b200.results import unit_factors
+    for kw in (dict(grid_size=64, bunch_current=100e-6), dict(grid_size=128, steps_per_Ts=4000, bunch_current=2e-3, gap=0.0)):
+        p = kara_params(**kw)
+        rs = ref.sim(p)
+        want = rs.units()
+        rs.close()
+        got = unit_factors(capi.derive(p))
+        assert np.allclose(got, want, rtol=1e-6, atol=0), (got, want)
+
+
 @pytest.mark.gpu
 def test_run_and_record_fills_the_layout(capi, ctx_fma, rng):
     """main()'s loop at its out-step cadence through the simulation object: one row per out-step"""
@@ -79,7 +93,8 @@ def test_run_and_record_fills_the_layout(capi, ctx_fma, rng):
     parts = (rng.random((5, 2)) * 40 + 12).astype(f32)
     sim = capi.Simulation(ctx_fma, p, 1, particles=parts)
     d = capi.derive(p)
-    rf = run_and_record(sim, p, d, steps=200, outstep=50, save_phase_space=2)
+    rf = run_and_record(sim, p, d, steps=200, outstep=50, save_phase_space=2, wake_impedance=sim.tables["zwake"])
+    rf.wake_impedance = sim.tables["zwake"]
     sim.close()
     ds = rf.datasets()
     assert ds["/Info/AxisValues_t"].shape == (5,) and np.allclose(ds["/Info/AxisValues_t"], np.arange(5) * 50 / d.steps)
@@ -87,3 +102,11 @@ def test_run_and_record_fills_the_layout(capi, ctx_fma, rng):
     assert ds["/PhaseSpace/data"].shape == (3, 1, 64, 64)   # out-steps 0, 2, 4
     assert np.all(ds["/CSR/Intensity/data"] > 0) and np.all(np.abs(ds["/BunchPopulation/data"] - 1) < 1e-4)
     assert np.all(ds["/BunchLength/data"] > 0.9) and rf.parameters["grid_size"] == 64
+    # the spectrum rows are the device's updateCSR spectrum (first nmax/2 bins), whose sum over ALL bins
+    # times delta_f is the intensity; the wake row belongs to the profile of the same out-step
+    assert np.all(ds["/CSR/Spectrum/data"].max(axis=2) > 0)
+    delta_f = 1.0 / d.dq / (d.padded_bins - 1)
+    assert np.allclose(ds["/CSR/Spectrum/data"].sum(axis=2) * delta_f, ds["/CSR/Intensity/data"], rtol=0.05)
+    assert np.abs(ds["/WakePotential/data"][0]).max() > 0          # t = 0 row is not the zero-initialised buffer
+    w_now = capi.Context.wake_potential(ctx_fma, ds["/BunchProfile/data"][-1, 0], rf.wake_impedance, d.wakescaling)
+    assert np.allclose(ds["/WakePotential/data"][-1, 0], w_now, rtol=1e-4, atol=1e-6 * np.abs(w_now).max())
