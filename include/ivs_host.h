@@ -102,6 +102,16 @@ int ivs_gaussian_projection(uint32_t n, float amin, float amax, double zoom, flo
 /* PhaseSpace::PhaseSpace with data == nullptr followed by main()'s initial
  * renormalisation (src/PS/PhaseSpace.cpp:52-65,457-484; src/main.cpp:528-532): n*n floats */
 int ivs_initial_grid(const ivs_derived* d, uint32_t n, double zoom, float* grid);
+/* Haissinski start distribution f = rho(q) exp(-p^2/2) (BASELINE configs[2]; the reference parses
+ * HaissinskiIterations and ignores it, src/IO/ProgramOptions.cpp:270-272): the stationary bunch
+ * profile rho ~ exp((dp/angle) int (rf + W[rho]) dq) of the step map, W[rho] = ElectricField::
+ * wakePotential of rho with `zwake` (nmax complex<float>, may be NULL: no wake) and `wakescaling`,
+ * rf_offset = RFKickMap offsets (n floats).  Damped fixed-point iteration (`relax` in (0,1]) in
+ * double.  grid: n*n floats for PhaseSpace's `data` constructor argument (inc/PS/PhaseSpace.hpp:60).
+ * Returns 0 if the last iteration changed rho by less than 1e-9 (relative L1, also in *residual), else 1. */
+int ivs_haissinski_grid(const ivs_derived* d, uint32_t n, const float* rf_offset, const float* zwake,
+                        uint32_t nmax, float wakescaling, uint32_t iterations, double relax, float* grid,
+                        double* residual);
 /* Airy functions used by the parallel-plates impedance (src/Z/ParallelPlatesCSR.cpp:48-53);
  * returns 0, or 1 if Bi/Bi' overflow a double (Boost would throw there) */
 int ivs_airy(double x, double* ai, double* aip, double* bi, double* bip);

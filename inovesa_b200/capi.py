@@ -89,6 +89,7 @@ SIGNATURES = {
     "ivs_radiation_impedance": (ci, [C.POINTER(RingParams), C.POINTER(Derived), _fp]),
     "ivs_initial_grid": (ci, [C.POINTER(Derived), u32, cd, _fp]),
     "ivs_gaussian_projection": (ci, [u32, cf, cf, cd, _fp]),
+    "ivs_haissinski_grid": (ci, [C.POINTER(Derived), u32, _fp, P, u32, cf, u32, cd, _fp, C.POINTER(cd)]),
     "ivs_airy": (ci, [cd] + [C.POINTER(cd)] * 4),
 }
 
@@ -181,6 +182,24 @@ def initial_grid(d, n, zoom=1.0):
     g = np.zeros((n, n), f32)
     load().ivs_initial_grid(C.byref(d), n, zoom, g.reshape(-1))
     return g
+
+
+def haissinski_grid(params, d, zwake=None, wakescaling=None, iterations=2000, relax=0.1, rf=None):
+    """stationary start distribution of the step map (see include/ivs_host.h); returns (grid, residual)"""
+    n = params.grid_size
+    rf = rf_kick_offsets(params, d) if rf is None else np.ascontiguousarray(rf, f32)
+    if zwake is None:
+        zwake, nz = wake_impedance(params, d)
+        zwake = zwake if nz else None
+    zw = None if zwake is None else np.ascontiguousarray(zwake, f32).reshape(-1)
+    g = np.zeros((n, n), f32)
+    res = cd(0)
+    rc = load().ivs_haissinski_grid(C.byref(d), n, rf, _ptr(zw), d.padded_bins,
+                                    d.wakescaling if wakescaling is None else wakescaling,
+                                    iterations, relax, g.reshape(-1), C.byref(res))
+    if rc not in (0, 1):
+        raise IvsError(rc, "ivs_haissinski_grid")
+    return g, res.value
 
 
 def airy(x):

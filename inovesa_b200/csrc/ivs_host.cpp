@@ -204,6 +204,41 @@ ztable z_collimator(size_t n, double outer, double inner) {
 
 }  // namespace
 
+// Unit wake function w[m], m = -(n-1)..(n-1) (index m + n - 1): c2r of the Hermitian-extended impedance
+// with the reference's conventions (imaginary part of bin 0 ignored, bins >= nmax/2 zero,
+// src/PS/ElectricField.cpp:229-234), in double.  wakePotential()[x] = scaling sum_x' rho[x'] w[x - x']
+// exactly in real arithmetic, because nmax >= 2n leaves no circular wrap.  Shared with ivs_step.cu.
+std::vector<double> ivs_wake_function_host(const float* z, uint32_t nmax, uint32_t n) {
+    std::vector<std::complex<double>> a(nmax, 0.0);
+    a[0] = std::complex<double>(z[0], 0.0);
+    for (uint32_t k = 1; k < nmax / 2; k++) {
+        a[k] = std::complex<double>(z[2 * k], z[2 * k + 1]);
+        a[nmax - k] = std::conj(a[k]);
+    }
+    // radix-2 FFT, sign +
+    for (uint32_t i = 1, j = 0; i < nmax; i++) {
+        uint32_t bit = nmax >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (uint32_t len = 2; len <= nmax; len <<= 1) {
+        for (uint32_t k = 0; k < len / 2; k++) {
+            const double ph = kTwoPi * (double)k / (double)len;
+            const std::complex<double> w(std::cos(ph), std::sin(ph));
+            for (uint32_t i = k; i < nmax; i += len) {
+                const std::complex<double> u = a[i], v = a[i + len / 2] * w;
+                a[i] = u + v;
+                a[i + len / 2] = u - v;
+            }
+        }
+    }
+    std::vector<double> w(2 * n - 1);
+    for (int m = -(int)(n - 1); m <= (int)(n - 1); m++)
+        w[m + (int)(n - 1)] = a[(uint32_t)((m + (int)nmax) % (int)nmax)].real();
+    return w;
+}
+
 extern "C" {
 
 int ivs_airy(double x, double* ai, double* aip, double* bi, double* bip) {
@@ -526,6 +561,67 @@ int ivs_initial_grid(const ivs_derived* d, uint32_t n, double zoom, float* grid)
     scale(integral());  // createFromProjections: normalize()
     scale(integral());  // constructor integrate(), then main(): normalize()
     return IVS_OK;
+}
+
+// Haissinski start distribution (BASELINE.json configs[2] "Haissinski-initialised"; the reference
+// parses HaissinskiIterations and ignores it, src/IO/ProgramOptions.cpp:270-272, so this is an
+// addition: the grid goes to PhaseSpace's `data` constructor argument, inc/PS/PhaseSpace.hpp:60).
+// Per step a particle moves by  q' = -angle p  (DriftMap, slip[0] = angle) and
+// p' = -(rf[x] + W[x]) dp  (RF + wake kick in cells, KickMap::applyTo subtracts the offset,
+// src/SM/KickMap.cpp:280-303), i.e. H = -angle p^2/2 + dp int (rf + W) dq, and with the
+// Fokker-Planck term the stationary density is  f = exp(H / angle) = exp(-p^2/2) rho(q),
+//     rho(q) ~ exp( (dp / angle) int^q (rf + W[rho]) dq' ),
+// W[rho] = wakePotential() of rho.  Solved by damped fixed-point iteration in double
+// (trapezoidal cumulative integral from the grid centre, Simpson-normalised like PhaseSpace).
+// Returns 0 when the relative L1 change of the last iteration is below 1e-9, 1 otherwise.
+int ivs_haissinski_grid(const ivs_derived* d, uint32_t n, const float* rf_offset, const float* zwake,
+                        uint32_t nmax, float wakescaling, uint32_t iterations, double relax, float* grid,
+                        double* residual) {
+    if (!d || !grid || !rf_offset || n < 4 || !(relax > 0 && relax <= 1)) return IVS_ERR_INVALID_ARGUMENT;
+    if (zwake && (nmax < 2 * n || (nmax & (nmax - 1)))) return IVS_ERR_INVALID_ARGUMENT;
+    const Axis ax0(n, d->qmin, d->qmax), ax1(n, d->pmin, d->pmax);
+    std::vector<float> wsf(n);
+    ivs_simpson_weights(n, ax0.delta, wsf.data());
+    std::vector<double> ws(wsf.begin(), wsf.end()), rho(n), next(n), force(n), pot(n), w;
+    if (zwake) w = ivs_wake_function_host(zwake, nmax, n);
+    const double dq = ax0.delta, k = (double)ax1.delta / (double)d->angle;
+    auto normalise = [&](std::vector<double>& r) {
+        double q = 0;
+        for (uint32_t x = 0; x < n; x++) q += r[x] * ws[x];
+        for (uint32_t x = 0; x < n; x++) r[x] /= q;
+    };
+    for (uint32_t x = 0; x < n; x++) rho[x] = std::exp(-0.5 * (double)ax0.at(x) * (double)ax0.at(x));
+    normalise(rho);
+    double res = 1.0;
+    for (uint32_t it = 0; it < iterations; it++) {
+        for (uint32_t x = 0; x < n; x++) {
+            double acc = 0;
+            if (zwake)
+                for (uint32_t xp = 0; xp < n; xp++) acc += rho[xp] * w[x + (n - 1) - xp];
+            force[x] = (double)rf_offset[x] + (double)wakescaling * acc;
+        }
+        pot[0] = 0;
+        for (uint32_t x = 1; x < n; x++) pot[x] = pot[x - 1] + 0.5 * (force[x] + force[x - 1]) * dq;
+        const double p0 = pot[n / 2];
+        for (uint32_t x = 0; x < n; x++) next[x] = std::exp(k * (pot[x] - p0));
+        normalise(next);
+        double num = 0, den = 0;
+        for (uint32_t x = 0; x < n; x++) {
+            num += std::fabs(next[x] - rho[x]);
+            den += std::fabs(rho[x]);
+            rho[x] = (1 - relax) * rho[x] + relax * next[x];
+        }
+        res = num / den;
+        if (res < 1e-12) break;
+    }
+    if (residual) *residual = res;
+    // f = rho(q) gauss(p), normalised to integral 1 with the Simpson weights on both axes
+    std::vector<double> py(n);
+    for (uint32_t y = 0; y < n; y++) py[y] = std::exp(-0.5 * (double)ax1.at(y) * (double)ax1.at(y));
+    normalise(py);
+    for (uint32_t x = 0; x < n; x++)
+        for (uint32_t y = 0; y < n; y++) grid[(size_t)x * n + y] = (float)(rho[x] * py[y]);
+    return res < 1e-9 ? 0 : 1;
 }
 
 }  // extern "C"

@@ -3,7 +3,12 @@
 #pragma once
 #include "ivs_common.cuh"
 
+#include <vector>
+
 struct ivs_sim;
+
+// unit wake function of an impedance table in double (ivs_host.cpp): w[m + n - 1], m = -(n-1)..(n-1)
+std::vector<double> ivs_wake_function_host(const float* z, uint32_t nmax, uint32_t n);
 
 // member-batched launchers (ivs_maps.cu, ivs_reduce.cu, ivs_field.cu, ivs_track.cu)
 ivs_status ivs_kick_y_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n, uint32_t members,

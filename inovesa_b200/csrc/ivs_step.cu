@@ -109,41 +109,6 @@ uint32_t launches_per_step(const ivs_sim* s) {
     return k;
 }
 
-// unit wake function w[m], m = -(n-1)..(n-1): c2r of the Hermitian-extended impedance with the
-// reference's conventions (imaginary part of bin 0 ignored, bins >= nmax/2 zero), in double.
-std::vector<double> wake_function_host(const float* z, uint32_t nmax, uint32_t n) {
-    const double two_pi = 6.283185307179586476925286766559005768;
-    std::vector<std::complex<double>> a(nmax, 0.0);
-    a[0] = std::complex<double>(z[0], 0.0);
-    for (uint32_t k = 1; k < nmax / 2; k++) {
-        a[k] = std::complex<double>(z[2 * k], z[2 * k + 1]);
-        a[nmax - k] = std::conj(a[k]);
-    }
-    // radix-2 FFT, sign +
-    for (uint32_t i = 1, j = 0; i < nmax; i++) {
-        uint32_t bit = nmax >> 1;
-        for (; j & bit; bit >>= 1) j ^= bit;
-        j ^= bit;
-        if (i < j) std::swap(a[i], a[j]);
-    }
-    for (uint32_t len = 2; len <= nmax; len <<= 1) {
-        for (uint32_t k = 0; k < len / 2; k++) {
-            const double ph = two_pi * (double)k / (double)len;
-            const std::complex<double> w(std::cos(ph), std::sin(ph));
-            for (uint32_t i = k; i < nmax; i += len) {
-                const std::complex<double> u = a[i], v = a[i + len / 2] * w;
-                a[i] = u + v;
-                a[i + len / 2] = u - v;
-            }
-        }
-    }
-    std::vector<double> w(2 * n - 1);
-    for (int m = -(int)(n - 1); m <= (int)(n - 1); m++) {
-        w[m + (int)(n - 1)] = a[(uint32_t)((m + (int)nmax) % (int)nmax)].real();
-    }
-    return w;
-}
-
 }  // namespace
 
 extern "C" {
@@ -158,7 +123,7 @@ ivs_status ivs_wake_function(ivs_ctx* ctx, const void* d_impedance, uint32_t nma
                 "ivs_wake_function: nmax must be a power of two >= 2n");
     std::vector<float> z(2 * (size_t)nmax);
     IVS_TRY(ivs_download(ctx, z.data(), d_impedance, z.size() * sizeof(float)));
-    std::vector<double> wd = wake_function_host(z.data(), nmax, n);
+    std::vector<double> wd = ivs_wake_function_host(z.data(), nmax, n);
     std::vector<float> w(wd.size());
     for (size_t i = 0; i < wd.size(); i++) w[i] = wakescaling * (float)wd[i];
     IVS_TRY(ivs_upload(ctx, d_wakefunction, w.data(), w.size() * sizeof(float)));
@@ -239,7 +204,7 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
         S_TRY(ivs_upload(ctx, s->impedance, d->impedance, (size_t)2 * s->nmax * sizeof(float)));
         S_TRY(ivs_upload(ctx, s->wakescaling, d->wakescaling, m * sizeof(float)));
         S_TRY(ivs_field_prepare(ctx, s->nmax));
-        wf = wake_function_host(d->impedance, s->nmax, n);
+        wf = ivs_wake_function_host(d->impedance, s->nmax, n);
         wf.push_back(0.0);
         S_TRY(ivs_upload(ctx, s->wakefunction, wf.data(), (size_t)2 * n * sizeof(double)));
     }
