@@ -590,6 +590,12 @@ __device__ unsigned long long g_wstat[4][32];  // [loop-end clock, mailbox polls
 #ifndef IVS_LAG
 #define IVS_LAG 4
 #endif
+#ifndef IVS_PROBE_NOKICK
+#define IVS_PROBE_NOKICK 0  // development aids: timing probes that leave out part of the arithmetic
+#endif
+#ifndef IVS_PROBE_NOFP
+#define IVS_PROBE_NOFP 0
+#endif
 constexpr int kLag = IVS_LAG;        // drifted rows wait this many iterations (in a per-thread FIFO in shared memory)
                                // for their Fokker-Planck step: the slack between neighbouring warps
 
@@ -711,6 +717,13 @@ __device__ __forceinline__ float4 kick_quad(uint32_t row_q, int fsum, int m0, ui
     default: return kick_quad_rr<FMA, 3>(p, A, B, C, m0, n, near_edge, w1, w2);
     }
 }
+
+#if IVS_PROBE_NOFP
+__device__ __forceinline__ float warp_sum_probe(float v) {
+    for (int o = 8; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
 
 // staged wake-function window: one pad double after every 8 keeps lanes that are 8 entries apart
 // on different banks
@@ -1132,7 +1145,15 @@ __global__ void __launch_bounds__(512 / QPT, 1) stream_step_kernel(const stream_
             const uint32_t landed = mbar_test(MORE ? nbar : kbar, MORE ? npar : kpar);
             const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
             float4 kq[QPT];
+#if IVS_PROBE_NOKICK  // timing probe (wrong results): the staged quad passes through unkicked
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                kq[j] = lds128(aload + j * 512);
+                kq[j].x += w1.x + w2.x + __int_as_float(f.x);
+            }
+#else
             kick_quads<FMA, QPT>(aload, f.x, y0 + f.y, n, near_edge, w1, w2, kq);
+#endif
             tp += 48;
             f = lds64i(tp + 32);  // next row's entry, a row ahead of its use
             aload += wrap ? ring_back : pitchB;  // ring_back = pitchB - K * pitchB: back to slot 0
@@ -1226,6 +1247,14 @@ __global__ void __launch_bounds__(512 / QPT, 1) stream_step_kernel(const stream_
             if (edge_r) { Rx[QPT - 1] = m.x; Ry[QPT - 1] = m.y; }
             // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
             float o[QPT][4];
+#if IVS_PROBE_NOFP  // timing probe (wrong results): no stencil, no neighbours
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                o[j][0] = dp[j].x + Lz[j]; o[j][1] = dp[j].y; o[j][2] = dp[j].z; o[j][3] = dp[j].w + Ry[j];
+                gout[j * 32] = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
+            }
+            ps = warp_sum_probe(ps);
+#else
 #define IVS_FP_COL(j, c)                                                 \
             {                                                            \
                 float v = __fmul_rn(in[c], w5[j][c][0]);                 \
@@ -1249,6 +1278,7 @@ __global__ void __launch_bounds__(512 / QPT, 1) stream_step_kernel(const stream_
                 gout[j * 32] = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
             }
 #undef IVS_FP_COL
+#endif
             gout += gstride;
             if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
             redp += NSEG * 4;

@@ -4,6 +4,8 @@
 // arithmetic follows the reference's CPU loops (the parity oracle), not its OpenCL variants.
 // They accept any grid size and any displacement (every tap is bounds checked), and are what
 // the fused step kernel (ivs_step.cu) is verified against on the device.
+#include <algorithm>
+
 #include "ivs_common.cuh"
 
 namespace {
@@ -175,6 +177,130 @@ rotate_kernel(const float* __restrict__ in, float* __restrict__ out, rot_params 
     out[(size_t)x0 * n + y0] = v;
 }
 
+// ---------------------------------------------------------------- RotationMap, tiled
+// The same arithmetic with the source cells served from shared memory.  A CTA owns an output tile
+// of kRotTX rows x kRotTY columns.  The map is affine, so the source coordinates of the tile are
+// bounded by those of its four corners: that bounding box (plus the stencil, clipped to the grid,
+// columns aligned to 16 bytes) is staged by the TMA engine, one cp.async.bulk per row completing
+// on an mbarrier.  For the rotation of a simulation step (angle = 2 pi / steps) the box is a few
+// cells larger than the tile, so the grid is read about once (8 B per cell); at any angle it stays
+// below (kRotTX + kRotTY + 8)^2 cells, which the launcher sizes the shared memory for.
+// Taps outside the grid are {index 0, weight 0} in the reference's table (:247-249): their source
+// value is in[0], read once per thread, so every sum (and the clamp) sees the same operands.
+constexpr int kRotTX = 32, kRotTY = 128;
+
+__device__ __forceinline__ uint32_t rot_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool FMA>
+__global__ void __launch_bounds__(kRotTY)
+rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_params p, uint32_t cap_rows,
+                   uint32_t pitch) {
+    extern __shared__ __align__(128) float tile[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int box[4];  // first row, rows, first column (multiple of 4), columns (multiple of 4)
+    const uint32_t n = p.n, it = p.it;
+    const uint32_t tx0 = blockIdx.y * kRotTX, ty0 = blockIdx.x * kRotTY;
+    const uint32_t lo = (it - 1) / 2;
+    auto source = [&](uint32_t x0, uint32_t y0, float& x1r, float& y1r) {
+        // Ruler::at(i) = min + i*delta (inc/PS/Ruler.hpp:47-49); src/SM/RotationMap.cpp:203-214
+        const float ax = IVS_ADD(p.min0, IVS_MUL((float)x0, p.d0));
+        const float ay = IVS_ADD(p.min1, IVS_MUL((float)y0, p.d1));
+        x1r = IVS_ADD(IVS_DIV(IVS_SUB(IVS_MUL(p.cos_dt, ax), IVS_MUL(p.sin_dt, ay)), p.d0), p.zb0);
+        y1r = IVS_ADD(IVS_DIV(IVS_ADD(IVS_MUL(p.sin_dt, ax), IVS_MUL(p.cos_dt, ay)), p.d1), p.zb1);
+    };
+    if (threadIdx.x == 0) {
+        const uint32_t xe = min(tx0 + kRotTX, n) - 1, ye = min(ty0 + kRotTY, n) - 1;
+        float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+        const uint32_t cx[2] = {tx0, xe}, cy[2] = {ty0, ye};
+        for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++) {
+                float xr, yr;
+                source(cx[a], cy[b], xr, yr);
+                xmin = fminf(xmin, xr); xmax = fmaxf(xmax, xr);
+                ymin = fminf(ymin, yr); ymax = fmaxf(ymax, yr);
+            }
+        // one cell of slack for the rounding of the corner coordinates, then the stencil
+        const float big = 1.0e9f;
+        int r0 = (int)floorf(fmaxf(fminf(xmin, big), -big)) - 1 - (int)lo;
+        int r1 = (int)floorf(fmaxf(fminf(xmax, big), -big)) + 1 + (int)(it - 1 - lo);
+        int c0 = (int)floorf(fmaxf(fminf(ymin, big), -big)) - 1 - (int)lo;
+        int c1 = (int)floorf(fmaxf(fminf(ymax, big), -big)) + 1 + (int)(it - 1 - lo);
+        r0 = max(r0, 0); c0 = max(c0, 0) & ~3;
+        r1 = min(r1, (int)n - 1); c1 = min(c1 | 3, (int)n - 1);
+        int rows = r1 - r0 + 1, cols = c1 - c0 + 1;
+        if (rows <= 0 || cols <= 0) rows = cols = 0;
+        if ((uint32_t)rows > cap_rows || (uint32_t)cols > pitch || (cols & 3)) rows = -1;  // cannot be staged: gather from global
+        box[0] = r0; box[1] = rows; box[2] = c0; box[3] = cols;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rot_smem_u32(&bar)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (rows > 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rot_smem_u32(&bar)),
+                         "r"((uint32_t)rows * (uint32_t)cols * 4u) : "memory");
+    }
+    __syncthreads();
+    const int r0 = box[0], rows = box[1], c0 = box[2], cols = box[3];
+    if (rows > 0) {
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             rot_smem_u32(tile + (size_t)r * pitch)),
+                         "l"(in + (size_t)(r0 + r) * n + c0), "r"((uint32_t)cols * 4u), "r"(rot_smem_u32(&bar))
+                         : "memory");
+        }
+    }
+    const float in0 = __ldg(in);
+    const uint32_t y0 = ty0 + threadIdx.x;
+    if (rows > 0) {
+        uint32_t ok;
+        do {
+            asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                         : "=r"(ok) : "r"(rot_smem_u32(&bar)), "r"(0u) : "memory");
+        } while (!ok);
+    }
+    if (y0 >= n) return;
+    const bool staged = rows >= 0;
+    for (uint32_t x0 = tx0; x0 < min(tx0 + kRotTX, n); x0++) {
+        float x1r, y1r;
+        source(x0, y0, x1r, y1r);
+        const float xi = truncf(x1r), yi = truncf(y1r);
+        const float xf = IVS_SUB(x1r, xi), yf = IVS_SUB(y1r, yi);
+        const uint32_t x1 = (uint32_t)(long long)xi, y1 = (uint32_t)(long long)yi;
+        float v = 0.0f;
+        if (x1 < n && y1 < n) {
+            float icq[4], icp[4];
+            ivs_calc_coefficients(xf, it, icq);
+            ivs_calc_coefficients(yf, it, icp);
+            float ceil = 1.17549435e-38f /* FLT_MIN */, flor = 3.402823466e+38f /* FLT_MAX */;
+            for (uint32_t i1 = 0; i1 < it; i1++) {
+                const uint32_t i0 = x1 + i1 - lo;
+                for (uint32_t j1 = 0; j1 < it; j1++) {
+                    const uint32_t j0 = y1 + j1 - lo;
+                    const bool ok = (i0 < n && j0 < n);
+                    float src = in0;
+                    if (ok) src = staged ? tile[(size_t)((int)i0 - r0) * pitch + ((int)j0 - c0)] : in[(size_t)i0 * n + j0];
+                    const float w = ok ? IVS_MUL(icq[i1], icp[j1]) : 0.0f;
+                    v = madd<FMA>(src, w, v);
+                    if (p.clamp && i1 >= 1 && i1 <= 2 && j1 >= 1 && j1 <= 2) {
+                        ceil = (ceil < src) ? src : ceil;  // std::max(ceil, src)
+                        flor = (src < flor) ? src : flor;  // std::min(flor, src)
+                    }
+                }
+            }
+            if (p.clamp) {
+                const float m = (v < ceil) ? v : ceil;  // std::min(ceil, v)
+                v = (m < flor) ? flor : m;              // std::max(m, flor)
+            }
+        } else if (p.clamp) {
+            // all 16 taps are {0,0}: value 0 clamped to [in[0], in[0]] (:161-171)
+            float ceil = 1.17549435e-38f, flor = 3.402823466e+38f;
+            ceil = (ceil < in0) ? in0 : ceil;
+            flor = (in0 < flor) ? in0 : flor;
+            const float m = (0.0f < ceil) ? 0.0f : ceil;
+            v = (m < flor) ? flor : m;
+        }
+        out[(size_t)x0 * n + y0] = v;
+    }
+}
+
 template <typename K, typename... Args>
 ivs_status launch(ivs_ctx* ctx, K kernel_fma, K kernel_strict, dim3 grid, dim3 block, size_t smem,
                   Args... args) {
@@ -276,8 +402,29 @@ ivs_status ivs_rotate(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, f
     p.d1 = (pmax - pmin) / (float)(n - 1);
     p.zb0 = ((qmin + qmax) / (qmin - qmax) + 1) * (float)(n - 1) / 2;  // inc/PS/Ruler.hpp:40
     p.zb1 = ((pmin + pmax) / (pmin - pmax) + 1) * (float)(n - 1) / 2;
-    return launch(ctx, rotate_kernel<true>, rotate_kernel<false>, dim3(ivs_div_up(n, 128), n),
-                  dim3(128), 0, (const float*)d_in, (float*)d_out, p);
+    if (n % 4 != 0)  // rows are staged in 16-byte units
+        return launch(ctx, rotate_kernel<true>, rotate_kernel<false>, dim3(ivs_div_up(n, 128), n),
+                      dim3(128), 0, (const float*)d_in, (float*)d_out, p);
+    // shared memory for the bounding box of a rotated tile (+ stencil, slack and column alignment)
+    const float ac = fabsf(p.cos_dt), as = fabsf(p.sin_dt);
+    // the two axes may have different cell sizes: source rows per output row / column
+    const float rx = p.d1 / p.d0, ry = p.d0 / p.d1;
+    uint32_t cap_rows = (uint32_t)ceilf(kRotTX * ac + kRotTY * as * rx) + 8;
+    uint32_t pitch = ((uint32_t)ceilf(kRotTY * ac + kRotTX * as * ry) + 8 + 6 + 3) & ~3u;
+    cap_rows = std::min<uint32_t>(cap_rows, n);
+    pitch = std::min<uint32_t>(pitch, n);
+    size_t smem = (size_t)cap_rows * pitch * sizeof(float);
+    if (smem > (size_t)kIvsMaxOptinSmem - 1024) {  // very anisotropic axes: keep what fits, the kernel gathers the rest
+        cap_rows = (uint32_t)(((size_t)kIvsMaxOptinSmem - 1024) / ((size_t)pitch * sizeof(float)));
+        smem = (size_t)cap_rows * pitch * sizeof(float);
+    }
+    if (smem > 40 * 1024) {
+        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+    }
+    return launch(ctx, rotate_tile_kernel<true>, rotate_tile_kernel<false>,
+                  dim3(ivs_div_up(n, kRotTY), ivs_div_up(n, kRotTX)), dim3(kRotTY), smem, (const float*)d_in,
+                  (float*)d_out, p, cap_rows, pitch);
 }
 
 }  // extern "C"

@@ -386,6 +386,45 @@ def test_above_threshold_statistics_match_oracle(capi, ctx_fma, oracle):
     osim.close()
 
 
+def test_bursting_period_and_spectrum_match_oracle(capi, ctx_fma, oracle_fma):
+    """north_star: "statistical agreement (bursting period and spectrum) beyond the chaotic horizon
+    above the microbunching threshold".  At 600 uA (config 1's ring) the bunch oscillates in its
+    quadrupole mode: energy spread and CSR power fluctuate by ~15-20 % at 1.95 f_s.  Both
+    implementations are sampled every 25 steps over 20 synchrotron periods after 2000 steps; compared
+    are the period of the dominant line of the CSR-power and energy-spread spectra (to one
+    frequency bin, 0.05 f_s) and the shape of the spectra between 0.3 and 6 f_s (cosine similarity
+    of the Hann-windowed power spectra >= 0.9)."""
+    p = kara_params(grid_size=256, bunch_current=600e-6)
+    nsamp, every = 800, 25
+    osim = oracle_fma.sim(p)
+    sim = capi.Simulation(ctx_fma, p, 1)
+    sim.set_radiation()
+    sim.step(2000)
+    osim.step(2000)
+    a, b = [], []
+    for _ in range(nsamp):
+        sim.step(every)
+        osim.step(every)
+        a.append(sim.observe()[0][[6, 7]])
+        b.append(osim.observe()[0][[6, 7]])
+    sim.close()
+    osim.close()
+    a, b = np.array(a, np.float64), np.array(b, np.float64)
+    f = np.fft.rfftfreq(nsamp, d=every / 1000.0)  # in units of f_s (1000 steps per T_s)
+    band = (f > 0.3) & (f < 6.0)
+    win = np.hanning(nsamp)
+    for c, name in ((0, "energy spread"), (1, "CSR power")):
+        sa = np.abs(np.fft.rfft((a[:, c] - a[:, c].mean()) * win)) ** 2
+        sb = np.abs(np.fft.rfft((b[:, c] - b[:, c].mean()) * win)) ** 2
+        fa, fb = f[band][np.argmax(sa[band])], f[band][np.argmax(sb[band])]
+        assert 1.5 < fb < 2.5, (name, fb)  # the quadrupole line is there in the reference
+        assert abs(fa - fb) <= f[1] + 1e-12, (name, fa, fb)
+        cos = (sa[band] * sb[band]).sum() / np.sqrt((sa[band] ** 2).sum() * (sb[band] ** 2).sum())
+        assert cos >= 0.9, (name, cos)
+        # fluctuation amplitude within 30 %
+        assert abs(a[:, c].std() / b[:, c].std() - 1) < 0.3, (name, a[:, c].std(), b[:, c].std())
+
+
 def test_rf_offsets_can_change_between_steps(capi, ctx_strict, oracle):
     """the DynamicRFKickMap hook (src/SM/DynamicRFKickMap.cpp:80-109: new KickMap::_offset every
     step): a simulation whose RF offsets are replaced half way equals the oracle run with the
