@@ -1149,7 +1149,7 @@ __global__ void __launch_bounds__(512 / QPT, 1) stream_step_kernel(const stream_
 #pragma unroll
             for (int j = 0; j < QPT; j++) {
                 kq[j] = lds128(aload + j * 512);
-                kq[j].x += w1.x + w2.x + __int_as_float(f.x);
+                kq[j].x += 1e-30f * (w1.x + w2.x + (float)f.x);
             }
 #else
             kick_quads<FMA, QPT>(aload, f.x, y0 + f.y, n, near_edge, w1, w2, kq);

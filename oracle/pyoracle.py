@@ -92,6 +92,9 @@ class Oracle:
         L.orc_sim_tables.argtypes = [P, P, P, P, P, P]
         L.orc_sim_set_tables.argtypes = [P, P, P, P, P]
         L.orc_sim_observe.argtypes = [P, _fp, P, P]
+        L.orc_sim_set_rf_modulation.argtypes = [P, _fp, u32]
+        L.orc_rf_calc_kick.argtypes = [ci, u32] + [cf] * 13 + [_fp]
+        L.orc_rf_modulation.argtypes = [u32, cf, cf, cf, cd, cd, cf, _fp, _fp]
 
     # --- single functions -------------------------------------------------------------
     def coefficients(self, f, it):
@@ -212,6 +215,15 @@ class Oracle:
         self.lib.orc_derive(C.byref(params), C.byref(d))
         return d
 
+    def rf_modulation(self, steps, phasespread, amplspread, modampl, modtimeincrement, revolutionpart,
+                      syncphase, gauss):
+        """DynamicRFKickMap::__calcModulation with given normal deviates gauss[steps][2]"""
+        out = np.zeros((steps, 2), f32)
+        g = np.ascontiguousarray(gauss, f32).reshape(-1)
+        self.lib.orc_rf_modulation(steps, phasespread, amplspread, modampl, modtimeincrement,
+                                   revolutionpart, syncphase, g, out.reshape(-1))
+        return out
+
     def sim(self, params, grid=None, particles=None, zwake=None, zrad=None):
         """zwake / zrad: impedance tables made earlier by make_impedance with the same parameters
         (tests/golden/impedance_tables.npz for the parallel-plates configs)"""
@@ -247,6 +259,7 @@ class Ref:
         L.ref_sim_tables.argtypes = [P, P, P, P, P, P]
         L.ref_sim_observe.argtypes = [P, _fp, P, P]
         L.ref_sim_units.argtypes = [P, C.POINTER(cd * 3)]
+        L.ref_sim_set_rf_modulation.argtypes = [P, _fp, u32, ci]
 
     def _check(self, rc):
         if rc == 1:
@@ -412,6 +425,16 @@ class _Sim:
         projy = np.zeros(self.n, f32)
         getattr(self.lib, self.px + "_sim_observe")(self.h, obs, _opt(spec), _opt(projy))
         return obs, spec, projy
+
+    def set_rf_modulation(self, phase_ampl, interpolation=4):
+        """DynamicRFKickMap with the given queue of (phase, amplitude) pairs, one per step"""
+        seq = np.ascontiguousarray(phase_ampl, f32).reshape(-1, 2)
+        if self.px == "orc":
+            self.lib.orc_sim_set_rf_modulation(self.h, seq.reshape(-1), len(seq))
+        else:
+            rc = self.lib.ref_sim_set_rf_modulation(self.h, seq.reshape(-1), len(seq), interpolation)
+            if rc:
+                raise RuntimeError(self.lib.ref_last_error().decode())
 
     def units(self):
         """(Volt, WattPerHertz, Watt) factors of the reference's ElectricField objects"""

@@ -25,6 +25,9 @@
 #include "IO/Display.hpp"
 #include "HelperFunctions.hpp"
 #include "PS/ElectricField.hpp"
+#include "SM/DynamicRFKickMap.hpp"
+#include <queue>
+#include <array>
 #include "PS/PhaseSpace.hpp"
 #include "SM/DriftMap.hpp"
 #include "SM/FokkerPlanckMap.hpp"
@@ -624,6 +627,25 @@ int ref_sim_observe(void* h, float* obs, float* csr_spectrum, float* projy) {
         obs[7] = s->rdtn_field->getCSRPower()[0];
         if (csr_spectrum) std::copy_n(s->rdtn_field->getCSRSpectrum(), s->d.padded_bins, csr_spectrum);
         if (projy) std::copy_n(s->t1->getProjection(1).origin(), s->n, projy);
+    });
+}
+
+// DynamicRFKickMap (src/SM/DynamicRFKickMap.cpp) with a GIVEN modulation queue: the object is built
+// by the reference's sine-RF constructor with zero noise / modulation and its private queue of
+// (phase, amplitude) pairs is replaced (the reference fills it from an unseeded mt19937, :36,80-94).
+// Only for the non-linear RF: the linear constructor of this snapshot binds to the wrong
+// RFKickMap constructor.
+int ref_sim_set_rf_modulation(void* h, const float* phase_ampl, uint32_t count, int interpolation) {
+    ref_sim* s = static_cast<ref_sim*>(h);
+    return guarded([&] {
+        const ivs_derived& d = s->d;
+        auto* m = new DynamicRFKickMap(s->t2, s->t1, s->n, s->n, d.revolutionpart, d.V_eff, d.f_RF, d.V0,
+                                       0, 0, 0, 0, 0, static_cast<SourceMap::InterpolationType>(interpolation),
+                                       false, nullptr);
+        std::queue<std::array<meshaxis_t, 2>> q;
+        for (uint32_t i = 0; i < count; i++) q.push({{phase_ampl[2 * i], phase_ampl[2 * i + 1]}});
+        m->_next_modulation = std::move(q);
+        s->rfm.reset(m);
     });
 }
 

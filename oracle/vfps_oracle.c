@@ -216,6 +216,52 @@ void orc_rf_offsets_nonlinear(uint32_t n, float qmin, float qmax, float pmin, fl
     free(axis0);
 }
 
+/* RFKickMap::_calcKick(phase, ampl) (src/SM/RFKickMap.cpp:59-83) as DynamicRFKickMap::apply calls it
+ * every step (src/SM/DynamicRFKickMap.cpp:96-105) */
+void orc_rf_calc_kick(int linear, uint32_t n, float qmin, float qmax, float pmin, float pmax,
+                      float bl_scale, float dE_scale, float angle, float revolutionpart, float V_RF,
+                      float f_RF, float V0, float phase, float ampl, float* offset) {
+    const float bl2phase = (float)((double)bl_scale / kC * (double)f_RF * kTwoPi);
+    if (linear) {
+        const float delta0 = orc_ruler_delta(n, qmin, qmax);
+        const float syncphase = 0; /* src/SM/RFKickMap.cpp:30 */
+        const float phaseoffs = (syncphase - phase);
+        const float xcenter = orc_ruler_zerobin(n, qmin, qmax);
+        for (uint32_t x = 0; x < n; x++) {
+            offset[x] = tanf(angle) * (xcenter - (float)x);
+            offset[x] += tanf(angle) * phaseoffs / bl2phase / delta0;
+            offset[x] *= ampl;
+        }
+    } else {
+        float* axis0 = (float*)malloc(sizeof(float) * n);
+        orc_ruler_axis(n, qmin, qmax, axis0);
+        const float delta1 = orc_ruler_delta(n, pmin, pmax);
+        for (uint32_t x = 0; x < n; x++) {
+            const float arg = MADD(axis0[x], bl2phase, phase);
+            offset[x] = revolutionpart * MADD(-ampl * V_RF, sinf(arg), V0) / delta1 / dE_scale;
+        }
+        free(axis0);
+    }
+}
+
+/* DynamicRFKickMap::__calcModulation (src/SM/DynamicRFKickMap.cpp:80-94) with the two normal
+ * deviates per step supplied by the caller (gauss[2 i], gauss[2 i + 1]; the reference draws them
+ * from an unseeded mt19937): out[2 i] = phase, out[2 i + 1] = amplitude factor */
+void orc_rf_modulation(uint32_t steps, float phasespread, float amplspread, float modampl,
+                       double modtimeincrement, double revolutionpart, float syncphase,
+                       const float* gauss, float* out) {
+    const float phasenoise_w = (float)(phasespread / sqrt(revolutionpart));
+    const float amplnoise_w = (float)(amplspread / sqrt(revolutionpart));
+    const float modtimedelta = (float)(kTwoPi * modtimeincrement);
+    for (uint32_t i = 0; i < steps; i++) {
+        const float phasenoise = gauss[2 * i] * phasenoise_w;
+        const float amplnoise = gauss[2 * i + 1] * amplnoise_w;
+        const float phasemod = modampl * sinf(modtimedelta * (float)i);
+        out[2 * i] = syncphase + phasenoise + phasemod;
+        out[2 * i + 1] = 1 + amplnoise;
+    }
+}
+
 /* src/SM/DriftMap.cpp:21-30 */
 void orc_drift_offsets(uint32_t n, float qmin, float qmax, float pmin, float pmax,
                        float dE_scale, const float* slip, uint32_t nslip, float E0,
@@ -973,6 +1019,8 @@ struct orc_sim {
     float* particles;
     float *axis0, *axis1;
     float filling;
+    float* rf_seq;             /* DynamicRFKickMap: (phase, amplitude) per step, NULL = static RF */
+    uint32_t rf_seq_len, rf_seq_pos;
 };
 
 static void sim_rebuild_tables(orc_sim* s) {
@@ -1076,7 +1124,7 @@ void orc_sim_destroy(orc_sim* s) {
     free(s->rf); free(s->drift); free(s->fp5);
     free(s->rf_idx); free(s->dr_idx); free(s->wk_idx); free(s->fp_idx);
     free(s->rf_w); free(s->dr_w); free(s->wk_w); free(s->fp_w);
-    free(s->zwake); free(s->zrad); free(s->particles); free(s->axis0); free(s->axis1);
+    free(s->zwake); free(s->zrad); free(s->particles); free(s->axis0); free(s->axis1); free(s->rf_seq);
     free(s);
 }
 
@@ -1096,6 +1144,15 @@ void orc_sim_step(orc_sim* s, uint32_t nsteps) {
         } else {
             memcpy(s->t2, s->t1, sizeof(float) * nn); /* Identity */
         }
+        if (s->rf_seq && s->rf_seq_pos < s->rf_seq_len) {
+            /* DynamicRFKickMap::apply: _calcKick(next modulation), then KickMap::apply */
+            const ivs_derived* d = &s->d;
+            orc_rf_calc_kick((int)s->p.linear_rf, n, d->qmin, d->qmax, d->pmin, d->pmax, d->bl_f, d->dE_f,
+                             d->angle, (float)d->revolutionpart, (float)d->V_eff, (float)d->f_RF,
+                             (float)d->V0, s->rf_seq[2 * s->rf_seq_pos], s->rf_seq[2 * s->rf_seq_pos + 1], s->rf);
+            orc_kick_update_sm(s->rf, n, n, s->it, s->rf_idx, s->rf_w);
+            s->rf_seq_pos++;
+        }
         kick_apply_table(n, s->it, 1, s->rf_idx, s->rf_w, s->t2, s->t1);
         if (s->np) orc_kick_track(n, 1, s->rf, s->particles, s->np);
         kick_apply_table(n, s->it, 0, s->dr_idx, s->dr_w, s->t1, s->t3);
@@ -1110,6 +1167,15 @@ void orc_sim_step(orc_sim* s, uint32_t nsteps) {
         }
         orc_project_x(n, s->t1, s->ws, s->proj);
     }
+}
+
+/* makes the RF map a DynamicRFKickMap with the given (phase, amplitude) queue, one entry per step */
+void orc_sim_set_rf_modulation(orc_sim* s, const float* phase_ampl, uint32_t count) {
+    free(s->rf_seq);
+    s->rf_seq = (float*)malloc(sizeof(float) * 2 * (count ? count : 1));
+    memcpy(s->rf_seq, phase_ampl, sizeof(float) * 2 * count);
+    s->rf_seq_len = count;
+    s->rf_seq_pos = 0;
 }
 
 void orc_sim_derived(const orc_sim* s, ivs_derived* d) { *d = s->d; }

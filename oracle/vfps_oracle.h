@@ -127,6 +127,14 @@ orc_sim* orc_sim_create(const ivs_ring_params* p, const float* grid, const float
 orc_sim* orc_sim_create_z(const ivs_ring_params* p, const float* grid, const float* particles,
                           uint32_t np, const float* zwake, const float* zrad);
 void orc_sim_destroy(orc_sim* s);
+/* DynamicRFKickMap (src/SM/DynamicRFKickMap.cpp:80-109) with a given modulation queue */
+void orc_sim_set_rf_modulation(orc_sim* s, const float* phase_ampl, uint32_t count);
+void orc_rf_calc_kick(int linear, uint32_t n, float qmin, float qmax, float pmin, float pmax,
+                      float bl_scale, float dE_scale, float angle, float revolutionpart, float V_RF,
+                      float f_RF, float V0, float phase, float ampl, float* offset);
+void orc_rf_modulation(uint32_t steps, float phasespread, float amplspread, float modampl,
+                       double modtimeincrement, double revolutionpart, float syncphase,
+                       const float* gauss, float* out);
 void orc_sim_step(orc_sim* s, uint32_t nsteps);
 void orc_sim_derived(const orc_sim* s, ivs_derived* d);
 void orc_sim_get(const orc_sim* s, float* grid, float* profile, float* wake, float* particles);
