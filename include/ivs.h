@@ -264,6 +264,32 @@ ivs_status ivs_sim_renormalize(ivs_sim* sim);
  * fused kernel stages. */
 ivs_status ivs_sim_set_rf_offset(ivs_sim* sim, const float* rf_offset);
 
+/* DynamicRFKickMap (src/SM/DynamicRFKickMap.cpp:14-109): the RF map whose phase and amplitude
+ * change every step.  The constants of RFKickMap::_calcKick(phase, ampl) (src/SM/RFKickMap.cpp:59-83)
+ * as the constructors derive them (:15-57); ivs_rf_model_init (ivs_host.h) fills it from ring
+ * parameters.  linear != 0: offset[x] = (tan(angle) (xcenter - x) + tan(angle) (syncphase - phase) /
+ * bl2phase / delta0) * ampl; else offset[x] = revolutionpart (-ampl V_RF sin(q_x bl2phase + phase) + V0)
+ * / delta1 / dE_scale. */
+typedef struct ivs_rf_model {
+    uint32_t linear;
+    float tan_angle;      /* std::tan(_angle), fp32 */
+    float xcenter;        /* axis 0 zerobin */
+    float syncphase;      /* 0 (linear) or asin(V0 / V_RF) */
+    float bl2phase;       /* scale(0,"Meter") / c * f_RF * 2 pi */
+    float qmin, delta0;   /* axis 0 */
+    float delta1;         /* axis 1 delta */
+    float dE_scale;       /* scale(1,"ElectronVolt") */
+    float revolutionpart, V_RF, V0;
+} ivs_rf_model;
+/* Makes the RF kick dynamic: step i (counted from this call) applies _calcKick(phase_ampl[2 i],
+ * phase_ampl[2 i + 1]) -- the queue DynamicRFKickMap::__calcModulation fills for all steps of the run
+ * (:80-94; ivs_rf_modulation in ivs_host.h generates one from a seed).  The queue is copied to the
+ * device and walked by a one-block kernel in front of every step, inside the step graph; past its end
+ * the last offsets stay in force.  count = 0 returns to the static map set by ivs_sim_set_rf_offset /
+ * ivs_sim_create.  The reference applies a DynamicRFKickMap on the CPU only (no OpenCL path, hpp:75). */
+ivs_status ivs_sim_set_rf_modulation(ivs_sim* sim, const ivs_rf_model* model, const float* phase_ampl,
+                                     uint32_t count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,17 @@ int ivs_gaussian_projection(uint32_t n, float amin, float amax, double zoom, flo
 /* PhaseSpace::PhaseSpace with data == nullptr followed by main()'s initial
  * renormalisation (src/PS/PhaseSpace.cpp:52-65,457-484; src/main.cpp:528-532): n*n floats */
 int ivs_initial_grid(const ivs_derived* d, uint32_t n, double zoom, float* grid);
+/* the constants of RFKickMap::_calcKick for these ring parameters (src/SM/RFKickMap.cpp:15-57 as
+ * src/main.cpp:600-650 calls the constructors): `model` points at an ivs_rf_model (ivs.h) */
+int ivs_rf_model_init(const ivs_ring_params* p, const ivs_derived* d, void* model);
+/* DynamicRFKickMap::__calcModulation (src/SM/DynamicRFKickMap.cpp:80-94): out[2 i] = syncphase +
+ * N(0,1) phasespread / sqrt(revolutionpart) + modampl sin(float(2 pi modtimeincrement) i),
+ * out[2 i + 1] = 1 + N(0,1) amplspread / sqrt(revolutionpart).  The normal deviates come from `gauss`
+ * (2 per step) if given, else from a counter-based generator keyed on `seed` (the reference uses an
+ * unseeded mt19937, :36, which cannot be reproduced). */
+int ivs_rf_modulation(uint64_t seed, uint32_t steps, float phasespread, float amplspread, float modampl,
+                      double modtimeincrement, double revolutionpart, float syncphase, const float* gauss,
+                      float* out);
 /* Haissinski start distribution f = rho(q) exp(-p^2/2) (BASELINE configs[2]; the reference parses
  * HaissinskiIterations and ignores it, src/IO/ProgramOptions.cpp:270-272): the stationary bunch
  * profile rho ~ exp((dp/angle) int (rf + W[rho]) dq) of the step map, W[rho] = ElectricField::

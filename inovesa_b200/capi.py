@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .params import Derived, RingParams, SimDesc
+from .params import Derived, RfModel, RingParams, SimDesc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # IVS_LIB: another build of the same library (A/B timing of kernel variants, tools/ab.sh)
@@ -76,6 +76,9 @@ SIGNATURES = {
     "ivs_sim_fields": (ci, [P, P, P]),
     "ivs_sim_renormalize": (ci, [P]),
     "ivs_sim_set_rf_offset": (ci, [P, _fp]),
+    "ivs_sim_set_rf_modulation": (ci, [P, C.POINTER(RfModel), P, u32]),
+    "ivs_rf_model_init": (ci, [C.POINTER(RingParams), C.POINTER(Derived), C.POINTER(RfModel)]),
+    "ivs_rf_modulation": (ci, [u64, u32, cf, cf, cf, cd, cd, cf, P, _fp]),
     # include/ivs_host.h
     "ivs_default_params": (None, [C.POINTER(RingParams)]),
     "ivs_derive": (ci, [C.POINTER(RingParams), C.POINTER(Derived)]),
@@ -200,6 +203,26 @@ def haissinski_grid(params, d, zwake=None, wakescaling=None, iterations=2000, re
     if rc not in (0, 1):
         raise IvsError(rc, "ivs_haissinski_grid")
     return g, res.value
+
+
+def rf_model(params, d):
+    m = RfModel()
+    rc = load().ivs_rf_model_init(C.byref(params), C.byref(d), C.byref(m))
+    if rc:
+        raise IvsError(rc, "ivs_rf_model_init")
+    return m
+
+
+def rf_modulation(steps, phasespread, amplspread, modampl, modtimeincrement, revolutionpart, syncphase,
+                  seed=0, gauss=None):
+    """DynamicRFKickMap::__calcModulation: (phase, amplitude) per step, [steps][2]"""
+    out = np.zeros((steps, 2), f32)
+    g = None if gauss is None else np.ascontiguousarray(gauss, f32).reshape(-1)
+    rc = load().ivs_rf_modulation(seed, steps, phasespread, amplspread, modampl, modtimeincrement,
+                                  revolutionpart, syncphase, _ptr(g), out.reshape(-1))
+    if rc:
+        raise IvsError(rc, "ivs_rf_modulation")
+    return out
 
 
 def airy(x):
@@ -554,6 +577,15 @@ class Simulation:
         rf = np.ascontiguousarray(rf, f32)
         assert rf.shape == (self.n,)
         self.ctx.check(self.lib.ivs_sim_set_rf_offset(self.h, rf))
+
+    def set_rf_modulation(self, phase_ampl, model=None):
+        """make the RF map a DynamicRFKickMap with this queue of (phase, amplitude) pairs; None: static again"""
+        if phase_ampl is None:
+            self.ctx.check(self.lib.ivs_sim_set_rf_modulation(self.h, None, None, 0))
+            return
+        seq = np.ascontiguousarray(phase_ampl, f32).reshape(-1, 2)
+        m = rf_model(self.params, self.d) if model is None else model
+        self.ctx.check(self.lib.ivs_sim_set_rf_modulation(self.h, C.byref(m), _ptr(seq), len(seq)))
 
     @property
     def steps_done(self):

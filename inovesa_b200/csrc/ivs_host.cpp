@@ -563,6 +563,71 @@ int ivs_initial_grid(const ivs_derived* d, uint32_t n, double zoom, float* grid)
     return IVS_OK;
 }
 
+// RFKickMap constructors (src/SM/RFKickMap.cpp:15-57) with the arguments of src/main.cpp:600-650
+int ivs_rf_model_init(const ivs_ring_params* o, const ivs_derived* d, void* model) {
+    if (!o || !d || !model) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_rf_model* m = static_cast<ivs_rf_model*>(model);
+    const Axis ax0(o->grid_size, d->qmin, d->qmax), ax1(o->grid_size, d->pmin, d->pmax);
+    const float f_RF = static_cast<float>(d->f_RF);
+    std::memset(m, 0, sizeof(*m));
+    m->linear = o->linear_rf ? 1u : 0u;
+    m->bl2phase = static_cast<float>(static_cast<double>(d->bl_f) / phys::c * static_cast<double>(f_RF) * kTwoPi);
+    m->xcenter = ax0.zerobin;
+    m->qmin = ax0.min;
+    m->delta0 = ax0.delta;
+    m->delta1 = ax1.delta;
+    m->dE_scale = d->dE_f;
+    if (o->linear_rf) {
+        m->tan_angle = std::tan(d->angle);
+        m->syncphase = 0;
+    } else {
+        m->revolutionpart = static_cast<float>(d->revolutionpart);
+        m->V_RF = static_cast<float>(d->V_eff);
+        m->V0 = static_cast<float>(d->V0);
+        m->syncphase = std::asin(m->V0 / m->V_RF);
+    }
+    return IVS_OK;
+}
+
+namespace {
+inline uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+}  // namespace
+
+// DynamicRFKickMap::__calcModulation (src/SM/DynamicRFKickMap.cpp:80-94)
+int ivs_rf_modulation(uint64_t seed, uint32_t steps, float phasespread, float amplspread, float modampl,
+                      double modtimeincrement, double revolutionpart, float syncphase, const float* gauss,
+                      float* out) {
+    if (!out || !(revolutionpart > 0)) return IVS_ERR_INVALID_ARGUMENT;
+    const float phasenoise_w = static_cast<float>(phasespread / std::sqrt(revolutionpart));
+    const float amplnoise_w = static_cast<float>(amplspread / std::sqrt(revolutionpart));
+    const float modtimedelta = static_cast<float>(kTwoPi * modtimeincrement);
+    for (uint32_t i = 0; i < steps; i++) {
+        float g0, g1;
+        if (gauss) {
+            g0 = gauss[2 * i];
+            g1 = gauss[2 * i + 1];
+        } else {  // Box-Muller on two counter-based uniforms
+            const uint64_t h = mix64(seed ^ mix64(i));
+            const double u1 = (static_cast<double>(h >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+            const double u2 = static_cast<double>(mix64(h) >> 11) * (1.0 / 9007199254740992.0);
+            const double r = std::sqrt(-2.0 * std::log(u1));
+            g0 = static_cast<float>(r * std::cos(kTwoPi * u2));
+            g1 = static_cast<float>(r * std::sin(kTwoPi * u2));
+        }
+        const float phasenoise = g0 * phasenoise_w;
+        const float amplnoise = g1 * amplnoise_w;
+        const float phasemod = modampl * std::sin(modtimedelta * static_cast<float>(i));
+        out[2 * i] = syncphase + phasenoise + phasemod;
+        out[2 * i + 1] = 1 + amplnoise;
+    }
+    return IVS_OK;
+}
+
 // Haissinski start distribution (BASELINE.json configs[2] "Haissinski-initialised"; the reference
 // parses HaissinskiIterations and ignores it, src/IO/ProgramOptions.cpp:270-272, so this is an
 // addition: the grid goes to PhaseSpace's `data` constructor argument, inc/PS/PhaseSpace.hpp:60).

@@ -50,6 +50,12 @@ ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, ui
                                  float dp, uint64_t seed, unsigned int* step_counter,
                                  const int* sim_status = nullptr);
 
+// DynamicRFKickMap: one block that turns the next (phase, amplitude) entry of the device queue into
+// KickMap::_offset and the fused kernels' tap tables (ivs_dynrf.cu)
+ivs_status ivs_dynrf_launch(ivs_ctx* ctx, const ivs_rf_model* model, const float* d_seq, uint32_t count,
+                            unsigned int* d_pos, const int* sim_status, uint32_t n, uint32_t it, float* d_offset,
+                            int* d_first, void* d_w, int* d_flag, int lo, int hi);
+
 // the fused step kernel (ivs_fused.cu)
 struct ivs_fused_plan {
     uint32_t launches_per_step = 1;

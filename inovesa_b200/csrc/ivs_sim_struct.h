@@ -36,6 +36,14 @@ struct ivs_sim {
     int cur_at_reset = 0;         // ... and the buffer parity at that moment
     uint64_t fallback_steps = 0;  // steps redone through the kernel sequence after an overflow
     unsigned int* track_counter = nullptr;  // device step counter of the stochastic tracking mode (+ block ticket)
+    // DynamicRFKickMap: model constants, device queue of (phase, amplitude) pairs, position in it
+    // (device word 0; word 1 = "an RF tap left the staged pad") and the step count at which it was set
+    bool dyn_rf = false;
+    ivs_rf_model rf_model{};
+    float* rf_seq = nullptr;
+    uint32_t rf_seq_len = 0;
+    unsigned int* rf_pos = nullptr;
+    uint64_t rf_step0 = 0;
     float f_scale = 0, cutoff = 0;
     uint64_t steps_done = 0;
     ivs_fused_plan plan{};

@@ -65,7 +65,16 @@ ivs_status enqueue_unfused_step(ivs_sim* s) {
 }
 
 ivs_status enqueue_step(ivs_sim* s) {
-    if (s->desc.flags & IVS_SIM_UNFUSED) return enqueue_unfused_step(s);
+    const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
+    if (s->dyn_rf) {
+        // DynamicRFKickMap::apply: _calcKick(next modulation) before the map is applied
+        // (src/SM/DynamicRFKickMap.cpp:102-109)
+        IVS_TRY(ivs_dynrf_launch(s->ctx, &s->rf_model, s->rf_seq, s->rf_seq_len, s->rf_pos,
+                                 unfused ? nullptr : s->status, s->n, s->it, s->rf,
+                                 unfused ? nullptr : (int*)s->plan.rf_first, unfused ? nullptr : s->plan.rf_w,
+                                 (int*)(s->rf_pos + 1), -16, 12));
+    }
+    if (unfused) return enqueue_unfused_step(s);
     return ivs_fused_enqueue_step(s->ctx, &s->plan, s);
 }
 
@@ -101,8 +110,8 @@ ivs_status capture(ivs_sim* s, uint32_t steps, cudaGraphExec_t* out) {
 
 // how many kernels one step launches (for ivs_ctx_launch_count bookkeeping under graphs)
 uint32_t launches_per_step(const ivs_sim* s) {
-    if (!(s->desc.flags & IVS_SIM_UNFUSED)) return s->plan.launches_per_step + (s->np ? 1 : 0);
-    uint32_t k = 3;  // rf kick, drift, projection
+    if (!(s->desc.flags & IVS_SIM_UNFUSED)) return s->plan.launches_per_step + (s->np ? 1 : 0) + (s->dyn_rf ? 1 : 0);
+    uint32_t k = 3 + (s->dyn_rf ? 1 : 0);  // rf kick, drift, projection
     if (s->has_wake) k += 2;
     if (s->has_fp) k += 1;
     if (s->np) k += 1;
@@ -246,7 +255,7 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
     float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
                      s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
                      (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power,
-                     (float*)s->track_counter, s->spectrum, s->wake_now};
+                     (float*)s->track_counter, s->spectrum, s->wake_now, s->rf_seq, (float*)s->rf_pos};
     for (float* b : bufs) if (b) cudaFree(b);
     if (s->status) cudaFree(s->status);
     if (s->host_flag) cudaFreeHost(s->host_flag);
@@ -313,6 +322,12 @@ static ivs_status settle(ivs_sim* s) {
     for (;;) {
         IVS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if ((s->desc.flags & IVS_SIM_UNFUSED) || s->fused_enqueued == 0) return IVS_OK;
+        if (s->dyn_rf) {
+            unsigned int w[2];
+            IVS_CUDA(ctx, cudaMemcpy(w, s->rf_pos, sizeof(w), cudaMemcpyDeviceToHost));
+            if (w[1] != 0)
+                return ivs_fail(ctx, IVS_ERR_HALO, "a dynamic RF kick displacement exceeds the fused kernel's staged pad: pass IVS_SIM_UNFUSED");
+        }
         if (*reinterpret_cast<volatile int*>(s->host_flag) == 0) {
             // clean; keep the 32-bit ticket counter far from wrapping
             if (s->fused_enqueued > (1u << 20)) IVS_TRY(reset_status(s));
@@ -328,6 +343,13 @@ static ivs_status settle(ivs_sim* s) {
         s->steps_done -= redo;
         IVS_TRY(reset_status(s));
         if (!s->grid[2]) IVS_TRY(dalloc(ctx, &s->grid[2], (size_t)s->members * s->n * s->n));
+        if (s->dyn_rf) {
+            // the queue position follows the steps that count: the offending step's entry is next again
+            const unsigned int pos = (unsigned int)std::min<uint64_t>(s->steps_done - s->rf_step0, s->rf_seq_len);
+            IVS_CUDA(ctx, cudaMemcpy(s->rf_pos, &pos, sizeof(pos), cudaMemcpyHostToDevice));
+            IVS_TRY(ivs_dynrf_launch(ctx, &s->rf_model, s->rf_seq, s->rf_seq_len, s->rf_pos, nullptr, s->n, s->it,
+                                     s->rf, (int*)s->plan.rf_first, s->plan.rf_w, (int*)(s->rf_pos + 1), -16, 12));
+        }
         IVS_TRY(enqueue_unfused_step(s));
         s->steps_done++;
         s->fallback_steps++;
@@ -482,6 +504,46 @@ ivs_status ivs_sim_set_rf_offset(ivs_sim* s, const float* rf_offset) {
     // the stream orders the copy after the steps already enqueued; the host array is consumed here
     IVS_TRY(ivs_upload(ctx, s->rf, rf_offset, s->n * sizeof(float)));
     return ivs_sync(ctx);
+}
+
+ivs_status ivs_sim_set_rf_modulation(ivs_sim* s, const ivs_rf_model* model, const float* phase_ampl,
+                                     uint32_t count) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_REQUIRE(ctx, count == 0 || (model && phase_ampl), "ivs_sim_set_rf_modulation: null pointer");
+    IVS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IVS_TRY(settle(s));
+    const bool was = s->dyn_rf;
+    if (s->rf_seq) { cudaFree(s->rf_seq); s->rf_seq = nullptr; }
+    s->dyn_rf = count != 0;
+    s->rf_seq_len = count;
+    s->rf_step0 = s->steps_done;
+    if (s->dyn_rf) {
+        s->rf_model = *model;
+        IVS_TRY(dalloc(ctx, &s->rf_seq, (size_t)2 * count));
+        IVS_TRY(ivs_upload(ctx, s->rf_seq, phase_ampl, (size_t)2 * count * sizeof(float)));
+        if (!s->rf_pos) IVS_TRY(dalloc(ctx, &s->rf_pos, 4));
+        IVS_TRY(ivs_memset_zero(ctx, s->rf_pos, 4 * sizeof(unsigned int)));
+        IVS_TRY(ivs_sync(ctx));
+    }
+    if (was != s->dyn_rf) {
+        // the step graphs gain or lose a node per step
+        drop_graphs(s);
+        if (!(s->desc.flags & IVS_SIM_NO_GRAPH)) {
+            const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
+            const int cur = s->cur;
+            IVS_TRY(capture(s, ivs_sim::kGraphSteps, &s->graphK[cur]));
+            if (unfused) {
+                IVS_TRY(capture(s, 1, &s->graph1[cur]));
+            } else {
+                s->cur = s->pcur = cur ^ 1;
+                ivs_status st = capture(s, ivs_sim::kGraphSteps, &s->graphK[cur ^ 1]);
+                s->cur = s->pcur = cur;
+                if (st != IVS_OK) return st;
+            }
+        }
+    }
+    return IVS_OK;
 }
 
 }  // extern "C"

@@ -102,6 +102,14 @@ def kara_params(**overrides):
     return default_params(**base)
 
 
+class RfModel(C.Structure):
+    """ivs_rf_model (include/ivs.h): constants of RFKickMap::_calcKick(phase, ampl)"""
+
+    _fields_ = [("linear", C.c_uint32)] + [(k, C.c_float) for k in (
+        "tan_angle", "xcenter", "syncphase", "bl2phase", "qmin", "delta0", "delta1", "dE_scale",
+        "revolutionpart", "V_RF", "V0")]
+
+
 class SimDesc(C.Structure):
     """ivs_sim_desc (include/ivs.h)."""
 

@@ -458,6 +458,49 @@ def test_rf_offsets_can_change_between_steps(capi, ctx_strict, oracle):
     assert e.value.code == capi.ERR_HALO
 
 
+@pytest.mark.parametrize("linear", [0, 1], ids=["sine-rf", "linear-rf"])
+def test_dynamic_rf_kick_map_matches_oracle(capi, ctx_strict, oracle, rng, linear):
+    """DynamicRFKickMap (src/SM/DynamicRFKickMap.cpp:80-109): phase noise, amplitude noise and a
+    sinusoidal phase modulation re-drawn every step.  The queue of (phase, amplitude) pairs is made by
+    the host helper from given normal deviates, handed to the oracle (whose DynamicRF restatement equals
+    the reference's own class bit for bit, tests/test_oracle_vs_ref.py) and to the device, where a
+    one-block kernel walks it inside the step graph -- on all three step paths, across graph replays,
+    direct launches and a change back to the static map."""
+    p = kara_params(grid_size=256, linear_rf=linear, steps_per_Ts=2000)
+    d = capi.derive(p)
+    m = capi.rf_model(p, d)
+    nsteps = 45
+    gauss = rng.standard_normal((nsteps, 2)).astype(f32)
+    seq = capi.rf_modulation(nsteps, 2e-3, 5e-4, 8e-3, 0.013, d.revolutionpart, m.syncphase, gauss=gauss)
+    assert np.array_equal(seq, oracle.rf_modulation(nsteps, 2e-3, 5e-4, 8e-3, 0.013, d.revolutionpart, m.syncphase, gauss))
+    assert seq[:, 0].std() > 1e-3 and np.abs(seq[:, 1] - 1).max() > 1e-4
+    osim = oracle.sim(p)
+    osim.set_rf_modulation(seq)
+    checkpoints = [3, 19, 45, 60]  # direct launches, a graph replay, ..., 15 steps past the end of the queue
+    want, done = [], 0
+    for cp in checkpoints:
+        osim.step(cp - done); done = cp
+        want.append(osim.get()[0].copy())
+    static = oracle.sim(p); static.step(45)
+    assert rel_l1(static.get()[0], want[2]) > 1e-4  # the modulation is not a no-op
+    static.close(); osim.close()
+    for flags in (0, capi.SIM_TILED, capi.SIM_UNFUSED, capi.SIM_NO_GRAPH):
+        sim = capi.Simulation(ctx_strict, p, 1, flags=flags)
+        sim.set_rf_modulation(seq)
+        done = 0
+        for cp, w in zip(checkpoints, want):
+            sim.step(cp - done); done = cp
+            assert rel_l1(sim.download()[0][0], w) <= L1_TOL, (flags, cp)
+        sim.close()
+    # seeded generator: reproducible, different seeds differ, N(0,1) statistics
+    a = capi.rf_modulation(4000, 1e-3, 1e-3, 0.0, 0.0, d.revolutionpart, 0.0, seed=5)
+    b = capi.rf_modulation(4000, 1e-3, 1e-3, 0.0, 0.0, d.revolutionpart, 0.0, seed=5)
+    c = capi.rf_modulation(4000, 1e-3, 1e-3, 0.0, 0.0, d.revolutionpart, 0.0, seed=6)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    sig = 1e-3 / np.sqrt(d.revolutionpart)
+    assert abs(a[:, 0].std() / sig - 1) < 0.05 and abs((a[:, 1] - 1).std() / sig - 1) < 0.05 and abs(a[:, 0].mean()) < 0.1 * sig
+
+
 def test_invalid_descriptors(capi, ctx_strict):
     p = kara_params(grid_size=4)
     with pytest.raises(capi.IvsError) as e:

@@ -128,3 +128,24 @@ def test_whole_simulation_bit_exact(oracle, ref, rng, kw):
     finally:
         rs.close()
         os_.close()
+
+
+def test_dynamic_rf_kick_map_bit_for_bit(oracle, ref):
+    """the oracle's DynamicRFKickMap restatement against the reference's own class (sine RF; the queue of
+    (phase, amplitude) pairs is given to both: the reference fills it from an unseeded mt19937)"""
+    from inovesa_b200.params import kara_params
+    p = kara_params(grid_size=64, linear_rf=0, steps_per_Ts=2000)
+    d = oracle.derive(p)
+    rng = np.random.default_rng(3)
+    sync = np.float32(np.arcsin(np.float32(d.V0) / np.float32(d.V_eff)))
+    seq = oracle.rf_modulation(30, 1e-3, 2e-4, 5e-3, 0.01, d.revolutionpart, sync, rng.standard_normal((30, 2)))
+    a, b, c = oracle.sim(p), ref.sim(p), oracle.sim(p)
+    a.set_rf_modulation(seq)
+    b.set_rf_modulation(seq)
+    for sim in (a, b, c):
+        sim.step(30)
+    ga, gb, gc = a.get()[0], b.get()[0], c.get()[0]
+    for sim in (a, b, c):
+        sim.close()
+    assert np.array_equal(ga, gb)
+    assert not np.array_equal(ga, gc)
