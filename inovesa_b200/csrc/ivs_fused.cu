@@ -671,24 +671,25 @@ __device__ __forceinline__ void sts128_volatile_if(uint32_t addr, const float4 v
 // `p` is the shared address of in[y0 + a], a = (f1+f2) rounded down to a multiple of 4, RR the rest
 // (A, B, C = the 12 staged values from p on, loaded by the caller);
 // m0 = y0 + f2 is the first wake-kicked column the quad needs.
-template <bool FMA, int RR, bool EDGE>
-__device__ __forceinline__ float4 kick_quad_rr(const float4 A, const float4 B, const float4 C, const float4 D, int m0, uint32_t n,
+template <bool FMA, int RR>
+__device__ __forceinline__ float4 kick_quad_rr(uint32_t p, const float4 A, const float4 B, const float4 C, int m0, uint32_t n,
                                                bool near_edge, const float4 w1, const float4 w2) {
-    // A, B, C (and D for the shift by 3) = the 12 (16) staged values from the aligned position on
     float in[16];
     {
         in[0] = A.x; in[1] = A.y; in[2] = A.z; in[3] = A.w;
         in[4] = B.x; in[5] = B.y; in[6] = B.z; in[7] = B.w;
         in[8] = C.x; in[9] = C.y; in[10] = C.z; in[11] = C.w;
-        in[12] = D.x; in[13] = D.y; in[14] = D.z; in[15] = D.w;
+        if (RR == 3) {
+            const float4 D = lds128(p + 48);
+            in[12] = D.x; in[13] = D.y; in[14] = D.z; in[15] = D.w;
+        }
     }
     float k1[7];
 #pragma unroll
     for (int i = 0; i < 7; i++) k1[i] = tap4<FMA>(in[RR + i], in[RR + i + 1], in[RR + i + 2], in[RR + i + 3], w1);
     // some of m0 .. m0+6 lie outside the grid: the wake-kicked grid is 0 there.  near_edge is a
-    // per-warp constant (only the first and the last warp of a row can get there); the instances of
-    // the row loop for the other warps (EDGE = false) do not contain the test
-    if (EDGE && near_edge && (uint32_t)m0 > n - 7) {
+    // per-warp constant (only the first and the last warp of a row can get there)
+    if (near_edge && (uint32_t)m0 > n - 7) {
 #pragma unroll
         for (int i = 0; i < 7; i++)
             if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
@@ -700,6 +701,23 @@ __device__ __forceinline__ float4 kick_quad_rr(const float4 A, const float4 B, c
     o.w = tap4<FMA>(k1[3], k1[4], k1[5], k1[6], w2);
     return o;
 }
+template <bool FMA>
+__device__ __forceinline__ float4 kick_quad(uint32_t row_q, int fsum, int m0, uint32_t n, bool near_edge, const float4 w1,
+                                            const float4 w2) {
+    const int a = fsum & ~3;  // floor to a multiple of 4 (two's complement: also for negatives)
+    const uint32_t p = row_q + (uint32_t)(a * 4);
+    // the three quads every alignment needs are requested before the switch (their latency then
+    // overlaps the branch); only the shift by 3 needs a fourth.  (Requested before the tap tables
+    // instead, or a whole stencil step earlier, measured 1 % and 6 % slower.)
+    const float4 A = lds128(p), B = lds128(p + 16), C = lds128(p + 32);
+    switch (fsum - a) {
+    case 0: return kick_quad_rr<FMA, 0>(p, A, B, C, m0, n, near_edge, w1, w2);
+    case 1: return kick_quad_rr<FMA, 1>(p, A, B, C, m0, n, near_edge, w1, w2);
+    case 2: return kick_quad_rr<FMA, 2>(p, A, B, C, m0, n, near_edge, w1, w2);
+    default: return kick_quad_rr<FMA, 3>(p, A, B, C, m0, n, near_edge, w1, w2);
+    }
+}
+
 #if IVS_PROBE_NOFP
 __device__ __forceinline__ float warp_sum_probe(float v) {
     for (int o = 8; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -712,31 +730,32 @@ __device__ __forceinline__ float warp_sum_probe(float v) {
 __device__ __forceinline__ uint32_t wwin_pos(uint32_t t) { return t + (t >> 3); }
 
 // wake kick + RF kick of the QPT quads a thread owns in one staged row (quad j sits 32 quads =
-// 512 bytes after quad j-1).  RR = (f1 + f2) mod 4, the alignment of the first tap, is the same for
-// all of them and a template parameter: the row loop is instantiated per alignment and only leaves
-// an instance when the alignment changes (every few hundred rows), so the instructions a warp
-// fetches in steady state are one contiguous loop body instead of one of four variants behind a switch.
-// the staged values the kick of the QPT quads of a thread needs (quad j sits 32 quads = 512 bytes
-// after quad j-1), from the aligned position p on
-template <int QPT, int RR>
-struct kick_in {
-    float4 A[QPT], B[QPT], C[QPT], D[QPT];
-    __device__ __forceinline__ void load(uint32_t p) {
-#pragma unroll
-        for (int j = 0; j < QPT; j++) {
-            A[j] = lds128(p + j * 512);
-            B[j] = lds128(p + j * 512 + 16);
-            C[j] = lds128(p + j * 512 + 32);
-            D[j] = RR == 3 ? lds128(p + j * 512 + 48) : make_float4(0, 0, 0, 0);  // only the shift by 3 needs a fourth
-        }
-    }
-};
-template <bool FMA, int QPT, int RR, bool EDGE>
-__device__ __forceinline__ void kick_quads(const kick_in<QPT, RR>& in, int m0, uint32_t n, const bool (&near_edge)[QPT],
+// 512 bytes after quad j-1).  The alignment of the first tap is the same for all of them, so one
+// warp-uniform switch serves QPT independent chains of arithmetic.
+template <bool FMA, int QPT>
+__device__ __forceinline__ void kick_quads(uint32_t row_q, int fsum, int m0, uint32_t n, const bool (&near_edge)[QPT],
                                            const float4 w1, const float4 w2, float4 (&kq)[QPT]) {
+    const int a = fsum & ~3;  // floor to a multiple of 4 (two's complement: also for negatives)
+    const uint32_t p = row_q + (uint32_t)(a * 4);
+    // the three staged quads every alignment needs are requested before the switch (their latency
+    // then overlaps the branch); only the shift by 3 needs a fourth
+    float4 A[QPT], B[QPT], C[QPT];
 #pragma unroll
-    for (int j = 0; j < QPT; j++)
-        kq[j] = kick_quad_rr<FMA, RR, EDGE>(in.A[j], in.B[j], in.C[j], in.D[j], m0 + j * 128, n, near_edge[j], w1, w2);
+    for (int j = 0; j < QPT; j++) {
+        A[j] = lds128(p + j * 512);
+        B[j] = lds128(p + j * 512 + 16);
+        C[j] = lds128(p + j * 512 + 32);
+    }
+#define IVS_KICK_CASE(RR)                                                                                       \
+    _Pragma("unroll") for (int j = 0; j < QPT; j++)                                                             \
+        kq[j] = kick_quad_rr<FMA, RR>(p + j * 512, A[j], B[j], C[j], m0 + j * 128, n, near_edge[j], w1, w2);
+    switch (fsum - a) {
+    case 0: IVS_KICK_CASE(0) break;
+    case 1: IVS_KICK_CASE(1) break;
+    case 2: IVS_KICK_CASE(2) break;
+    default: IVS_KICK_CASE(3) break;
+    }
+#undef IVS_KICK_CASE
 }
 
 // A thread owns QPT quads of columns (QPT float4 per row) for the whole strip: quad j of the thread
@@ -1115,289 +1134,183 @@ __global__ void __launch_bounds__(512 / QPT, 1) stream_step_kernel(const stream_
         const bool red_lane = QPT == 2 ? (lane & 15) == 0 : lane == 0;
         const uint32_t lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
 
-        // shared-memory stores of the row loop: plain asm (ordered among the other asm statements, which
-        // is all the ordering they need) -- a "memory" clobber would pin every load behind them
-        auto sts128 = [](uint32_t addr, const float4 v) {
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
-        };
-        const uint32_t mail_mask = kMailSlots - 1;
-        // the neighbour warps' edge values of output row `orow` (lane 0 / lane 31 read them): blocks,
-        // serving the staging duty, until both have posted the row
-        auto mail_wait = [&](const int it, const uint32_t orow) -> float4 {
-            float4 m = make_float4(0, 0, 0, 0);
-            const uint32_t pa = peek + (orow & mail_mask) * 16;
-            if (edge) m = lds128_volatile(pa);
-            uint32_t tries = 0;
-            while (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1)) {
-                // the neighbour is more than kLag - 1 rows behind: poll (warp-uniformly, so that lane 0
-                // keeps serving the staging duty)
-                if (it >= pwin) {
-                    duty_probe();
-                    duty_issue();
-                }
-                if (edge) m = lds128_volatile(pa);
-#if IVS_WARP_CLOCKS
-                n_mpoll++;
-#endif
-                if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
-            }
-            return m;
-        };
-        // the slow paths at the end of a kick: this warp's turn to stage a row (one in NW iterations),
-        // or the next kick's row has not landed yet (kbar / kpar already point at it)
-        auto kick_tail = [&](const int it, const uint32_t landed) {
-            if (it >= pwin) {
-                duty_probe();
-                duty_issue();
-            }
-            if (!landed) wait_row(kbar, kpar, it);
-        };
-
-        // ---- One iteration = up to two independent pieces of work:
-        //   KICK: staged row r0 + it -> wake kick + RF kick -> drift sums -> drifted row d (output row
-        //         it - NT + 1 once the sums are full), parked in the FIFO; POST: d is a real output row
-        //         whose edge values the neighbour warps need; MORE: another kick follows.
-        //   STEN: the stencil step on drifted output row `orow` (parked kLag iterations ago, read from
-        //         the FIFO slot this iteration's kick overwrites): neighbours, Fokker-Planck, store,
-        //         partial row sum; the warp sum of the row before is reduced on the side.
-        // Written as ONE straight-line sequence -- every load first, every store last, no branch in
-        // between -- so that the compiler interleaves the two instruction streams: the shuffles, the
-        // row-sum butterfly and the shared-memory round trips of the stencil step hide behind the kick's
-        // arithmetic.  m = the neighbours' mailbox entry for `orow` (already there, see mail_wait).
-        // Returns whether the next kick's staged row has landed.
-        auto iteration = [&](auto rr_tag, auto edge_tag, auto kick_tag, auto sten_tag, const int it, const uint32_t orow,
-                             const float4 m, const bool POST, const bool MORE) -> uint32_t {
-            constexpr int RR = decltype(rr_tag)::value;
-            constexpr bool EDGE = decltype(edge_tag)::value, KICK = decltype(kick_tag)::value, STEN = decltype(sten_tag)::value;
-            const uint32_t fa = fifo_t + (uint32_t)(it & (kLag - 1)) * (QPT * T * 16);
-            // ------------------------------------------------ loads
-            uint32_t nbar = kbar + 8, npar = kpar, landed = 1;
+        // ---- one kick step: staged row r0 + it -> wake kick + RF kick -> window -> drifted row d
+        // (output row it - NT + 1 once the window is full).  POST: d is a real output row whose edge
+        // values the neighbour warps need.  MORE: another kick follows, its row has to have landed.
+        auto kick_step = [&](const int it, const uint32_t fa, const bool POST, const bool MORE) {
+            // probes whose answers are needed at the end of the step
+            uint32_t nbar = kbar + 8, npar = kpar;
             const bool wrap = nbar == full_end;  // the next row sits in slot 0
             if (wrap) { nbar = full_b; npar ^= 1; }
-            float4 w1, w2;
-            kick_in<QPT, RR> kin;
-            int2 fnext = f;
-            if (KICK) {
-                landed = mbar_test(MORE ? nbar : kbar, MORE ? npar : kpar);
-                w1 = lds128(tp);
-                w2 = lds128(tp + 16);
-                kin.load(aload + (uint32_t)((f.x - RR) * 4));  // f.x - RR: f1 + f2 rounded down to a multiple of 4
-                fnext = lds64i(tp + 48 + 32);                  // next row's entry, a row ahead of its use
-            }
-            float4 dp[QPT];
-            if (STEN) {
-#pragma unroll
-                for (int j = 0; j < QPT; j++) dp[j] = lds128(fa + j * fifo_j);
-            }
-            // ------------------------------------------------ stencil step, part 1: neighbours inside the warp
-            // quad j of lane l sits between quad j of lanes l-1 and l+1; lane 0's left neighbour is lane
-            // 31's quad j-1, lane 31's right one lane 0's quad j+1
-            float Lz[QPT], Lw[QPT], Rx[QPT], Ry[QPT];
-            float ps = 0.0f;
-            if (STEN) {
-#pragma unroll
-                for (int j = 0; j < QPT; j++) {
-                    const float sz = (j > 0 && lane == 31) ? dp[j - 1].z : dp[j].z;
-                    const float sw = (j > 0 && lane == 31) ? dp[j - 1].w : dp[j].w;
-                    const float sx = (j + 1 < QPT && lane == 0) ? dp[j + 1].x : dp[j].x;
-                    const float sy = (j + 1 < QPT && lane == 0) ? dp[j + 1].y : dp[j].y;
-                    Lz[j] = __shfl_sync(0xffffffffu, sz, lane_up);
-                    Lw[j] = __shfl_sync(0xffffffffu, sw, lane_up);
-                    Rx[j] = __shfl_sync(0xffffffffu, sx, lane_dn);
-                    Ry[j] = __shfl_sync(0xffffffffu, sy, lane_dn);
-                }
-                // the row sums of the row before: first level of the butterfly (QPT = 2: the two segments'
-                // sums are transposed into the two half-warps, same tree per segment as with one quad)
-                if (QPT == 2) {
-                    const bool upper = (lane & 16) != 0;
-                    const float send = upper ? pprev[0] : pprev[QPT - 1];
-                    const float keep = upper ? pprev[QPT - 1] : pprev[0];
-                    ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                } else {
-                    ps = pprev[0];
-                    ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 16));
-                }
-            }
-            // ------------------------------------------------ kick and drift
-            if (KICK) {
-                float4 kq[QPT];
+            const uint32_t landed = mbar_test(MORE ? nbar : kbar, MORE ? npar : kpar);
+            const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
+            float4 kq[QPT];
 #if IVS_PROBE_NOKICK  // timing probe (wrong results): the staged quad passes through unkicked
 #pragma unroll
-                for (int j = 0; j < QPT; j++) {
-                    kq[j] = kin.B[j];
-                    kq[j].x += 1e-30f * (w1.x + w2.x + kin.A[j].x + kin.C[j].x + kin.D[j].x);
-                }
+            for (int j = 0; j < QPT; j++) {
+                kq[j] = lds128(aload + j * 512);
+                kq[j].x += 1e-30f * (w1.x + w2.x + (float)f.x);
+            }
 #else
-                kick_quads<FMA, QPT, RR, EDGE>(kin, y0 + f.y, n, near_edge, w1, w2, kq);
+            kick_quads<FMA, QPT>(aload, f.x, y0 + f.y, n, near_edge, w1, w2, kq);
 #endif
-                if (STEN) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
+            tp += 48;
+            f = lds64i(tp + 32);  // next row's entry, a row ahead of its use
+            aload += wrap ? ring_back : pitchB;  // ring_back = pitchB - K * pitchB: back to slot 0
 #pragma unroll
-                for (int j = 0; j < QPT; j++) {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
+            for (int j = 0; j < QPT; j++) {  // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
 #define IVS_DRIFT_COL(c, m)                                                                           \
-                    d[j].m = madd<FMA>(kq[j].m, dw[j][c][NT - 1], P[j][NT - 2].m);                    \
-                    _Pragma("unroll") for (int t = NT - 2; t > 0; t--) P[j][t].m = madd<FMA>(kq[j].m, dw[j][c][t], P[j][t - 1].m); \
-                    P[j][0].m = __fmul_rn(kq[j].m, dw[j][c][0]);
-                    IVS_DRIFT_COL(0, x)
-                    IVS_DRIFT_COL(1, y)
-                    IVS_DRIFT_COL(2, z)
-                    IVS_DRIFT_COL(3, w)
+                d[j].m = madd<FMA>(kq[j].m, dw[j][c][NT - 1], P[j][NT - 2].m);                        \
+                _Pragma("unroll") for (int t = NT - 2; t > 0; t--) P[j][t].m = madd<FMA>(kq[j].m, dw[j][c][t], P[j][t - 1].m); \
+                P[j][0].m = __fmul_rn(kq[j].m, dw[j][c][0]);
+                IVS_DRIFT_COL(0, x)
+                IVS_DRIFT_COL(1, y)
+                IVS_DRIFT_COL(2, z)
+                IVS_DRIFT_COL(3, w)
 #undef IVS_DRIFT_COL
-                }
-            } else if (STEN) {
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
+                // parked in this thread's FIFO entry until its stencil step kLag iterations later
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(fa + j * fifo_j), "f"(d[j].x), "f"(d[j].y), "f"(d[j].z), "f"(d[j].w) : "memory");
             }
-            // ------------------------------------------------ stencil step, part 2
-            float o[QPT][4];
-            if (STEN) {
-                if (edge_l) { Lz[0] = m.x; Lw[0] = m.y; }
-                if (edge_r) { Rx[QPT - 1] = m.x; Ry[QPT - 1] = m.y; }
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
-#if IVS_PROBE_NOFP  // timing probe (wrong results): no stencil
-#pragma unroll
-                for (int j = 0; j < QPT; j++) {
-                    o[j][0] = dp[j].x + 1e-30f * Lz[j]; o[j][1] = dp[j].y + 1e-30f * Lw[j];
-                    o[j][2] = dp[j].z + 1e-30f * Rx[j]; o[j][3] = dp[j].w + 1e-30f * Ry[j];
-                }
-#else
-                // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
-#define IVS_FP_COL(j, c)                                                 \
-                {                                                        \
-                    float v = __fmul_rn(in[c], w5[j][c][0]);             \
-                    v = madd<FMA>(in[1 + c], w5[j][c][1], v);            \
-                    v = madd<FMA>(in[2 + c], w5[j][c][2], v);            \
-                    v = madd<FMA>(in[3 + c], w5[j][c][3], v);            \
-                    v = madd<FMA>(in[4 + c], w5[j][c][4], v);            \
-                    o[j][c] = v;                                         \
-                }
-#pragma unroll
-                for (int j = 0; j < QPT; j++) {
-                    const float in[8] = {Lz[j], Lw[j], dp[j].x, dp[j].y, dp[j].z, dp[j].w, Rx[j], Ry[j]};
-                    IVS_FP_COL(j, 0)
-                    IVS_FP_COL(j, 1)
-                    IVS_FP_COL(j, 2)
-                    IVS_FP_COL(j, 3)
-                }
-#undef IVS_FP_COL
-#endif
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
-#pragma unroll
-                for (int j = 0; j < QPT; j++) {
-                    float p = __fmul_rn(o[j][0], ws4[j].x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
-                    p = __fadd_rn(p, __fmul_rn(o[j][1], ws4[j].y));
-                    p = __fadd_rn(p, __fmul_rn(o[j][2], ws4[j].z));
-                    p = __fadd_rn(p, __fmul_rn(o[j][3], ws4[j].w));
-                    pprev[j] = p;
-                }
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
-            }
-            // ------------------------------------------------ stores
-            if (STEN) {
-#pragma unroll
-                for (int j = 0; j < QPT; j++) gout[j * 32] = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
-                gout += gstride;
-            }
-            if (KICK) {
-                // parked in this thread's FIFO entries until the stencil step kLag iterations later
-#pragma unroll
-                for (int j = 0; j < QPT; j++) sts128(fa + j * fifo_j, d[j]);
-                const uint32_t prow_out = (uint32_t)(it - NT + 1);
-                const uint32_t ms = (prow_out & mail_mask) * 16;
+            if (POST) {
+                const uint32_t orow = (uint32_t)(it - NT + 1);
+                const uint32_t ms = (orow & (kMailSlots - 1)) * 16;
                 // lane 0 posts (x, y) of its first quad for the left neighbour, lane 31 (z, w) of its last for the right one
                 const bool l0 = lane == 0;
                 sts128_volatile_if(post_me + ms,
-                                   make_float4(l0 ? d[0].x : d[QPT - 1].z, l0 ? d[0].y : d[QPT - 1].w, __uint_as_float(prow_out + 1), 0.0f),
-                                   POST && (l0 || lane == 31));
-                // the staged row is in registers everywhere (its drift has been computed): hand it back
-                mbar_arrive_if(kbar + eoff, lane == 0);
-                tp += 48;
-                f = fnext;
-                aload += wrap ? ring_back : pitchB;  // ring_back = pitchB - K * pitchB: back to slot 0
-                kbar = nbar;
-                kpar = npar;
+                                   make_float4(l0 ? d[0].x : d[QPT - 1].z, l0 ? d[0].y : d[QPT - 1].w, __uint_as_float(orow + 1), 0.0f),
+                                   l0 || lane == 31);
             }
-            if (STEN) {
-                if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps));
-                redp += NSEG * 4;
+            // the staged row is in registers everywhere (its drift has been computed): hand it back
+            mbar_arrive_if(kbar + eoff, lane == 0);
+            kbar = nbar;
+            kpar = npar;
+            if (it >= pwin || !landed) {  // one rarely taken region for both slow paths
+                if (it >= pwin) {  // this warp's turn to stage a row (one in NW iterations)
+                    duty_probe();
+                    duty_issue();
+                }
+                if (!landed) wait_row(nbar, npar, it);
             }
-            return landed;
+        };
+        // ---- one stencil step on drifted output row `orow` (out of the FIFO): neighbours,
+        // Fokker-Planck, store, partial row sum; the warp sum of the row before is reduced on the side
+        auto fp_step = [&](const int it, const uint32_t fa, const uint32_t orow) {
+            float4 dp[QPT];
+#pragma unroll
+            for (int j = 0; j < QPT; j++) dp[j] = lds128(fa + j * fifo_j);
+            float4 m = make_float4(0, 0, 0, 0);
+            const uint32_t pa = peek + (orow & (kMailSlots - 1)) * 16;
+            if (edge) m = lds128_volatile(pa);
+            // neighbours inside the warp: quad j of lane l sits between quad j of lanes l-1 and l+1;
+            // lane 0's left neighbour is lane 31's quad j-1, lane 31's right one lane 0's quad j+1
+            float Lz[QPT], Lw[QPT], Rx[QPT], Ry[QPT];
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                const float sz = (j > 0 && lane == 31) ? dp[j - 1].z : dp[j].z;
+                const float sw = (j > 0 && lane == 31) ? dp[j - 1].w : dp[j].w;
+                const float sx = (j + 1 < QPT && lane == 0) ? dp[j + 1].x : dp[j].x;
+                const float sy = (j + 1 < QPT && lane == 0) ? dp[j + 1].y : dp[j].y;
+                Lz[j] = __shfl_sync(0xffffffffu, sz, lane_up);
+                Lw[j] = __shfl_sync(0xffffffffu, sw, lane_up);
+                Rx[j] = __shfl_sync(0xffffffffu, sx, lane_dn);
+                Ry[j] = __shfl_sync(0xffffffffu, sy, lane_dn);
+            }
+            // the row sums of the row before: first level of the butterfly (QPT = 2: the two segments'
+            // sums are transposed into the two half-warps, same tree per segment as with one quad)
+            float ps;
+            if (QPT == 2) {
+                const bool upper = (lane & 16) != 0;
+                const float send = upper ? pprev[0] : pprev[QPT - 1];
+                const float keep = upper ? pprev[QPT - 1] : pprev[0];
+                ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+            } else {
+                ps = pprev[0];
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 16));
+            }
+            if (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1)) {
+                // the neighbour is more than a row behind: poll (warp-uniformly, so that lane 0
+                // keeps serving the staging duty)
+                uint32_t tries = 0;
+                do {
+                    if (it >= pwin) {
+                        duty_probe();
+                        duty_issue();
+                    }
+                    if (edge) m = lds128_volatile(pa);
+#if IVS_WARP_CLOCKS
+                    n_mpoll++;
+#endif
+                    if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
+                } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(m.z) == orow + 1));
+            }
+            if (edge_l) { Lz[0] = m.x; Lw[0] = m.y; }
+            if (edge_r) { Rx[QPT - 1] = m.x; Ry[QPT - 1] = m.y; }
+            // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
+            float o[QPT][4];
+#if IVS_PROBE_NOFP  // timing probe (wrong results): no stencil, no neighbours
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                o[j][0] = dp[j].x + Lz[j]; o[j][1] = dp[j].y; o[j][2] = dp[j].z; o[j][3] = dp[j].w + Ry[j];
+                gout[j * 32] = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
+            }
+            ps = warp_sum_probe(ps);
+#else
+#define IVS_FP_COL(j, c)                                                 \
+            {                                                            \
+                float v = __fmul_rn(in[c], w5[j][c][0]);                 \
+                v = madd<FMA>(in[1 + c], w5[j][c][1], v);                \
+                v = madd<FMA>(in[2 + c], w5[j][c][2], v);                \
+                v = madd<FMA>(in[3 + c], w5[j][c][3], v);                \
+                v = madd<FMA>(in[4 + c], w5[j][c][4], v);                \
+                o[j][c] = v;                                             \
+            }
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                const float in[8] = {Lz[j], Lw[j], dp[j].x, dp[j].y, dp[j].z, dp[j].w, Rx[j], Ry[j]};
+                IVS_FP_COL(j, 0)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
+                IVS_FP_COL(j, 1)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
+                IVS_FP_COL(j, 2)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
+                IVS_FP_COL(j, 3)
+                if (j == 0) ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
+                gout[j * 32] = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
+            }
+#undef IVS_FP_COL
+#endif
+            gout += gstride;
+            if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
+            redp += NSEG * 4;
+#pragma unroll
+            for (int j = 0; j < QPT; j++) {
+                float p = __fmul_rn(o[j][0], ws4[j].x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
+                p = __fadd_rn(p, __fmul_rn(o[j][1], ws4[j].y));
+                p = __fadd_rn(p, __fmul_rn(o[j][2], ws4[j].z));
+                p = __fadd_rn(p, __fmul_rn(o[j][3], ws4[j].w));
+                pprev[j] = p;
+            }
         };
 
         // Iteration `it` kicks row r0 + it; from it = NT-1 on a drifted output row (it - NT + 1) comes
         // out and is parked in FIFO slot it mod kLag; the stencil handles the row parked kLag
-        // iterations before (output row it - NT + 1 - kLag), so a warp only waits for a neighbour that
-        // is more than kLag - 1 rows late.
-        const int fp_from = NT - 1 + kLag, it_end = (int)nkicks + kLag;
+        // iterations before (output row it - NT + 1 - kLag, read from the same slot before this
+        // iteration's kick overwrites it), so a warp only waits for a neighbour that is more than
+        // kLag - 1 rows late.
+        auto fifo_at = [&](int i) { return fifo_t + (uint32_t)(i & (kLag - 1)) * (QPT * T * 16); };
         int it = 0;
-        float4 m_cur = make_float4(0, 0, 0, 0);  // mailbox entry of the row the next stencil step handles
-        // Steady state (a stencil step and a kick per iteration), instantiated per alignment RR of the
-        // kick's first tap and for warps that do / do not come near the edge of a row: an instance runs
-        // while the rows keep its alignment (the tap positions move by a cell every few hundred rows), so
-        // the instructions a warp fetches are one contiguous loop body.  The mailbox entry the NEXT stencil
-        // step needs is requested at the top and looked at at the end, where the other slow paths sit.
-        auto steady = [&](auto rr_tag, auto edge_tag) {
-            constexpr int RR = decltype(rr_tag)::value;
-            do {
-                const uint32_t orow = (uint32_t)(it - fp_from);
-                float4 m_nx = make_float4(0, 0, 0, 0);
-                if (edge) m_nx = lds128_volatile(peek + ((orow + 1) & mail_mask) * 16);
-                const uint32_t landed = iteration(rr_tag, edge_tag, std::true_type{}, std::true_type{}, it, orow, m_cur, true, true);
-                const bool ok = __all_sync(0xffffffffu, !edge || __float_as_uint(m_nx.z) == orow + 2);
-                if (!ok || it >= pwin || !landed) {  // one rarely taken region for all slow paths
-                    kick_tail(it, landed);
-                    if (!ok) m_nx = mail_wait(it, orow + 1);
-                }
-                m_cur = m_nx;
-                it++;
-            } while (it + 1 < (int)nkicks && (f.x & 3) == RR);  // f: the next row's entry (read ahead)
-        };
-        bool any_edge = false;
-#pragma unroll
-        for (int j = 0; j < QPT; j++) any_edge = any_edge || near_edge[j];
-        while (it < it_end) {
-            const int rr = f.x & 3;  // warp-uniform
-            if (it >= fp_from && it + 1 < (int)nkicks) {
-                if (any_edge) {
-                    switch (rr) {
-                    case 0: steady(std::integral_constant<int, 0>{}, std::true_type{}); break;
-                    case 1: steady(std::integral_constant<int, 1>{}, std::true_type{}); break;
-                    case 2: steady(std::integral_constant<int, 2>{}, std::true_type{}); break;
-                    default: steady(std::integral_constant<int, 3>{}, std::true_type{}); break;
-                    }
-                } else {
-                    switch (rr) {
-                    case 0: steady(std::integral_constant<int, 0>{}, std::false_type{}); break;
-                    case 1: steady(std::integral_constant<int, 1>{}, std::false_type{}); break;
-                    case 2: steady(std::integral_constant<int, 2>{}, std::false_type{}); break;
-                    default: steady(std::integral_constant<int, 3>{}, std::false_type{}); break;
-                    }
-                }
-                continue;
-            }
-            // filling (no stencil step yet) and draining (no kick any more): one iteration at a time
-            if (it < (int)nkicks) {
-                const bool post = it + 1 >= NT, more = it + 1 < (int)nkicks;
-                uint32_t landed;
-#define IVS_FILL(RRV)                                                                                                   \
-                if (it >= fp_from)                                                                                      \
-                    landed = iteration(std::integral_constant<int, RRV>{}, std::true_type{}, std::true_type{}, std::true_type{}, it, \
-                                       (uint32_t)(it - fp_from), m_cur, post, more);                                    \
-                else                                                                                                    \
-                    landed = iteration(std::integral_constant<int, RRV>{}, std::true_type{}, std::true_type{}, std::false_type{}, it, \
-                                       0u, m_cur, post, more);
-                switch (rr) {
-                case 0: IVS_FILL(0) break;
-                case 1: IVS_FILL(1) break;
-                case 2: IVS_FILL(2) break;
-                default: IVS_FILL(3) break;
-                }
-#undef IVS_FILL
-                kick_tail(it, landed);
-            } else {
-                iteration(std::integral_constant<int, 0>{}, std::true_type{}, std::false_type{}, std::true_type{}, it,
-                          (uint32_t)(it - fp_from), m_cur, false, false);
-            }
-            if (it + 1 >= fp_from && it + 1 < it_end) m_cur = mail_wait(it, (uint32_t)(it + 1 - fp_from));
-            it++;
+        for (; it < NT - 1 + kLag; it++) {  // fill the drift sums and the FIFO
+            if (it < (int)nkicks) kick_step(it, fifo_at(it), it + 1 >= NT, it + 1 < (int)nkicks);
+        }
+        for (; it + 1 < (int)nkicks; it++) {  // steady state
+            const uint32_t fa = fifo_at(it);
+            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
+            kick_step(it, fa, true, true);
+        }
+        for (; it < (int)nkicks + kLag; it++) {  // the last kick and the rows still parked
+            const uint32_t fa = fifo_at(it);
+            fp_step(it, fa, (uint32_t)(it - (NT - 1 + kLag)));
+            if (it < (int)nkicks) kick_step(it, fa, true, false);
         }
 #if IVS_WARP_CLOCKS
         if (lane == 0) {
