@@ -33,94 +33,12 @@
 #include <type_traits>
 #include <vector>
 
-#include "ivs_internal.h"
-#include "ivs_sim_struct.h"
+#include "ivs_fused_common.cuh"
 
 namespace {
 
 constexpr int kPad = 16;   // zero columns on each side of a staged row (floats)
 constexpr int kChunk = 8;  // outputs per lane and chunk in the row passes
-
-struct fused_args {
-    const float* in;
-    float* out;
-    const float* rho_in;
-    float* rho_out;
-    float* wake_out;
-    const double* wakefn;
-    const float* wakescaling;
-    const int* rf_first;
-    const float4* rf_w;
-    const int* dr_first;
-    const float4* dr_w;
-    const int* fp_base;
-    const float4* fp_w;
-    const float* fp_w5;
-    const float* ws;
-    int* status;     // [0] ordinal of the first step that left the staged pad (kStatusClean: none), [1] CTA tickets
-    int* host_flag;  // host-mapped copy of "status[0] is set" (read by the host without a sync)
-    uint32_t n, it, hl, hr, pitch;
-    int has_wake;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-// TMA engine, 1-D bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
-    } while (!ok);
-}
-
-
-// ---- step bookkeeping shared by the three fused kernels.  status[0] = ordinal (counted from the
-// host's last reset of the two words) of the first step in which a wake kick left the staged pad,
-// status[1] = CTA ticket counter (ticket / CTAs per step = this step's ordinal).  Once status[0] is
-// set every later step exits without writing, so the input of the offending step stays intact
-// in the ping-pong buffer and the host can redo it through the kernel sequence (ivs_step.cu).
-constexpr int kStatusClean = 0x7fffffff;
-__device__ __forceinline__ void step_ctl_begin(const fused_args& g, int* ctl) {
-    ctl[0] = *reinterpret_cast<volatile int*>(g.status);
-    ctl[1] = (int)atomicAdd(reinterpret_cast<unsigned int*>(g.status) + 1, 1u);
-}
-__device__ __forceinline__ void step_ctl_overflow(const fused_args& g, const int* ctl) {
-    const unsigned int ord = (unsigned int)ctl[1] / (gridDim.x * gridDim.y);
-    atomicMin(g.status, (int)ord);
-    *reinterpret_cast<volatile int*>(g.host_flag) = 1;
-    __threadfence_system();
-}
-
-template <bool FMA>
-__device__ __forceinline__ float tap4(float a0, float a1, float a2, float a3, const float4 w) {
-    // value = 0; value += in*w, four times in the reference's order.  The first add (0 + a*w)
-    // only decides the sign of a zero result; it is folded away.
-    float v = __fmul_rn(a0, w.x);
-    v = madd<FMA>(a1, w.y, v);
-    v = madd<FMA>(a2, w.z, v);
-    v = madd<FMA>(a3, w.w, v);
-    return v;
-}
 
 // one 4-tap pass along a staged row, in place, by one warp.  `row` points at column 0; columns
 // [-kPad, n+kPad) are addressable and the pads hold zeros.
@@ -596,74 +514,14 @@ __device__ unsigned long long g_wstat[4][32];  // [loop-end clock, mailbox polls
 #ifndef IVS_PROBE_NOFP
 #define IVS_PROBE_NOFP 0
 #endif
+#ifndef IVS_PROBE_FIXRR
+#define IVS_PROBE_FIXRR 0  // timing probe (wrong results): one alignment variant of the kick for every row
+#endif
+#ifndef IVS_PROBE_NT6
+#define IVS_PROBE_NT6 0    // timing probe (right results): every warp runs the 6-row drift window
+#endif
 constexpr int kLag = IVS_LAG;        // drifted rows wait this many iterations (in a per-thread FIFO in shared memory)
                                // for their Fokker-Planck step: the slack between neighbouring warps
-
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-struct stream_args {
-    fused_args f;
-    uint32_t strip;      // rows per strip
-    uint32_t kslots;     // ring slots
-    uint32_t max_strip;  // capacity of the partial-sum table (rows)
-    uint32_t max_rin;    // capacity of the per-row tap tables (input rows)
-    uint32_t wwin_len;   // doubles in the staged wake-function window
-};
-
-// shared-memory accessors on 32-bit shared addresses (no 64-bit generic pointer arithmetic)
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float4 lds128_volatile(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "r"(addr)
-                 : "memory");
-    return v;
-}
-__device__ __forceinline__ int2 lds64i(uint32_t addr) {
-    int2 v;
-    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-// non-blocking probe of an mbarrier phase
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t phase) {
-    uint32_t ok;
-    asm volatile(
-        "{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(ok)
-        : "r"(bar), "r"(phase)
-        : "memory");
-    return ok;
-}
-__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t phase) {
-    uint32_t ok;
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(ok)
-        : "r"(bar), "r"(phase)
-        : "memory");
-    return ok;
-}
-__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// the same as predicated instructions (no branch around a one-lane operation)
-__device__ __forceinline__ void mbar_arrive_if(uint32_t bar, bool on) {
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p mbarrier.arrive.shared::cta.b64 _, [%0]; }" ::"r"(bar),
-                 "r"((uint32_t)on)
-                 : "memory");
-}
-__device__ __forceinline__ void sts128_volatile_if(uint32_t addr, const float4 v, bool on) {
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(addr),
-                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)on)
-                 : "memory");
-}
 
 // wake kick then RF kick of one quad of columns (y0 .. y0+3) of a staged row, in registers.
 //   k1[m] = sum_t in[m + f1 + t] w1[t]         wake kick (src/SM/KickMap.cpp:243-266), 0 outside the grid
@@ -725,10 +583,6 @@ __device__ __forceinline__ float warp_sum_probe(float v) {
 }
 #endif
 
-// staged wake-function window: one pad double after every 8 keeps lanes that are 8 entries apart
-// on different banks
-__device__ __forceinline__ uint32_t wwin_pos(uint32_t t) { return t + (t >> 3); }
-
 // wake kick + RF kick of the QPT quads a thread owns in one staged row (quad j sits 32 quads =
 // 512 bytes after quad j-1).  The alignment of the first tap is the same for all of them, so one
 // warp-uniform switch serves QPT independent chains of arithmetic.
@@ -749,12 +603,16 @@ __device__ __forceinline__ void kick_quads(uint32_t row_q, int fsum, int m0, uin
 #define IVS_KICK_CASE(RR)                                                                                       \
     _Pragma("unroll") for (int j = 0; j < QPT; j++)                                                             \
         kq[j] = kick_quad_rr<FMA, RR>(p + j * 512, A[j], B[j], C[j], m0 + j * 128, n, near_edge[j], w1, w2);
+#if IVS_PROBE_FIXRR
+    IVS_KICK_CASE(1)
+#else
     switch (fsum - a) {
     case 0: IVS_KICK_CASE(0) break;
     case 1: IVS_KICK_CASE(1) break;
     case 2: IVS_KICK_CASE(2) break;
     default: IVS_KICK_CASE(3) break;
     }
+#endif
 #undef IVS_KICK_CASE
 }
 
@@ -1338,9 +1196,13 @@ __global__ void __launch_bounds__(512 / QPT, 1) stream_step_kernel(const stream_
             }
         }
     };
+#if IVS_PROBE_NT6
+    run(std::integral_constant<int, 6>{});
+#else
     if (spread == 0) run(std::integral_constant<int, 4>{});
     else if (spread == 1) run(std::integral_constant<int, 5>{});
     else run(std::integral_constant<int, 6>{});
+#endif
 
     // the strip's row sums: one thread per row adds the segments' partials in fixed order
     __syncthreads();
@@ -1441,6 +1303,9 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
     // rows with all-zero drift weights read the window starting at -1: keep that in range
     plan->halo_lo = std::max(plan->halo_lo, 1u);
     plan->halo_hi = std::max(plan->halo_hi, 2u);
+#if IVS_PROBE_NT6
+    plan->halo_hi += 2;  // every warp reads a 6-row window
+#endif
     plan->pad_y = kPad;
     // ---- streaming kernel (default for grid sizes that are multiples of 256, up to 2048)
     plan->stream = false;
@@ -1541,6 +1406,26 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             IVS_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
         }
     }
+    // ---- column-block kernel (ivs_stream8.cu): same domain of grid sizes, 8 adjacent columns per lane
+    if ((s->desc.flags & IVS_SIM_STREAM8) && !(s->desc.flags & IVS_SIM_TILED) && n % 256 == 0 && n <= 2048) {
+        size_t keep_smem = plan->smem;
+        uint32_t keep_threads = plan->threads;
+        if (ivs_stream8_plan(ctx, s, plan, dr_first.data())) {
+            if (!plan->fp5) {
+                std::vector<float> fps(fpw);  // out-of-grid taps zeroed, as for the streaming kernel
+                fps[0] = fps[1] = 0.0f;
+                fps[5] = 0.0f;
+                fps[(size_t)(n - 1) * 5 + 3] = fps[(size_t)(n - 1) * 5 + 4] = 0.0f;
+                fps[(size_t)(n - 2) * 5 + 4] = 0.0f;
+                IVS_CUDA(ctx, cudaMalloc(&plan->fp5, (size_t)n * 20));
+                IVS_CUDA(ctx, cudaMemcpy(plan->fp5, fps.data(), (size_t)n * 20, cudaMemcpyHostToDevice));
+            }
+            plan->stream = false;
+        } else {
+            plan->smem = keep_smem;
+            plan->threads = keep_threads;
+        }
+    }
     // tile height: minimise (rounds of CTAs over the machine) x (rows staged per CTA)
     const uint32_t halo = plan->halo_lo + plan->halo_hi;
     const int candidates[3] = {16, 8, 4};
@@ -1565,10 +1450,10 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         const uint64_t cost = rounds * R * std::max<uint32_t>(1, n / th);
         if (cost < best) { best = cost; tx = c; threads = th; smem = sb; }
     }
-    if (plan->stream) { tx = 16; threads = plan->threads; smem = plan->smem; }
+    if (plan->stream || plan->stream8) { tx = 16; threads = plan->threads; smem = plan->smem; }
     if (tx == 0)
         return ivs_fail(ctx, IVS_ERR_UNSUPPORTED, "drift displacement needs more halo rows than fit in shared memory: pass IVS_SIM_UNFUSED");
-    if (!plan->stream) { plan->tx = tx; plan->threads = threads; plan->smem = smem; }
+    if (!plan->stream && !plan->stream8) { plan->tx = tx; plan->threads = threads; plan->smem = smem; }
     plan->launches_per_step = 1;
     auto up = [&](void** dst, const void* src, size_t bytes) -> ivs_status {
         IVS_CUDA(ctx, cudaMalloc(dst, bytes));
@@ -1581,7 +1466,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         (st = up(&plan->fp_base, fp_base.data(), n * 4)) || (st = up(&plan->fp_w, fp_w.data(), n * 16)))
         return st;
     // opt in to the large dynamic shared memory once (not per launch)
-    if (plan->stream) {
+    if (plan->stream || plan->stream8) {
         plan->ready = true;
         return IVS_OK;
     }
@@ -1655,6 +1540,10 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
     a.n = s->n; a.it = s->it; a.hl = plan->halo_lo; a.hr = plan->halo_hi; a.pitch = s->n + 2 * kPad;
     a.has_wake = s->has_wake ? 1 : 0;
     ivs_status st;
+    if (plan->stream8) {
+        st = ivs_stream8_launch(ctx, plan, s, a);
+        goto launched;
+    }
     if (plan->stream) {
         stream_args sa;
         sa.f = a;

@@ -1,0 +1,640 @@
+// ivs_stream8.cu -- the fused simulation step as a streaming kernel of fully independent warps
+// with the kicks' displacement absorbed by the staging copy (sm_100a).
+//
+//   wake potential -> wake kick (y) -> RF kick (y) -> drift (x) -> Fokker-Planck (y) -> X projection
+//   (src/main.cpp:948-1053; maps src/SM/KickMap.cpp:221-266, src/SM/FokkerPlanckMap.cpp:197-211,
+//    projection src/PS/PhaseSpace.cpp:313-321, wake src/PS/ElectricField.cpp:186-253)
+//
+// Same arithmetic per cell, in the same order, as stream_step_kernel / the tile kernels of
+// ivs_fused.cu and the kernel sequence of ivs_maps.cu (bit for bit, tested); what differs is how the
+// data moves.  A CTA owns a strip of consecutive rows x of one member; a warp owns a block of 256
+// adjacent columns y of that strip and streams its part of the rows through a ring of its own:
+//
+//   staging : the two kicks of a row read its cells at  y + f1(x) + f2(x) + 0..6  (first wake tap +
+//             first RF tap).  That whole-cell displacement is applied by the copy into shared memory:
+//             the warp copies the 264 cells from column  256 w + f1 + f2  on with 4-byte cp.async
+//             (LDGSTS.32; taps outside the grid and rows outside the grid are zero-filled by the
+//             copy).  The staged row then sits at a FIXED alignment relative to the lanes' columns,
+//             for every row: one straight-line kick, no variants per tap alignment, no zero pads.
+//             (TMA cannot do this: bulk copies and tensor-map coordinates move multiples of 16 B.)
+//             Even and odd quads of the staged cells are kept in two halves of the slot so that a
+//             lane's 14 cells (8 columns + 3 + 3 taps) are 3 LDS.128 + 1 LDS.64 without bank conflicts.
+//             The ring is private to the warp: cp.async groups + __syncwarp, no mbarrier, no
+//             producer role, no slot hand-back between warps.
+//   kick    : a lane owns 8 ADJACENT columns: 11 wake-kicked values (44 multiply-adds) feed the 8 RF
+//             outputs (32) -- 9.5 per cell against 11 with a quad per lane.
+//   drift   : column-local running sums in registers, NT = 4 + spread taps (ivs_fused.cu).
+//   hand-over: the drifted row is written to a small per-warp row FIFO in shared memory, again split
+//             in even and odd quads.  The stencil stage reads it back kLag rows later in a different
+//             thread mapping -- lane l owns quads l and 32 + l of the block, so the two STG.128 of a
+//             row are fully coalesced -- and takes the neighbouring quads from the same FIFO row
+//             (LDS.128) instead of by shuffles.  Only the two quads beyond the block's ends come from
+//             the neighbour warps: their edge lanes post them in a mailbox (sequence stamp = row).
+//             The lag of kLag rows between posting and reading is the only coupling between warps.
+//   Fokker-Planck, STG.128, Simpson-weighted row sums (same summation tree as everywhere else).
+//
+// The wake potential of the strip's rows is formed by the whole CTA during the set-up exactly as in
+// stream_step_kernel (Toeplitz product in double).
+#include <algorithm>
+#include <cstdio>
+#include <type_traits>
+#include <vector>
+
+#include "ivs_fused_common.cuh"
+
+namespace {
+
+constexpr int kSlots8 = 8;             // staged rows per warp (ring depth)
+constexpr int kLag8 = 4;               // rows between drift and stencil = depth of the row FIFO
+constexpr int kMail8 = 32;             // mailbox depth per warp edge (> 2 kLag8 + 2)
+constexpr uint32_t kSlotB = 1152;      // bytes per slot: even quads at 0 (33 quads), odd quads at kOddB (33 quads)
+constexpr uint32_t kOddB = 576;        // 144 floats: 16 banks away from the even half
+
+template <int DOFF, int SOFF>
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 4;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
+template <int DOFF>
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const float* src, uint32_t bytes) {
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1], 4, %3;" ::"r"(dst), "l"(src), "n"(DOFF), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds32i(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool FMA>
+__global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args sa) {
+    const fused_args& g = sa.f;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ int ctl[2];
+    const uint32_t n = g.n, nq = g.n >> 2, hl = g.hl;
+    const uint32_t H = g.hl + g.hr;
+    const uint32_t T = blockDim.x;             // == n / 8
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+    const uint32_t NSEG = NW * 2;              // segments of 128 columns in a row
+    const uint32_t member = blockIdx.y;
+    const uint32_t xa = blockIdx.x * sa.strip;
+    const uint32_t S = min(sa.strip, n - xa);  // output rows of this strip
+    const uint32_t RIN = S + H;                // input rows the strip depends on
+    const int xs = (int)xa - (int)hl;          // grid row of input row 0
+
+    // shared memory carve-up (every block 16-byte aligned)
+    unsigned char* sp = reinterpret_cast<unsigned char*>(smem);
+    auto carve = [&sp](size_t bytes) {
+        unsigned char* p = sp;
+        sp += (bytes + 15) & ~(size_t)15;
+        return p;
+    };
+    unsigned char* ring = carve((size_t)NW * kSlots8 * kSlotB);                  // [warp][slot]
+    unsigned char* fifo = carve((size_t)NW * kLag8 * kSlotB);                    // [warp][row mod kLag8]
+    double* rho = reinterpret_cast<double*>(carve((size_t)(n + (n >> 5)) * 8));  // last step's profile (skewed)
+    double* wwin = reinterpret_cast<double*>(carve((size_t)sa.wwin_len * 8));    // wake function window
+    double* partial = reinterpret_cast<double*>(carve((size_t)NSEG * sa.max_rin * 8));  // wake partial sums
+    float* red = reinterpret_cast<float*>(carve((size_t)sa.max_strip * NSEG * 4));       // row-sum partials
+    // per input row: wake taps, RF taps, (f1 + f2, f2, -, -)
+    float4* tab = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 48));
+    float4* mail = reinterpret_cast<float4*>(carve((size_t)NW * 2 * kMail8 * 16));  // [warp][side][slot]
+    float4* zeroq = reinterpret_cast<float4*>(carve(16));                           // the quad beyond the grid's ends
+
+    const float* gin = g.in + (size_t)member * n * n;
+
+    if (tid == 0) step_ctl_begin(g, ctl);
+    // ---- per-thread constants, requested early.  Drift stage: columns cb + 8 lane + 0..7
+    const uint32_t cb = warp * 256;
+    const uint32_t ycol = cb + 8 * lane;
+    int dfs[8];
+    float4 dwl[8];
+    {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(g.dr_first + ycol));
+        const int4 b = __ldg(reinterpret_cast<const int4*>(g.dr_first + ycol) + 1);
+        dfs[0] = a.x; dfs[1] = a.y; dfs[2] = a.z; dfs[3] = a.w;
+        dfs[4] = b.x; dfs[5] = b.y; dfs[6] = b.z; dfs[7] = b.w;
+#pragma unroll
+        for (int c = 0; c < 8; c++) dwl[c] = __ldg(&g.dr_w[ycol + c]);
+    }
+    // stencil stage: quads (cb / 4) + 32 j + lane, j = 0, 1
+    float w5[2][4][5];
+    float4 ws4[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t qf = (cb >> 2) + 32 * j + lane;
+        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)qf * 20);
+        float t[20];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float4 v = __ldg(wp + k);
+            t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) w5[j][c][k] = t[c * 5 + k];
+        ws4[j] = __ldg(reinterpret_cast<const float4*>(g.ws) + qf);
+    }
+    // last step's profile and the first batch of the wake-function window are requested in the same
+    // round trip (T = n / 8 threads: 8 profile entries and 10 window entries each).
+    // w[x - x'] is stored at table index x - x' + n - 1; window entry t holds the table entry
+    // xs + t, so row r and x' meet at t = r - x' + n - 1
+    constexpr int NRV = 8, NWV = 10;
+    const int wtop = (int)(2 * n - 1);
+    const uint32_t tcount = n + ((RIN + 63) & ~63u);
+    float rv[NRV];
+    double wv0[NWV];
+    int pre_f2 = -1;
+    float4 pre_w2 = make_float4(0, 0, 0, 0);  // rows outside the grid are zeros
+    if (tid < RIN && (uint32_t)(xs + (int)tid) < n) {
+        pre_f2 = __ldg(&g.rf_first[xs + (int)tid]);
+        pre_w2 = __ldg(&g.rf_w[xs + (int)tid]);
+    }
+    if (g.has_wake) {
+        const float* rin = g.rho_in + (size_t)member * n;
+#pragma unroll
+        for (int k = 0; k < NRV; k++) rv[k] = __ldg(rin + tid + k * T);
+#pragma unroll
+        for (int k = 0; k < NWV; k++)
+            wv0[k] = __ldg(g.wakefn + min(max(xs + (int)(tid + k * T), 0), wtop));  // clamped entries belong to rows outside the grid
+    }
+    __syncthreads();
+    // an earlier step of this run left the supported range of displacements (the host redoes it on
+    // another path and re-enqueues what follows): nothing may be written any more
+    if (ctl[0] != kStatusClean) return;
+
+    // ---- set-up: mailboxes, the zero quad, per-row tables, last step's profile and the wake-function
+    // window in shared memory
+    for (uint32_t i = tid; i < NW * 2 * kMail8; i += T) mail[i] = make_float4(0, 0, 0, 0);  // seq 0 = nothing posted
+    if (tid == 0) zeroq[0] = make_float4(0, 0, 0, 0);
+    if (tid < RIN) {
+        tab[3 * tid + 1] = pre_w2;
+        tab[3 * tid + 2] = make_float4(0.0f, __int_as_float(pre_f2), 0.0f, 0.0f);
+    }
+    for (uint32_t r = tid + T; r < RIN; r += T) {  // small grids: strips longer than the block
+        const int x = xs + (int)r;
+        const bool valid = (uint32_t)x < n;
+        const int f2 = valid ? __ldg(&g.rf_first[x]) : -1;
+        tab[3 * r + 1] = valid ? __ldg(&g.rf_w[x]) : make_float4(0, 0, 0, 0);
+        tab[3 * r + 2] = make_float4(0.0f, __int_as_float(f2), 0.0f, 0.0f);
+    }
+    if (g.has_wake) {
+#pragma unroll
+        for (int k = 0; k < NRV; k++) {
+            const uint32_t i = tid + k * T;
+            rho[i + (i >> 5)] = (double)rv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < NWV; k++) {
+            const uint32_t t = tid + k * T;
+            if (t < tcount) wwin[wwin_pos(t)] = wv0[k];
+        }
+        for (uint32_t t0 = tid + NWV * T; t0 < tcount; t0 += NWV * T) {  // small grids: the rest of the window
+            double wv[NWV];
+#pragma unroll
+            for (int k = 0; k < NWV; k++)
+                wv[k] = __ldg(g.wakefn + min(max(xs + (int)(t0 + k * T), 0), wtop));
+#pragma unroll
+            for (int k = 0; k < NWV; k++) {
+                const uint32_t t = t0 + k * T;
+                if (t < tcount) wwin[wwin_pos(t)] = wv[k];
+            }
+        }
+    }
+    __syncthreads();
+    if (g.has_wake) {
+        // W[x] = scaling * sum_x' rho[x'] w[x-x']  (src/PS/ElectricField.cpp:186-253 as a Toeplitz
+        // product).  Segment s sums x' in [128 s, 128 s + 128); a lane owns 8 consecutive rows and 32
+        // consecutive x', so the 8 wake-function values it needs slide through registers.
+        const uint32_t rbk = lane & 7, sub = lane >> 3;
+#pragma unroll 1
+        for (uint32_t seg = warp * 2; seg < (warp + 1) * 2; seg++) {
+            const uint32_t xb = seg * 128 + sub * 32;
+            const double* rp = rho + xb + (xb >> 5);
+            for (uint32_t pass = 0; pass * 64 < RIN; pass++) {  // warp-uniform trip count
+                const uint32_t r0 = pass * 64 + rbk * 8;
+                const uint32_t t0 = r0 + n - 1 - xb;
+                double wv[8], acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    wv[j] = wwin[wwin_pos(t0 + j)];
+                    acc[j] = 0.0;
+                }
+#pragma unroll 8
+                for (uint32_t k = 0; k < 32; k++) {
+                    const double rh = rp[k];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[j] = __fma_rn(rh, wv[j], acc[j]);
+#pragma unroll
+                    for (int j = 7; j > 0; j--) wv[j] = wv[j - 1];
+                    wv[0] = wwin[wwin_pos(max((int)(t0 - k) - 1, 0))];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+                    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+                }
+                if (sub == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (r0 + j < RIN) partial[(size_t)seg * sa.max_rin + r0 + j] = acc[j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const float scal = g.has_wake ? g.wakescaling[member] : 0.0f;
+        for (uint32_t r = tid; r < RIN; r += T) {
+            const int x = xs + (int)r;
+            const bool valid = (uint32_t)x < n;
+            // no wake map: the identity as a 4-tap row (0, 1, 0, 0) at first = -1
+            ivs_taps t;
+            t.first = -1;
+            t.w[0] = 0.0f; t.w[1] = 1.0f; t.w[2] = 0.0f; t.w[3] = 0.0f;
+            if (valid && g.has_wake) {
+                double acc = 0.0;
+                for (uint32_t k = 0; k < NSEG; k++) acc += partial[(size_t)k * sa.max_rin + r];
+                const float wk = __fmul_rn(scal, (float)acc);  // src/PS/ElectricField.cpp:236-241
+                t = ivs_kick_taps(wk, n, g.it);
+                if (t.first < -16 || t.first > 8) {
+                    // beyond the range the fused kernels agree on: record the step (the host redoes it
+                    // through the kernel sequence, which has no such limit) and keep the addresses in range
+                    step_ctl_overflow(g, ctl);
+                    t.first = -1;
+                    t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.0f;
+                }
+                if (r >= hl && r < hl + S) g.wake_out[(size_t)member * n + x] = wk;
+            }
+            const int f2 = __float_as_int(tab[3 * r + 2].y);
+            tab[3 * r] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+            tab[3 * r + 2].x = __int_as_float(t.first + f2);
+        }
+    }
+    __syncthreads();  // tables and mailboxes visible to everybody
+
+    // =============================== the row loop ==============================================
+    int wfmin = 0x7fffffff, wfmax = -0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        wfmin = min(wfmin, dfs[c]);
+        wfmax = max(wfmax, dfs[c]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wfmin = min(wfmin, __shfl_xor_sync(0xffffffffu, wfmin, o));
+        wfmax = max(wfmax, __shfl_xor_sync(0xffffffffu, wfmax, o));
+    }
+    const int spread = wfmax - wfmin;  // <= 2 (checked when the plan was made)
+
+    const uint32_t tab_b = smem_u32(tab);
+    const uint32_t ring_w = smem_u32(ring) + warp * (kSlots8 * kSlotB);
+    const uint32_t fifo_w = smem_u32(fifo) + warp * (kLag8 * kSlotB);
+    const uint32_t mail_b = smem_u32(mail);
+    // mailboxes: lane 0 posts (x, y) of the block's first quad for the left neighbour, lane 31 (z, w) of
+    // its last quad for the right neighbour
+    const uint32_t post_me = mail_b + (warp * 2 + (lane == 0 ? 0 : 1)) * kMail8 * 16;
+    const bool edge_l = lane == 0 && warp > 0, edge_r = lane == 31 && warp + 1 < NW;
+    const bool edge = edge_l || edge_r;
+    // the two quads beyond the block's ends: the neighbour's post, or zeros beyond the grid
+    const bool spec_l = lane == 0, spec_r = lane == 31;
+    const uint32_t spec_base = edge_l   ? mail_b + ((warp - 1) * 2 + 1) * kMail8 * 16
+                               : edge_r ? mail_b + ((warp + 1) * 2 + 0) * kMail8 * 16
+                                        : smem_u32(zeroq);
+    const uint32_t spec_mask = edge ? (kMail8 - 1) * 16 : 0;
+    // stencil-stage offsets inside a FIFO row: own quad (j = 0), its left and right neighbours
+    const uint32_t own_off = (lane & 1) ? kOddB + (lane >> 1) * 16 : (lane >> 1) * 16;
+    const int nb_l = (lane & 1) ? -(int)kOddB : (int)kOddB - 16;
+    const int nb_r = (lane & 1) ? 16 - (int)kOddB : (int)kOddB;
+    const bool edge_warp = warp == 0 || warp + 1 == NW;
+    const bool slow_stage = edge_warp || xs < 0 || xs + (int)RIN > (int)n;
+    // staging: this lane's cell of every group of 32 staged cells (see the header comment)
+    const uint32_t st_dst = ((lane >> 2) & 1) * kOddB + ((lane >> 3) * 4 + (lane & 3)) * 4;
+    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + (cb >> 2) + lane;
+
+    auto run = [&](auto nt_tag) {
+        constexpr int NT = decltype(nt_tag)::value;
+        float dw[8][NT];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const float wv[4] = {dwl[c].x, dwl[c].y, dwl[c].z, dwl[c].w};
+            const int off = dfs[c] - wfmin;  // 0 .. NT-4
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                float v = 0.0f;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (t - u >= 0 && t - u <= NT - 4) v = (off == t - u) ? wv[u] : v;
+                dw[c][t] = v;
+            }
+        }
+        // rows r0 .. r0+NT-1 make output row 0; kick number k (k = 0, 1, ...) reads input row r0 + k
+        const uint32_t r0 = (uint32_t)((int)hl + wfmin);
+        const int nkicks = (int)(S + NT - 1);
+
+        // ---- staging of input row r0 + k into slot k mod kSlots8 (one cp.async group per call)
+        auto stage = [&](int k) {
+            if (k < nkicks) {
+                const uint32_t r = r0 + (uint32_t)k;
+                const int fs = lds32i(tab_b + r * 48 + 32);
+                const int x = xs + (int)r;
+                const uint32_t dst = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + st_dst;
+                if (!slow_stage) {
+                    const float* src = gin + ((long long)x * (long long)n + (long long)((int)cb + fs + (int)lane));
+                    cp_async4<0, 0>(dst, src);
+                    cp_async4<64, 128>(dst, src);
+                    cp_async4<128, 256>(dst, src);
+                    cp_async4<192, 384>(dst, src);
+                    cp_async4<256, 512>(dst, src);
+                    cp_async4<320, 640>(dst, src);
+                    cp_async4<384, 768>(dst, src);
+                    cp_async4<448, 896>(dst, src);
+                    if (lane < 8) cp_async4<512, 1024>(dst, src);
+                } else {
+                    // a block at the grid's edge, or a strip with rows outside the grid: cells outside are zeros
+                    const bool rowok = (uint32_t)x < n;
+                    const int col0 = (int)cb + fs + (int)lane;
+                    const float* rowp = gin + (size_t)(rowok ? x : 0) * n;
+#define IVS_STAGE_Z(K2)                                                         \
+    {                                                                           \
+        const int col = col0 + 32 * (K2);                                       \
+        const bool ok = rowok && (uint32_t)col < n;                             \
+        cp_async4_zfill<64 * (K2)>(dst, rowp + (ok ? col : 0), ok ? 4u : 0u);   \
+    }
+                    IVS_STAGE_Z(0) IVS_STAGE_Z(1) IVS_STAGE_Z(2) IVS_STAGE_Z(3)
+                    IVS_STAGE_Z(4) IVS_STAGE_Z(5) IVS_STAGE_Z(6) IVS_STAGE_Z(7)
+                    if (lane < 8) IVS_STAGE_Z(8)
+#undef IVS_STAGE_Z
+                }
+            }
+            cp_async_commit();
+        };
+
+        // drift as running sums: P[c][j] is the output row that has taken j + 1 of its NT taps so far
+        float P[8][NT - 1];
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int t = 0; t < NT - 1; t++) P[c][t] = 0.0f;
+        float pprev[2] = {0.0f, 0.0f};  // this lane's part of a finished row's sums (reduced an iteration later)
+        // where the row sums reduced next go: lane 0 holds segment 2 warp's, lane 16 the next one's
+        uint32_t redp = smem_u32(red) + (warp * 2 + (lane >= 16 ? 1 : 0)) * 4 - NSEG * 4;
+        const bool red_lane = (lane & 15) == 0;
+        const size_t gstride = (size_t)nq;
+
+        // ---- one kick step: staged row r0 + it -> wake kick + RF kick -> drift sums -> drifted row
+        // (output row it - NT + 1 once the sums are full) -> FIFO row `frow`, edges posted
+        auto kick_step = [&](const int it, const uint32_t frow, const bool POST) {
+            const uint32_t tp = tab_b + (r0 + (uint32_t)it) * 48;
+            const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
+            const uint32_t s = ring_w + ((uint32_t)it & (kSlots8 - 1)) * kSlotB + lane * 16;
+            float in[14];
+            {
+                const float4 a0 = lds128(s), b0 = lds128(s + kOddB), a1 = lds128(s + 16);
+                const float2 b1 = lds64f(s + kOddB + 16);
+                in[0] = a0.x; in[1] = a0.y; in[2] = a0.z; in[3] = a0.w;
+                in[4] = b0.x; in[5] = b0.y; in[6] = b0.z; in[7] = b0.w;
+                in[8] = a1.x; in[9] = a1.y; in[10] = a1.z; in[11] = a1.w;
+                in[12] = b1.x; in[13] = b1.y;
+            }
+            // k1[i] = wake-kicked cell ycol + f2 + i (src/SM/KickMap.cpp:243-266), 0 outside the grid
+            float k1[11];
+#pragma unroll
+            for (int i = 0; i < 11; i++) k1[i] = tap4<FMA>(in[i], in[i + 1], in[i + 2], in[i + 3], w1);
+            if (edge_warp) {
+                const int m0 = (int)ycol + lds32i(tp + 36);
+#pragma unroll
+                for (int i = 0; i < 11; i++)
+                    if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
+            }
+            float d[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const float kq = tap4<FMA>(k1[c], k1[c + 1], k1[c + 2], k1[c + 3], w2);  // RF kick, same loop
+                // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
+                d[c] = madd<FMA>(kq, dw[c][NT - 1], P[c][NT - 2]);
+#pragma unroll
+                for (int t = NT - 2; t > 0; t--) P[c][t] = madd<FMA>(kq, dw[c][t], P[c][t - 1]);
+                P[c][0] = __fmul_rn(kq, dw[c][0]);
+            }
+            // parked in the row FIFO until its stencil step kLag8 iterations later
+            sts128(frow + lane * 16, d[0], d[1], d[2], d[3]);
+            sts128(frow + kOddB + lane * 16, d[4], d[5], d[6], d[7]);
+            if (POST) {
+                const uint32_t orow = (uint32_t)(it - NT + 1);
+                const float seq = __uint_as_float(orow + 1);
+                const bool l0 = lane == 0;
+                sts128_volatile_if(post_me + (orow & (kMail8 - 1)) * 16,
+                                   make_float4(l0 ? d[0] : seq, l0 ? d[1] : 0.0f, l0 ? seq : d[6], l0 ? 0.0f : d[7]),
+                                   l0 || lane == 31);
+            }
+        };
+        // ---- one stencil step on drifted output row `orow` (out of FIFO row `frow`): neighbours,
+        // Fokker-Planck, store, partial row sums; the warp sum of the row before is reduced on the side
+        auto fp_step = [&](const uint32_t frow, const uint32_t orow) {
+            const uint32_t fo = frow + own_off;
+            const float4 o0 = lds128(fo), o1 = lds128(fo + 256);
+            const float4 r0q = lds128(fo + nb_r), l1q = lds128(fo + 256 + nb_l);
+            const uint32_t sp_a = spec_base + ((orow * 16) & spec_mask);
+            const uint32_t la = spec_l ? sp_a : fo + nb_l;
+            const uint32_t ra = spec_r ? sp_a : fo + 256 + nb_r;
+            float4 l0q = lds128_volatile(la), r1q = lds128_volatile(ra);
+            const uint32_t want = orow + 1;
+            // the row sums of the row before: first level of the butterfly (the two segments' sums are
+            // transposed into the two half-warps, same tree per segment as everywhere else)
+            float ps;
+            {
+                const bool upper = (lane & 16) != 0;
+                const float send = upper ? pprev[0] : pprev[1];
+                const float keep = upper ? pprev[1] : pprev[0];
+                ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+            }
+            if (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want)) {
+                // the neighbour is more than kLag8 - 1 rows behind: poll
+                uint32_t tries = 0;
+                do {
+                    if (edge_l) l0q = lds128_volatile(la);
+                    if (edge_r) r1q = lds128_volatile(ra);
+                    if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
+                } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want));
+            }
+            // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
+            float o[2][4];
+#define IVS_FP_COL(j, c)                                                 \
+            {                                                            \
+                float v = __fmul_rn(in[c], w5[j][c][0]);                 \
+                v = madd<FMA>(in[1 + c], w5[j][c][1], v);                \
+                v = madd<FMA>(in[2 + c], w5[j][c][2], v);                \
+                v = madd<FMA>(in[3 + c], w5[j][c][3], v);                \
+                v = madd<FMA>(in[4 + c], w5[j][c][4], v);                \
+                o[j][c] = v;                                             \
+            }
+            {
+                const float in[8] = {l0q.z, l0q.w, o0.x, o0.y, o0.z, o0.w, r0q.x, r0q.y};
+                IVS_FP_COL(0, 0)
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
+                IVS_FP_COL(0, 1)
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
+                IVS_FP_COL(0, 2)
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
+                IVS_FP_COL(0, 3)
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
+                gout[0] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+            }
+            {
+                const float in[8] = {l1q.z, l1q.w, o1.x, o1.y, o1.z, o1.w, r1q.x, r1q.y};
+                IVS_FP_COL(1, 0)
+                IVS_FP_COL(1, 1)
+                IVS_FP_COL(1, 2)
+                IVS_FP_COL(1, 3)
+                gout[32] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+            }
+#undef IVS_FP_COL
+            gout += gstride;
+            if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
+            redp += NSEG * 4;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                float p = __fmul_rn(o[j][0], ws4[j].x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
+                p = __fadd_rn(p, __fmul_rn(o[j][1], ws4[j].y));
+                p = __fadd_rn(p, __fmul_rn(o[j][2], ws4[j].z));
+                p = __fadd_rn(p, __fmul_rn(o[j][3], ws4[j].w));
+                pprev[j] = p;
+            }
+        };
+
+        // Iteration `it` kicks row r0 + it; from it = NT-1 on a drifted output row (it - NT + 1) comes
+        // out and is parked in FIFO row it mod kLag8; the stencil handles the row parked kLag8
+        // iterations before (output row it - NT + 1 - kLag8, read from the same FIFO row before this
+        // iteration's kick overwrites it), so a warp only waits for a neighbour that is more than
+        // kLag8 - 1 rows late.
+        auto fifo_at = [&](int i) { return fifo_w + (uint32_t)(i & (kLag8 - 1)) * kSlotB; };
+#pragma unroll 1
+        for (int k = 0; k < kSlots8 - 1; k++) stage(k);
+        const int it_end = nkicks + kLag8;
+#pragma unroll 1
+        for (int it = 0; it < it_end; it++) {
+            const uint32_t fr = fifo_at(it);
+            const bool kick = it < nkicks;
+            if (kick) {
+                cp_async_wait<kSlots8 - 2>();  // row r0 + it has landed (this lane's part of it)
+            }
+            __syncwarp();  // ... and everybody's; the FIFO row written an iteration ago is visible; slot it-1 is free
+            if (kick) stage(it + kSlots8 - 1);
+            if (it >= NT - 1 + kLag8) fp_step(fr, (uint32_t)(it - (NT - 1 + kLag8)));
+            __syncwarp();  // the stencil's reads of FIFO row `fr` precede the drift's writes to it
+            if (kick) kick_step(it, fr, it + 1 >= NT);
+        }
+        // the last row's sums
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            float p = pprev[j];
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
+            if (lane == 0) red[(S - 1) * NSEG + warp * 2 + j] = p;
+        }
+    };
+    if (spread == 0) run(std::integral_constant<int, 4>{});
+    else if (spread == 1) run(std::integral_constant<int, 5>{});
+    else run(std::integral_constant<int, 6>{});
+
+    // the strip's row sums: one thread per row adds the segments' partials in fixed order
+    __syncthreads();
+    for (uint32_t i = tid; i < S; i += T) {
+        float v = 0.0f;
+        for (uint32_t k = 0; k < NSEG; k++) v = __fadd_rn(v, red[i * NSEG + k]);
+        g.rho_out[(size_t)member * n + xa + i] = v;
+    }
+}
+
+size_t stream8_fixed_smem(uint32_t n, uint32_t S0, uint32_t H, uint32_t* wwin_len_out) {
+    auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const uint32_t NW = n / 256, NSEG = n / 128;
+    const uint32_t max_rin = S0 + H;
+    const uint32_t wcount = n + ((max_rin + 63) & ~63u);
+    const uint32_t wwin_len = wcount + (wcount >> 3) + 8;
+    if (wwin_len_out) *wwin_len_out = wwin_len;
+    return a16((size_t)NW * kSlots8 * kSlotB) + a16((size_t)NW * kLag8 * kSlotB) + a16((size_t)(n + n / 32) * 8) +
+           a16((size_t)wwin_len * 8) + a16((size_t)NSEG * max_rin * 8) + a16((size_t)S0 * NSEG * 4) +
+           a16((size_t)(max_rin + 1) * 48) + a16((size_t)NW * 2 * kMail8 * 16) + 16;
+}
+
+}  // namespace
+
+// Launch plan of the column-block kernel: strip length search with the cost model of the streaming
+// kernel (ivs_fused.cu).  Returns false when the kernel does not apply (grid size, drift spread).
+bool ivs_stream8_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan, const int* dr_first) {
+    const uint32_t n = s->n;
+    if (n % 256 != 0 || n > 2048) return false;
+    // over a warp's 256 columns the first drift tap may vary by at most 2 rows (window of up to 6 rows)
+    for (uint32_t w = 0; w < n / 256; w++) {
+        const auto mm = std::minmax_element(dr_first + 256 * w, dr_first + 256 * (w + 1));
+        if (*mm.second - *mm.first > 2) return false;
+    }
+    const uint32_t H = plan->halo_lo + plan->halo_hi;
+    const uint32_t threads = n / 8;
+    const bool fma = ctx->arith == IVS_ARITH_FMA;
+    const void* kfn = fma ? (const void*)stream8_step_kernel<true> : (const void*)stream8_step_kernel<false>;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kfn) != cudaSuccess) return false;
+    const uint32_t regs_thread = (std::max(fa.numRegs, 32) + 7) & ~7;
+    const uint32_t by_regs = std::max<uint32_t>(1, 65536u / (regs_thread * threads));  // CTAs per SM
+    double best = 1e300;
+    uint32_t bestP = 0, best_rin = 0, best_wwin = 0;
+    size_t best_sb = 0;
+    const uint32_t forceP = s->desc.strips;  // 0: the planner's choice
+    for (uint32_t P = 1; P <= n / 2; P++) {
+        if (forceP && P != forceP) continue;
+        const uint32_t S0 = ivs_div_up(n, P);
+        if ((uint64_t)S0 * (P - 1) >= n || S0 > 128) continue;  // last strip empty / table cap
+        if (S0 < 8 && (uint64_t)P * s->members > (uint64_t)ctx->sm_count) continue;
+        uint32_t wwin_len = 0;
+        const size_t sb = stream8_fixed_smem(n, S0, H, &wwin_len);
+        uint32_t want = std::min<uint32_t>(by_regs, 16);
+        for (; want >= 1; want--)
+            if (sb <= (size_t)227 * 1024 / want - 1024) break;
+        if (want < 1) continue;
+        const uint64_t units = (uint64_t)P * s->members;
+        const uint64_t slots = (uint64_t)ctx->sm_count * want;
+        const uint64_t rounds = (units + slots - 1) / slots;
+        const uint32_t resident = (uint32_t)std::min<uint64_t>(want, ivs_div_up((uint32_t)units, ctx->sm_count));
+        const double fill = std::min(1.0, resident * (n / 128) / 16.0);
+        const double cost = (double)rounds * (S0 + H + 16) * resident / std::max(fill, 1.0 / 16);
+        if (cost < best) { best = cost; bestP = P; best_sb = sb; best_rin = S0 + H; best_wwin = wwin_len; }
+    }
+    if (!bestP) return false;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem) != cudaSuccess) return false;
+    plan->stream8 = true;
+    plan->strip = ivs_div_up(n, bestP);
+    plan->max_strip = plan->strip;
+    plan->max_rin = best_rin;
+    plan->wwin_len = best_wwin;
+    plan->threads = threads;
+    plan->smem = best_sb;
+    plan->kslots = kSlots8;
+    return true;
+}
+
+ivs_status ivs_stream8_launch(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_sim* s, const fused_args& a) {
+    stream_args sa;
+    sa.f = a;
+    sa.f.fp_w5 = (const float*)plan->fp5;
+    sa.strip = plan->strip; sa.kslots = plan->kslots;
+    sa.max_strip = plan->max_strip; sa.max_rin = plan->max_rin; sa.wwin_len = plan->wwin_len;
+    const dim3 sgrid(ivs_div_up(s->n, plan->strip), s->members);
+    if (ctx->arith == IVS_ARITH_FMA) stream8_step_kernel<true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+    else stream8_step_kernel<false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+    IVS_LAUNCHED(ctx);
+    return IVS_OK;
+}
