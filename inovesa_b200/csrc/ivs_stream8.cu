@@ -54,9 +54,10 @@ template <int DOFF, int SOFF>
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 4;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
 }
-template <int DOFF>
+template <int DOFF, int SOFF>
 __device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const float* src, uint32_t bytes) {
-    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1], 4, %3;" ::"r"(dst), "l"(src), "n"(DOFF), "r"(bytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 4, %4;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF), "r"(bytes)
+                 : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
     const int nb_l = (lane & 1) ? -(int)kOddB : (int)kOddB - 16;
     const int nb_r = (lane & 1) ? 16 - (int)kOddB : (int)kOddB;
     const bool edge_warp = warp == 0 || warp + 1 == NW;
-    const bool slow_stage = edge_warp || xs < 0 || xs + (int)RIN > (int)n;
+    const bool strip_edge = xs < 0 || xs + (int)RIN > (int)n;  // some of the strip's input rows lie outside the grid
     // staging: this lane's cell of every group of 32 staged cells (see the header comment)
     const uint32_t st_dst = ((lane >> 2) & 1) * kOddB + ((lane >> 3) * 4 + (lane & 3)) * 4;
     float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + (cb >> 2) + lane;
@@ -343,15 +344,19 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         const uint32_t r0 = (uint32_t)((int)hl + wfmin);
         const int nkicks = (int)(S + NT - 1);
 
-        // ---- staging of input row r0 + k into slot k mod kSlots8 (one cp.async group per call)
+        // ---- staging of input row r0 + k into slot k mod kSlots8, one cp.async group per call.
+        // Cursors: the next row's cells (this lane's first), its table entry, its grid row; the
+        // whole-cell displacement f1 + f2 of the next row is fetched a call ahead.
+        const float* srow = gin + ((long long)(xs + (int)r0) * (long long)n + (long long)(cb + lane));
+        uint32_t stab = tab_b + r0 * 48 + 32;
+        int sx = xs + (int)r0;
+        int fs_next = lds32i(stab);
         auto stage = [&](int k) {
-            if (k < nkicks) {
-                const uint32_t r = r0 + (uint32_t)k;
-                const int fs = lds32i(tab_b + r * 48 + 32);
-                const int x = xs + (int)r;
-                const uint32_t dst = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + st_dst;
-                if (!slow_stage) {
-                    const float* src = gin + ((long long)x * (long long)n + (long long)((int)cb + fs + (int)lane));
+            const int fs = fs_next;
+            const uint32_t dst = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + st_dst;
+            const float* src = srow + fs;
+            if (!strip_edge || (uint32_t)sx < n) {
+                if (!edge_warp) {
                     cp_async4<0, 0>(dst, src);
                     cp_async4<64, 128>(dst, src);
                     cp_async4<128, 256>(dst, src);
@@ -360,25 +365,39 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                     cp_async4<320, 640>(dst, src);
                     cp_async4<384, 768>(dst, src);
                     cp_async4<448, 896>(dst, src);
-                    if (lane < 8) cp_async4<512, 1024>(dst, src);
+                    cp_async4<512, 1024>(dst, src);  // 8 of these 32 cells are needed; the rest lands in the slot's slack
                 } else {
-                    // a block at the grid's edge, or a strip with rows outside the grid: cells outside are zeros
-                    const bool rowok = (uint32_t)x < n;
-                    const int col0 = (int)cb + fs + (int)lane;
-                    const float* rowp = gin + (size_t)(rowok ? x : 0) * n;
-#define IVS_STAGE_Z(K2)                                                         \
-    {                                                                           \
-        const int col = col0 + 32 * (K2);                                       \
-        const bool ok = rowok && (uint32_t)col < n;                             \
-        cp_async4_zfill<64 * (K2)>(dst, rowp + (ok ? col : 0), ok ? 4u : 0u);   \
-    }
-                    IVS_STAGE_Z(0) IVS_STAGE_Z(1) IVS_STAGE_Z(2) IVS_STAGE_Z(3)
-                    IVS_STAGE_Z(4) IVS_STAGE_Z(5) IVS_STAGE_Z(6) IVS_STAGE_Z(7)
-                    if (lane < 8) IVS_STAGE_Z(8)
-#undef IVS_STAGE_Z
+                    // a block at the grid's edge: cells outside the grid are zeros (src-size 0: nothing is
+                    // read).  Only the first 32 cells can lie left of the grid and only the last 64 right
+                    // of it (|f1 + f2| <= 32).
+                    const int col0 = (int)(cb + lane) + fs;
+                    cp_async4_zfill<0, 0>(dst, src, col0 >= 0 ? 4u : 0u);
+                    cp_async4<64, 128>(dst, src);
+                    cp_async4<128, 256>(dst, src);
+                    cp_async4<192, 384>(dst, src);
+                    cp_async4<256, 512>(dst, src);
+                    cp_async4<320, 640>(dst, src);
+                    cp_async4<384, 768>(dst, src);
+                    cp_async4_zfill<448, 896>(dst, src, col0 + 224 < (int)n ? 4u : 0u);
+                    cp_async4_zfill<512, 1024>(dst, src, col0 + 256 < (int)n ? 4u : 0u);
                 }
+            } else {
+                // a row outside the grid (first and last strip of a member): zeros
+                cp_async4_zfill<0, 0>(dst, gin, 0u);
+                cp_async4_zfill<64, 0>(dst, gin, 0u);
+                cp_async4_zfill<128, 0>(dst, gin, 0u);
+                cp_async4_zfill<192, 0>(dst, gin, 0u);
+                cp_async4_zfill<256, 0>(dst, gin, 0u);
+                cp_async4_zfill<320, 0>(dst, gin, 0u);
+                cp_async4_zfill<384, 0>(dst, gin, 0u);
+                cp_async4_zfill<448, 0>(dst, gin, 0u);
+                cp_async4_zfill<512, 0>(dst, gin, 0u);
             }
             cp_async_commit();
+            srow += n;
+            stab += 48;
+            sx++;
+            fs_next = lds32i(stab);  // the table has an entry beyond the last row
         };
 
         // drift as running sums: P[c][j] is the output row that has taken j + 1 of its NT taps so far
@@ -393,148 +412,196 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         const bool red_lane = (lane & 15) == 0;
         const size_t gstride = (size_t)nq;
 
-        // ---- one kick step: staged row r0 + it -> wake kick + RF kick -> drift sums -> drifted row
-        // (output row it - NT + 1 once the sums are full) -> FIFO row `frow`, edges posted
-        auto kick_step = [&](const int it, const uint32_t frow, const bool POST) {
-            const uint32_t tp = tab_b + (r0 + (uint32_t)it) * 48;
-            const float4 w1 = lds128(tp), w2 = lds128(tp + 16);
-            const uint32_t s = ring_w + ((uint32_t)it & (kSlots8 - 1)) * kSlotB + lane * 16;
-            float in[14];
-            {
-                const float4 a0 = lds128(s), b0 = lds128(s + kOddB), a1 = lds128(s + 16);
-                const float2 b1 = lds64f(s + kOddB + 16);
-                in[0] = a0.x; in[1] = a0.y; in[2] = a0.z; in[3] = a0.w;
-                in[4] = b0.x; in[5] = b0.y; in[6] = b0.z; in[7] = b0.w;
-                in[8] = a1.x; in[9] = a1.y; in[10] = a1.z; in[11] = a1.w;
-                in[12] = b1.x; in[13] = b1.y;
-            }
-            // k1[i] = wake-kicked cell ycol + f2 + i (src/SM/KickMap.cpp:243-266), 0 outside the grid
-            float k1[11];
-#pragma unroll
-            for (int i = 0; i < 11; i++) k1[i] = tap4<FMA>(in[i], in[i + 1], in[i + 2], in[i + 3], w1);
-            if (edge_warp) {
-                const int m0 = (int)ycol + lds32i(tp + 36);
-#pragma unroll
-                for (int i = 0; i < 11; i++)
-                    if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
-            }
-            float d[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const float kq = tap4<FMA>(k1[c], k1[c + 1], k1[c + 2], k1[c + 3], w2);  // RF kick, same loop
-                // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
-                d[c] = madd<FMA>(kq, dw[c][NT - 1], P[c][NT - 2]);
-#pragma unroll
-                for (int t = NT - 2; t > 0; t--) P[c][t] = madd<FMA>(kq, dw[c][t], P[c][t - 1]);
-                P[c][0] = __fmul_rn(kq, dw[c][0]);
-            }
-            // parked in the row FIFO until its stencil step kLag8 iterations later
-            sts128(frow + lane * 16, d[0], d[1], d[2], d[3]);
-            sts128(frow + kOddB + lane * 16, d[4], d[5], d[6], d[7]);
-            if (POST) {
-                const uint32_t orow = (uint32_t)(it - NT + 1);
-                const float seq = __uint_as_float(orow + 1);
-                const bool l0 = lane == 0;
-                sts128_volatile_if(post_me + (orow & (kMail8 - 1)) * 16,
-                                   make_float4(l0 ? d[0] : seq, l0 ? d[1] : 0.0f, l0 ? seq : d[6], l0 ? 0.0f : d[7]),
-                                   l0 || lane == 31);
-            }
-        };
-        // ---- one stencil step on drifted output row `orow` (out of FIFO row `frow`): neighbours,
-        // Fokker-Planck, store, partial row sums; the warp sum of the row before is reduced on the side
-        auto fp_step = [&](const uint32_t frow, const uint32_t orow) {
-            const uint32_t fo = frow + own_off;
-            const float4 o0 = lds128(fo), o1 = lds128(fo + 256);
-            const float4 r0q = lds128(fo + nb_r), l1q = lds128(fo + 256 + nb_l);
-            const uint32_t sp_a = spec_base + ((orow * 16) & spec_mask);
-            const uint32_t la = spec_l ? sp_a : fo + nb_l;
-            const uint32_t ra = spec_r ? sp_a : fo + 256 + nb_r;
-            float4 l0q = lds128_volatile(la), r1q = lds128_volatile(ra);
-            const uint32_t want = orow + 1;
-            // the row sums of the row before: first level of the butterfly (the two segments' sums are
-            // transposed into the two half-warps, same tree per segment as everywhere else)
-            float ps;
-            {
-                const bool upper = (lane & 16) != 0;
-                const float send = upper ? pprev[0] : pprev[1];
-                const float keep = upper ? pprev[1] : pprev[0];
-                ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-            }
-            if (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want)) {
-                // the neighbour is more than kLag8 - 1 rows behind: poll
-                uint32_t tries = 0;
-                do {
-                    if (edge_l) l0q = lds128_volatile(la);
-                    if (edge_r) r1q = lds128_volatile(ra);
-                    if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
-                } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want));
-            }
-            // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
-            float o[2][4];
-#define IVS_FP_COL(j, c)                                                 \
-            {                                                            \
-                float v = __fmul_rn(in[c], w5[j][c][0]);                 \
-                v = madd<FMA>(in[1 + c], w5[j][c][1], v);                \
-                v = madd<FMA>(in[2 + c], w5[j][c][2], v);                \
-                v = madd<FMA>(in[3 + c], w5[j][c][3], v);                \
-                v = madd<FMA>(in[4 + c], w5[j][c][4], v);                \
-                o[j][c] = v;                                             \
-            }
-            {
-                const float in[8] = {l0q.z, l0q.w, o0.x, o0.y, o0.z, o0.w, r0q.x, r0q.y};
-                IVS_FP_COL(0, 0)
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
-                IVS_FP_COL(0, 1)
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
-                IVS_FP_COL(0, 2)
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
-                IVS_FP_COL(0, 3)
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
-                gout[0] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
-            }
-            {
-                const float in[8] = {l1q.z, l1q.w, o1.x, o1.y, o1.z, o1.w, r1q.x, r1q.y};
-                IVS_FP_COL(1, 0)
-                IVS_FP_COL(1, 1)
-                IVS_FP_COL(1, 2)
-                IVS_FP_COL(1, 3)
-                gout[32] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
-            }
-#undef IVS_FP_COL
-            gout += gstride;
-            if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
-            redp += NSEG * 4;
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                float p = __fmul_rn(o[j][0], ws4[j].x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
-                p = __fadd_rn(p, __fmul_rn(o[j][1], ws4[j].y));
-                p = __fadd_rn(p, __fmul_rn(o[j][2], ws4[j].z));
-                p = __fadd_rn(p, __fmul_rn(o[j][3], ws4[j].w));
-                pprev[j] = p;
-            }
+        // the staged cells and taps of the row the next kick works on, requested an iteration ahead
+        float4 w1, w2;
+        float in[14];
+        auto load_row = [&](const int k) {
+            const uint32_t tp = tab_b + (r0 + (uint32_t)k) * 48;
+            w1 = lds128(tp);
+            w2 = lds128(tp + 16);
+            const uint32_t sl = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + lane * 16;
+            const float4 a0 = lds128(sl), b0 = lds128(sl + kOddB), a1 = lds128(sl + 16);
+            const float2 b1 = lds64f(sl + kOddB + 16);
+            in[0] = a0.x; in[1] = a0.y; in[2] = a0.z; in[3] = a0.w;
+            in[4] = b0.x; in[5] = b0.y; in[6] = b0.z; in[7] = b0.w;
+            in[8] = a1.x; in[9] = a1.y; in[10] = a1.z; in[11] = a1.w;
+            in[12] = b1.x; in[13] = b1.y;
         };
 
-        // Iteration `it` kicks row r0 + it; from it = NT-1 on a drifted output row (it - NT + 1) comes
-        // out and is parked in FIFO row it mod kLag8; the stencil handles the row parked kLag8
-        // iterations before (output row it - NT + 1 - kLag8, read from the same FIFO row before this
-        // iteration's kick overwrites it), so a warp only waits for a neighbour that is more than
-        // kLag8 - 1 rows late.
-        auto fifo_at = [&](int i) { return fifo_w + (uint32_t)(i & (kLag8 - 1)) * kSlotB; };
-#pragma unroll 1
-        for (int k = 0; k < kSlots8 - 1; k++) stage(k);
-        const int it_end = nkicks + kLag8;
-#pragma unroll 1
-        for (int it = 0; it < it_end; it++) {
-            const uint32_t fr = fifo_at(it);
-            const bool kick = it < nkicks;
-            if (kick) {
-                cp_async_wait<kSlots8 - 2>();  // row r0 + it has landed (this lane's part of it)
-            }
+        // One iteration.  Iteration `it` kicks input row r0 + it (KICK); from it = NT-1 on a drifted
+        // output row (it - NT + 1) comes out and is parked in FIFO row it mod kLag8; the stencil (FP)
+        // handles the row parked kLag8 iterations before (output row it - NT + 1 - kLag8, read from the
+        // same FIFO row before this iteration's kick overwrites it), so a warp only waits for a
+        // neighbour that is more than kLag8 - 1 rows late.  Shared-memory loads run ahead of their
+        // use: the stencil's are requested before the kick's arithmetic, the next kick's after this one's.
+        auto iter = [&](const int it, auto fp_tag, auto kick_tag, auto stage_tag) {
+            constexpr bool FP = decltype(fp_tag)::value, KICK = decltype(kick_tag)::value;
+            constexpr bool STAGE = decltype(stage_tag)::value;
+            const uint32_t frow = fifo_w + ((uint32_t)it & (kLag8 - 1)) * kSlotB;
+            const uint32_t orow = (uint32_t)(it - (NT - 1 + kLag8));  // the stencil's output row
+            if (KICK) cp_async_wait<kSlots8 - 3>();  // row r0 + it + 1 has landed (this lane's part of it)
             __syncwarp();  // ... and everybody's; the FIFO row written an iteration ago is visible; slot it-1 is free
-            if (kick) stage(it + kSlots8 - 1);
-            if (it >= NT - 1 + kLag8) fp_step(fr, (uint32_t)(it - (NT - 1 + kLag8)));
-            __syncwarp();  // the stencil's reads of FIFO row `fr` precede the drift's writes to it
-            if (kick) kick_step(it, fr, it + 1 >= NT);
+            if (STAGE) stage(it + kSlots8 - 1);
+            else if (KICK) cp_async_commit();  // keeps the group count in step
+            float4 o0, o1, r0q, l1q, l0q, r1q;
+            uint32_t la = 0, ra = 0;
+            if (FP) {
+                const uint32_t fo = frow + own_off;
+                o0 = lds128(fo);
+                o1 = lds128(fo + 256);
+                r0q = lds128(fo + nb_r);
+                l1q = lds128(fo + 256 + nb_l);
+                const uint32_t sp_a = spec_base + ((orow * 16) & spec_mask);
+                la = spec_l ? sp_a : fo + nb_l;
+                ra = spec_r ? sp_a : fo + 256 + nb_r;
+                l0q = lds128_volatile(la);
+                r1q = lds128_volatile(ra);
+            }
+            __syncwarp();  // the stencil's reads of FIFO row `frow` precede the drift's writes to it
+            if (KICK) {
+                // k1[i] = wake-kicked cell ycol + f2 + i (src/SM/KickMap.cpp:243-266), 0 outside the grid
+                float k1[11];
+#pragma unroll
+                for (int i = 0; i < 11; i++) k1[i] = tap4<FMA>(in[i], in[i + 1], in[i + 2], in[i + 3], w1);
+                if (edge_warp) {
+                    const int f2 = lds32i(tab_b + (r0 + (uint32_t)it) * 48 + 36);
+                    const int m0 = (int)ycol + f2;
+                    if (NW > 1 && f2 >= -3 && f2 <= 1) {
+                        // only the block's first 3 (left edge of the grid) or last 4 (right edge) can lie outside
+                        if (warp == 0) {
+#pragma unroll
+                            for (int i = 0; i < 3; i++)
+                                if (m0 + i < 0) k1[i] = 0.0f;
+                        } else {
+#pragma unroll
+                            for (int i = 7; i < 11; i++)
+                                if (m0 + i >= (int)n) k1[i] = 0.0f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 11; i++)
+                            if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
+                    }
+                }
+                float kq[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) kq[c] = tap4<FMA>(k1[c], k1[c + 1], k1[c + 2], k1[c + 3], w2);  // RF kick, same loop
+                load_row(it + 1);  // the registers are free again: the next row's cells and taps
+                float d[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    // src/SM/KickMap.cpp:221-242, column-local 4-tap along x
+                    d[c] = madd<FMA>(kq[c], dw[c][NT - 1], P[c][NT - 2]);
+#pragma unroll
+                    for (int t = NT - 2; t > 0; t--) P[c][t] = madd<FMA>(kq[c], dw[c][t], P[c][t - 1]);
+                    P[c][0] = __fmul_rn(kq[c], dw[c][0]);
+                }
+                // parked in the row FIFO until its stencil step kLag8 iterations later
+                sts128(frow + lane * 16, d[0], d[1], d[2], d[3]);
+                sts128(frow + kOddB + lane * 16, d[4], d[5], d[6], d[7]);
+                if (it + 1 >= NT) {  // a real output row: its ends are posted for the neighbour warps
+                    const uint32_t prow = (uint32_t)(it - NT + 1);
+                    const float seq = __uint_as_float(prow + 1);
+                    const bool l0 = lane == 0;
+                    sts128_volatile_if(post_me + (prow & (kMail8 - 1)) * 16,
+                                       make_float4(l0 ? d[0] : seq, l0 ? d[1] : 0.0f, l0 ? seq : d[6], l0 ? 0.0f : d[7]),
+                                       l0 || lane == 31);
+                }
+            }
+            if (FP) {
+                const uint32_t want = orow + 1;
+                // the row sums of the row before: first level of the butterfly (the two segments' sums are
+                // transposed into the two half-warps, same tree per segment as everywhere else)
+                float ps;
+                {
+                    const bool upper = (lane & 16) != 0;
+                    const float send = upper ? pprev[0] : pprev[1];
+                    const float keep = upper ? pprev[1] : pprev[0];
+                    ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                }
+                if (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want)) {
+                    // the neighbour is more than kLag8 - 1 rows behind: poll
+                    uint32_t tries = 0;
+                    do {
+                        if (edge_l) l0q = lds128_volatile(la);
+                        if (edge_r) r1q = lds128_volatile(ra);
+                        if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
+                    } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want));
+                }
+                // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
+                float o[2][4];
+#define IVS_FP_COL(j, c)                                                 \
+                {                                                        \
+                    float v = __fmul_rn(fin[c], w5[j][c][0]);            \
+                    v = madd<FMA>(fin[1 + c], w5[j][c][1], v);           \
+                    v = madd<FMA>(fin[2 + c], w5[j][c][2], v);           \
+                    v = madd<FMA>(fin[3 + c], w5[j][c][3], v);           \
+                    v = madd<FMA>(fin[4 + c], w5[j][c][4], v);           \
+                    o[j][c] = v;                                         \
+                }
+                {
+                    const float fin[8] = {l0q.z, l0q.w, o0.x, o0.y, o0.z, o0.w, r0q.x, r0q.y};
+                    const float ps8 = __shfl_xor_sync(0xffffffffu, ps, 8);
+                    IVS_FP_COL(0, 0)
+                    IVS_FP_COL(0, 1)
+                    ps = __fadd_rn(ps, ps8);
+                    const float ps4 = __shfl_xor_sync(0xffffffffu, ps, 4);
+                    IVS_FP_COL(0, 2)
+                    IVS_FP_COL(0, 3)
+                    ps = __fadd_rn(ps, ps4);
+                    gout[0] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+                }
+                {
+                    const float fin[8] = {l1q.z, l1q.w, o1.x, o1.y, o1.z, o1.w, r1q.x, r1q.y};
+                    const float ps2 = __shfl_xor_sync(0xffffffffu, ps, 2);
+                    IVS_FP_COL(1, 0)
+                    IVS_FP_COL(1, 1)
+                    ps = __fadd_rn(ps, ps2);
+                    const float ps1 = __shfl_xor_sync(0xffffffffu, ps, 1);
+                    IVS_FP_COL(1, 2)
+                    IVS_FP_COL(1, 3)
+                    ps = __fadd_rn(ps, ps1);
+                    gout[32] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+                }
+#undef IVS_FP_COL
+                gout += gstride;
+                if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
+                redp += NSEG * 4;
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    float p = __fmul_rn(o[j][0], ws4[j].x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
+                    p = __fadd_rn(p, __fmul_rn(o[j][1], ws4[j].y));
+                    p = __fadd_rn(p, __fmul_rn(o[j][2], ws4[j].z));
+                    p = __fadd_rn(p, __fmul_rn(o[j][3], ws4[j].w));
+                    pprev[j] = p;
+                }
+            }
+        };
+        const std::true_type yes{};
+        const std::false_type no{};
+        // prologue: the first kSlots8 - 1 rows are requested, the first one is loaded
+#pragma unroll 1
+        for (int k = 0; k < kSlots8 - 1; k++) {
+            if (k < nkicks) stage(k);
+            else cp_async_commit();
+        }
+        cp_async_wait<kSlots8 - 2>();
+        __syncwarp();
+        load_row(0);
+        const int n_stage = nkicks - (kSlots8 - 1);  // iterations that still have a row to request
+        int it = 0;
+#pragma unroll 1
+        for (; it < NT - 1 + kLag8 && it < nkicks; it++) {  // fill the drift sums and the FIFO
+            if (it < n_stage) iter(it, no, yes, yes);
+            else iter(it, no, yes, no);
+        }
+#pragma unroll 1
+        for (; it < n_stage; it++) iter(it, yes, yes, yes);  // steady state
+#pragma unroll 1
+        for (; it < nkicks; it++) iter(it, yes, yes, no);    // the last rows are in flight or staged
+#pragma unroll 1
+        for (; it < nkicks + kLag8; it++) {                  // the rows still parked
+            if (it >= NT - 1 + kLag8) iter(it, yes, no, no);
         }
         // the last row's sums
 #pragma unroll
