@@ -356,31 +356,20 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             const uint32_t dst = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + st_dst;
             const float* src = srow + fs;
             if (!strip_edge || (uint32_t)sx < n) {
-                if (!edge_warp) {
-                    cp_async4<0, 0>(dst, src);
-                    cp_async4<64, 128>(dst, src);
-                    cp_async4<128, 256>(dst, src);
-                    cp_async4<192, 384>(dst, src);
-                    cp_async4<256, 512>(dst, src);
-                    cp_async4<320, 640>(dst, src);
-                    cp_async4<384, 768>(dst, src);
-                    cp_async4<448, 896>(dst, src);
-                    cp_async4<512, 1024>(dst, src);  // 8 of these 32 cells are needed; the rest lands in the slot's slack
-                } else {
-                    // a block at the grid's edge: cells outside the grid are zeros (src-size 0: nothing is
-                    // read).  Only the first 32 cells can lie left of the grid and only the last 64 right
-                    // of it (|f1 + f2| <= 32).
-                    const int col0 = (int)(cb + lane) + fs;
-                    cp_async4_zfill<0, 0>(dst, src, col0 >= 0 ? 4u : 0u);
-                    cp_async4<64, 128>(dst, src);
-                    cp_async4<128, 256>(dst, src);
-                    cp_async4<192, 384>(dst, src);
-                    cp_async4<256, 512>(dst, src);
-                    cp_async4<320, 640>(dst, src);
-                    cp_async4<384, 768>(dst, src);
-                    cp_async4_zfill<448, 896>(dst, src, col0 + 224 < (int)n ? 4u : 0u);
-                    cp_async4_zfill<512, 1024>(dst, src, col0 + 256 < (int)n ? 4u : 0u);
-                }
+                // cells outside the grid are zeros (src-size 0: nothing is read).  Only the first 32 cells
+                // can lie left of the grid and only the last 64 right of it (|f1 + f2| <= 32), and only in
+                // the grid's first and last block; the three guards are the same code for every block so
+                // that all warps of a CTA keep the same pace.
+                const int col0 = (int)(cb + lane) + fs;
+                cp_async4_zfill<0, 0>(dst, src, col0 >= 0 ? 4u : 0u);
+                cp_async4<64, 128>(dst, src);
+                cp_async4<128, 256>(dst, src);
+                cp_async4<192, 384>(dst, src);
+                cp_async4<256, 512>(dst, src);
+                cp_async4<320, 640>(dst, src);
+                cp_async4<384, 768>(dst, src);
+                cp_async4_zfill<448, 896>(dst, src, col0 + 224 < (int)n ? 4u : 0u);
+                cp_async4_zfill<512, 1024>(dst, src, col0 + 256 < (int)n ? 4u : 0u);  // 8 of these 32 cells are needed
             } else {
                 // a row outside the grid (first and last strip of a member): zeros
                 cp_async4_zfill<0, 0>(dst, gin, 0u);
@@ -395,8 +384,8 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             }
             cp_async_commit();
             srow += n;
-            stab += 48;
             sx++;
+            stab += 48;
             fs_next = lds32i(stab);  // the table has an entry beyond the last row
         };
 
@@ -458,6 +447,20 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 r1q = lds128_volatile(ra);
             }
             __syncwarp();  // the stencil's reads of FIFO row `frow` precede the drift's writes to it
+            // the row sums of the row the stencil handled an iteration ago: the two segments' sums are
+            // transposed into the two half-warps, then four more levels (same tree per segment as
+            // everywhere else); the shuffles' latency disappears behind the kick's arithmetic
+            float ps = 0.0f;
+            if (FP) {
+                const bool upper = (lane & 16) != 0;
+                const float send = upper ? pprev[0] : pprev[1];
+                const float keep = upper ? pprev[1] : pprev[0];
+                ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
+                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
+            }
             if (KICK) {
                 // k1[i] = wake-kicked cell ycol + f2 + i (src/SM/KickMap.cpp:243-266), 0 outside the grid
                 float k1[11];
@@ -510,15 +513,6 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             }
             if (FP) {
                 const uint32_t want = orow + 1;
-                // the row sums of the row before: first level of the butterfly (the two segments' sums are
-                // transposed into the two half-warps, same tree per segment as everywhere else)
-                float ps;
-                {
-                    const bool upper = (lane & 16) != 0;
-                    const float send = upper ? pprev[0] : pprev[1];
-                    const float keep = upper ? pprev[1] : pprev[0];
-                    ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                }
                 if (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want)) {
                     // the neighbour is more than kLag8 - 1 rows behind: poll
                     uint32_t tries = 0;
@@ -541,26 +535,18 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 }
                 {
                     const float fin[8] = {l0q.z, l0q.w, o0.x, o0.y, o0.z, o0.w, r0q.x, r0q.y};
-                    const float ps8 = __shfl_xor_sync(0xffffffffu, ps, 8);
                     IVS_FP_COL(0, 0)
                     IVS_FP_COL(0, 1)
-                    ps = __fadd_rn(ps, ps8);
-                    const float ps4 = __shfl_xor_sync(0xffffffffu, ps, 4);
                     IVS_FP_COL(0, 2)
                     IVS_FP_COL(0, 3)
-                    ps = __fadd_rn(ps, ps4);
                     gout[0] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
                 }
                 {
                     const float fin[8] = {l1q.z, l1q.w, o1.x, o1.y, o1.z, o1.w, r1q.x, r1q.y};
-                    const float ps2 = __shfl_xor_sync(0xffffffffu, ps, 2);
                     IVS_FP_COL(1, 0)
                     IVS_FP_COL(1, 1)
-                    ps = __fadd_rn(ps, ps2);
-                    const float ps1 = __shfl_xor_sync(0xffffffffu, ps, 1);
                     IVS_FP_COL(1, 2)
                     IVS_FP_COL(1, 3)
-                    ps = __fadd_rn(ps, ps1);
                     gout[32] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
                 }
 #undef IVS_FP_COL
