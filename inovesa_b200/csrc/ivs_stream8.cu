@@ -351,10 +351,17 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         uint32_t stab = tab_b + r0 * 48 + 32;
         int sx = xs + (int)r0;
         int fs_next = lds32i(stab);
+        if (strip_edge) {  // stale shared memory must not meet the zero weights as NaN * 0
+            for (uint32_t i = lane; i < kSlots8 * kSlotB / 16; i += 32)
+                sts128(ring_w + i * 16, 0.0f, 0.0f, 0.0f, 0.0f);
+            __syncwarp();
+        }
         auto stage = [&](int k) {
             const int fs = fs_next;
             const uint32_t dst = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + st_dst;
             const float* src = srow + fs;
+            // rows outside the grid (first and last strip of a member) are not copied: their RF taps are
+            // zeros and the slots of such a strip were cleared during the set-up
             if (!strip_edge || (uint32_t)sx < n) {
                 // cells outside the grid are zeros (src-size 0: nothing is read).  Only the first 32 cells
                 // can lie left of the grid and only the last 64 right of it (|f1 + f2| <= 32), and only in
@@ -370,17 +377,6 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 cp_async4<384, 768>(dst, src);
                 cp_async4_zfill<448, 896>(dst, src, col0 + 224 < (int)n ? 4u : 0u);
                 cp_async4_zfill<512, 1024>(dst, src, col0 + 256 < (int)n ? 4u : 0u);  // 8 of these 32 cells are needed
-            } else {
-                // a row outside the grid (first and last strip of a member): zeros
-                cp_async4_zfill<0, 0>(dst, gin, 0u);
-                cp_async4_zfill<64, 0>(dst, gin, 0u);
-                cp_async4_zfill<128, 0>(dst, gin, 0u);
-                cp_async4_zfill<192, 0>(dst, gin, 0u);
-                cp_async4_zfill<256, 0>(dst, gin, 0u);
-                cp_async4_zfill<320, 0>(dst, gin, 0u);
-                cp_async4_zfill<384, 0>(dst, gin, 0u);
-                cp_async4_zfill<448, 0>(dst, gin, 0u);
-                cp_async4_zfill<512, 0>(dst, gin, 0u);
             }
             cp_async_commit();
             srow += n;
@@ -395,19 +391,43 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         for (int c = 0; c < 8; c++)
 #pragma unroll
             for (int t = 0; t < NT - 1; t++) P[c][t] = 0.0f;
-        float pprev[2] = {0.0f, 0.0f};  // this lane's part of a finished row's sums (reduced an iteration later)
+        float pprev[2] = {0.0f, 0.0f};  // this lane's part of the sums of the row the stencil handled last
+        // The row sums' butterfly (xor 16, 8, 4, 2, 1: the same tree per 128-column segment as everywhere
+        // else) is spread over five iterations, one level each: every iteration issues five independent
+        // shuffle + add pairs for five different rows, so no add ever waits for its shuffle.
+        // lvl[k] = the sum after k + 1 levels of the row handled k + 2 stencil steps ago.
+        float lvl[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         // where the row sums reduced next go: lane 0 holds segment 2 warp's, lane 16 the next one's
-        uint32_t redp = smem_u32(red) + (warp * 2 + (lane >= 16 ? 1 : 0)) * 4 - NSEG * 4;
+        uint32_t redp = smem_u32(red) + (warp * 2 + (lane >= 16 ? 1 : 0)) * 4 - 5 * NSEG * 4;
         const bool red_lane = (lane & 15) == 0;
         const size_t gstride = (size_t)nq;
 
+        auto rowsum_step = [&]() {
+            const bool upper = (lane & 16) != 0;
+            // first level: the two segments' sums are transposed into the two half-warps
+            const float send = upper ? pprev[0] : pprev[1];
+            const float keep = upper ? pprev[1] : pprev[0];
+            const float s16 = __shfl_xor_sync(0xffffffffu, send, 16);
+            const float s8 = __shfl_xor_sync(0xffffffffu, lvl[0], 8);
+            const float s4 = __shfl_xor_sync(0xffffffffu, lvl[1], 4);
+            const float s2 = __shfl_xor_sync(0xffffffffu, lvl[2], 2);
+            const float s1 = __shfl_xor_sync(0xffffffffu, lvl[3], 1);
+            const float done = __fadd_rn(lvl[3], s1);
+            lvl[3] = __fadd_rn(lvl[2], s2);
+            lvl[2] = __fadd_rn(lvl[1], s4);
+            lvl[1] = __fadd_rn(lvl[0], s8);
+            lvl[0] = __fadd_rn(keep, s16);
+            return done;
+        };
         // the staged cells and taps of the row the next kick works on, requested an iteration ahead
         float4 w1, w2;
         float in[14];
+        int f2row = -1;  // first RF tap of that row (only the grid's first and last block look at it)
         auto load_row = [&](const int k) {
             const uint32_t tp = tab_b + (r0 + (uint32_t)k) * 48;
             w1 = lds128(tp);
             w2 = lds128(tp + 16);
+            if (edge_warp) f2row = lds32i(tp + 36);
             const uint32_t sl = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + lane * 16;
             const float4 a0 = lds128(sl), b0 = lds128(sl + kOddB), a1 = lds128(sl + 16);
             const float2 b1 = lds64f(sl + kOddB + 16);
@@ -447,27 +467,20 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 r1q = lds128_volatile(ra);
             }
             __syncwarp();  // the stencil's reads of FIFO row `frow` precede the drift's writes to it
-            // the row sums of the row the stencil handled an iteration ago: the two segments' sums are
-            // transposed into the two half-warps, then four more levels (same tree per segment as
-            // everywhere else); the shuffles' latency disappears behind the kick's arithmetic
+            // one level of the row sums' butterfly for each of the last five rows (see lvl above)
             float ps = 0.0f;
-            if (FP) {
-                const bool upper = (lane & 16) != 0;
-                const float send = upper ? pprev[0] : pprev[1];
-                const float keep = upper ? pprev[1] : pprev[0];
-                ps = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4));
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
-                ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
-            }
+            if (FP) ps = rowsum_step();
+            bool arrived = true;
             if (KICK) {
+                const uint32_t prow = (uint32_t)(it - NT + 1);  // the output row this kick completes
+                const float seq = __uint_as_float(prow + 1);
+                const uint32_t post_a = post_me + (prow & (kMail8 - 1)) * 16;
                 // k1[i] = wake-kicked cell ycol + f2 + i (src/SM/KickMap.cpp:243-266), 0 outside the grid
                 float k1[11];
 #pragma unroll
                 for (int i = 0; i < 11; i++) k1[i] = tap4<FMA>(in[i], in[i + 1], in[i + 2], in[i + 3], w1);
                 if (edge_warp) {
-                    const int f2 = lds32i(tab_b + (r0 + (uint32_t)it) * 48 + 36);
+                    const int f2 = f2row;
                     const int m0 = (int)ycol + f2;
                     if (NW > 1 && f2 >= -3 && f2 <= 1) {
                         // only the block's first 3 (left edge of the grid) or last 4 (right edge) can lie outside
@@ -486,6 +499,8 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                             if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
                     }
                 }
+                // has the neighbours' post for the stencil's row arrived?  Asked here, used after the drift
+                if (FP) arrived = __all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == orow + 1);
                 float kq[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) kq[c] = tap4<FMA>(k1[c], k1[c + 1], k1[c + 2], k1[c + 3], w2);  // RF kick, same loop
@@ -503,17 +518,16 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 sts128(frow + lane * 16, d[0], d[1], d[2], d[3]);
                 sts128(frow + kOddB + lane * 16, d[4], d[5], d[6], d[7]);
                 if (it + 1 >= NT) {  // a real output row: its ends are posted for the neighbour warps
-                    const uint32_t prow = (uint32_t)(it - NT + 1);
-                    const float seq = __uint_as_float(prow + 1);
                     const bool l0 = lane == 0;
-                    sts128_volatile_if(post_me + (prow & (kMail8 - 1)) * 16,
+                    sts128_volatile_if(post_a,
                                        make_float4(l0 ? d[0] : seq, l0 ? d[1] : 0.0f, l0 ? seq : d[6], l0 ? 0.0f : d[7]),
                                        l0 || lane == 31);
                 }
             }
             if (FP) {
                 const uint32_t want = orow + 1;
-                if (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want)) {
+                if (!KICK) arrived = __all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want);
+                if (!arrived) {
                     // the neighbour is more than kLag8 - 1 rows behind: poll
                     uint32_t tries = 0;
                     do {
@@ -551,7 +565,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 }
 #undef IVS_FP_COL
                 gout += gstride;
-                if (red_lane && orow > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
+                if (red_lane && orow >= 5) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
                 redp += NSEG * 4;
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
@@ -589,13 +603,14 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         for (; it < nkicks + kLag8; it++) {                  // the rows still parked
             if (it >= NT - 1 + kLag8) iter(it, yes, no, no);
         }
-        // the last row's sums
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            float p = pprev[j];
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, o2));
-            if (lane == 0) red[(S - 1) * NSEG + warp * 2 + j] = p;
+        // the five rows still in the butterfly
+#pragma unroll 1
+        for (int e = 0; e < 5; e++) {
+            const float tot = rowsum_step();
+            pprev[0] = pprev[1] = 0.0f;
+            const int row = (int)S - 5 + e;
+            if (red_lane && row >= 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(tot) : "memory");
+            redp += NSEG * 4;
         }
     };
     if (spread == 0) run(std::integral_constant<int, 4>{});
