@@ -216,9 +216,10 @@ enum {
     IVS_SIM_UNFUSED = 2u,       /* run the step as the reference's kernel sequence (debug / parity) */
     IVS_SIM_NO_GRAPH = 4u,      /* launch kernels directly instead of replaying a CUDA graph */
     IVS_SIM_TILED = 8u,         /* fused step as the tile kernel instead of the streaming pipeline */
-    IVS_SIM_QPT1 = 16u,         /* tuning: streaming kernel with one quad of columns per thread ... */
-    IVS_SIM_QPT2 = 32u,         /* ... or two (default: two from 1024 columns on) */
-    IVS_SIM_STREAM8 = 64u       /* tuning: column-block kernel (8 adjacent columns per lane, warp-private rings) */
+    IVS_SIM_QPT1 = 16u,         /* tuning: the streaming kernel (shared TMA ring) with one quad of columns per thread ... */
+    IVS_SIM_QPT2 = 32u,         /* ... or two, instead of the column-block kernel */
+    IVS_SIM_STREAM8 = 64u       /* the column-block kernel (8 adjacent columns per lane, warp-private rings): the
+                                   default for grid sizes that are multiples of 256 up to 2048 */
 };
 
 ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* desc, ivs_sim** out);

@@ -1407,7 +1407,9 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
         }
     }
     // ---- column-block kernel (ivs_stream8.cu): same domain of grid sizes, 8 adjacent columns per lane
-    if ((s->desc.flags & IVS_SIM_STREAM8) && !(s->desc.flags & IVS_SIM_TILED) && n % 256 == 0 && n <= 2048) {
+    // (the default; IVS_SIM_QPT1 / IVS_SIM_QPT2 select the streaming kernel instead)
+    const bool want8 = (s->desc.flags & IVS_SIM_STREAM8) || !(s->desc.flags & (IVS_SIM_QPT1 | IVS_SIM_QPT2));
+    if (want8 && !(s->desc.flags & IVS_SIM_TILED) && n % 256 == 0 && n <= 2048) {
         size_t keep_smem = plan->smem;
         uint32_t keep_threads = plan->threads;
         if (ivs_stream8_plan(ctx, s, plan, dr_first.data())) {

@@ -44,8 +44,17 @@
 
 namespace {
 
-constexpr int kSlots8 = 8;             // staged rows per warp (ring depth)
-constexpr int kLag8 = 4;               // rows between drift and stencil = depth of the row FIFO
+#ifndef IVS_S8_SLOTS
+#define IVS_S8_SLOTS 8
+#endif
+#ifndef IVS_S8_LAG
+#define IVS_S8_LAG 4
+#endif
+#ifndef IVS_S8_UNROLL2
+#define IVS_S8_UNROLL2 0
+#endif
+constexpr int kSlots8 = IVS_S8_SLOTS;  // staged rows per warp (ring depth, a power of two)
+constexpr int kLag8 = IVS_S8_LAG;      // rows between drift and stencil = depth of the row FIFO (a power of two)
 constexpr int kMail8 = 32;             // mailbox depth per warp edge (> 2 kLag8 + 2)
 constexpr uint32_t kSlotB = 1152;      // bytes per slot: even quads at 0 (33 quads), odd quads at kOddB (33 quads)
 constexpr uint32_t kOddB = 576;        // 144 floats: 16 banks away from the even half
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         // Cursors: the next row's cells (this lane's first), its table entry, its grid row; the
         // whole-cell displacement f1 + f2 of the next row is fetched a call ahead.
         const float* srow = gin + ((long long)(xs + (int)r0) * (long long)n + (long long)(cb + lane));
-        uint32_t stab = tab_b + r0 * 48 + 32;
+        const uint32_t stab = tab_b + r0 * 48 + 32;
         int sx = xs + (int)r0;
         int fs_next = lds32i(stab);
         if (strip_edge) {  // stale shared memory must not meet the zero weights as NaN * 0
@@ -381,8 +390,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             cp_async_commit();
             srow += n;
             sx++;
-            stab += 48;
-            fs_next = lds32i(stab);  // the table has an entry beyond the last row
+            fs_next = lds32i(stab + (uint32_t)(k + 1) * 48);  // the table has an entry beyond the last row
         };
 
         // drift as running sums: P[c][j] is the output row that has taken j + 1 of its NT taps so far
@@ -419,14 +427,19 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             lvl[0] = __fadd_rn(keep, s16);
             return done;
         };
-        // the staged cells and taps of the row the next kick works on, requested an iteration ahead
-        float4 w1, w2;
+        // What crosses from one iteration to the next: the wake-kicked cells k1 of the row the next
+        // kick works on (k1[i] = cell ycol + f2 + i of that row after the wake kick,
+        // src/SM/KickMap.cpp:243-266, 0 outside the grid) and that row's RF taps.  Its staged cells and
+        // taps are requested in the middle of an iteration and turned into k1 at its end.
+        float k1[11];
+        float4 w2 = make_float4(0, 0, 0, 0);
+        float4 w1n, w2n;
         float in[14];
         int f2row = -1;  // first RF tap of that row (only the grid's first and last block look at it)
         auto load_row = [&](const int k) {
             const uint32_t tp = tab_b + (r0 + (uint32_t)k) * 48;
-            w1 = lds128(tp);
-            w2 = lds128(tp + 16);
+            w1n = lds128(tp);
+            w2n = lds128(tp + 16);
             if (edge_warp) f2row = lds32i(tp + 36);
             const uint32_t sl = ring_w + ((uint32_t)k & (kSlots8 - 1)) * kSlotB + lane * 16;
             const float4 a0 = lds128(sl), b0 = lds128(sl + kOddB), a1 = lds128(sl + 16);
@@ -435,6 +448,31 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             in[4] = b0.x; in[5] = b0.y; in[6] = b0.z; in[7] = b0.w;
             in[8] = a1.x; in[9] = a1.y; in[10] = a1.z; in[11] = a1.w;
             in[12] = b1.x; in[13] = b1.y;
+        };
+        auto wake_kick = [&]() {
+#pragma unroll
+            for (int i = 0; i < 11; i++) k1[i] = tap4<FMA>(in[i], in[i + 1], in[i + 2], in[i + 3], w1n);
+            w2 = w2n;
+            if (edge_warp) {
+                const int f2 = f2row;
+                const int m0 = (int)ycol + f2;
+                if (NW > 1 && f2 >= -3 && f2 <= 1) {
+                    // only the block's first 3 (left edge of the grid) or last 4 (right edge) can lie outside
+                    if (warp == 0) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++)
+                            if (m0 + i < 0) k1[i] = 0.0f;
+                    } else {
+#pragma unroll
+                        for (int i = 7; i < 11; i++)
+                            if (m0 + i >= (int)n) k1[i] = 0.0f;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 11; i++)
+                        if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
+                }
+            }
         };
 
         // One iteration.  Iteration `it` kicks input row r0 + it (KICK); from it = NT-1 on a drifted
@@ -475,30 +513,6 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 const uint32_t prow = (uint32_t)(it - NT + 1);  // the output row this kick completes
                 const float seq = __uint_as_float(prow + 1);
                 const uint32_t post_a = post_me + (prow & (kMail8 - 1)) * 16;
-                // k1[i] = wake-kicked cell ycol + f2 + i (src/SM/KickMap.cpp:243-266), 0 outside the grid
-                float k1[11];
-#pragma unroll
-                for (int i = 0; i < 11; i++) k1[i] = tap4<FMA>(in[i], in[i + 1], in[i + 2], in[i + 3], w1);
-                if (edge_warp) {
-                    const int f2 = f2row;
-                    const int m0 = (int)ycol + f2;
-                    if (NW > 1 && f2 >= -3 && f2 <= 1) {
-                        // only the block's first 3 (left edge of the grid) or last 4 (right edge) can lie outside
-                        if (warp == 0) {
-#pragma unroll
-                            for (int i = 0; i < 3; i++)
-                                if (m0 + i < 0) k1[i] = 0.0f;
-                        } else {
-#pragma unroll
-                            for (int i = 7; i < 11; i++)
-                                if (m0 + i >= (int)n) k1[i] = 0.0f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 11; i++)
-                            if ((uint32_t)(m0 + i) >= n) k1[i] = 0.0f;
-                    }
-                }
                 // has the neighbours' post for the stencil's row arrived?  Asked here, used after the drift
                 if (FP) arrived = __all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == orow + 1);
                 float kq[8];
@@ -523,6 +537,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                                        make_float4(l0 ? d[0] : seq, l0 ? d[1] : 0.0f, l0 ? seq : d[6], l0 ? 0.0f : d[7]),
                                        l0 || lane == 31);
                 }
+                wake_kick();  // of the row just loaded, for the next iteration
             }
             if (FP) {
                 const uint32_t want = orow + 1;
@@ -588,6 +603,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         cp_async_wait<kSlots8 - 2>();
         __syncwarp();
         load_row(0);
+        wake_kick();
         const int n_stage = nkicks - (kSlots8 - 1);  // iterations that still have a row to request
         int it = 0;
 #pragma unroll 1
@@ -595,6 +611,13 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             if (it < n_stage) iter(it, no, yes, yes);
             else iter(it, no, yes, no);
         }
+#if IVS_S8_UNROLL2
+#pragma unroll 1
+        for (; it + 1 < n_stage; it += 2) {  // steady state, two rows per trip
+            iter(it, yes, yes, yes);
+            iter(it + 1, yes, yes, yes);
+        }
+#endif
 #pragma unroll 1
         for (; it < n_stage; it++) iter(it, yes, yes, yes);  // steady state
 #pragma unroll 1
