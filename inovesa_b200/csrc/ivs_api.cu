@@ -59,7 +59,11 @@ ivs_status ivs_ctx_create(int device, int arith, ivs_ctx** out) {
         return ivs_fail(nullptr, IVS_ERR_UNSUPPORTED, "ivs_ctx_create: kernels are built for sm_100a (Blackwell B200) only");
     }
     ctx->sm_count = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return ivs_check_cuda(nullptr, e, "cudaStreamCreate"); }
+    // the context's stream is the most urgent one: side streams of a simulation (tracked particles) only
+    // get the SMs it leaves idle
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_lo = prio_hi = 0;
+    if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { delete ctx; return ivs_check_cuda(nullptr, e, "cudaStreamCreate"); }
     if ((e = cudaMalloc((void**)&ctx->scratch, 4096)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return ivs_check_cuda(nullptr, e, "cudaMalloc"); }
     *out = ctx;
     return IVS_OK;

@@ -1529,7 +1529,14 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
     a.out = s->grid[s->cur ^ 1];
     a.rho_in = s->profile[s->pcur];
     a.rho_out = s->profile[s->pcur ^ 1];
-    a.wake_out = s->wake;
+    // with tracked particles on the side stream the steps alternate between two wake buffers
+    const int wb = s->track_overlap ? s->cur : 0;
+    a.wake_out = s->wakebuf[wb];
+    a.wb = wb;
+    if (s->track_inflight[wb]) {  // the tracking launch that still reads this buffer (two steps ago)
+        IVS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_track[wb], 0));
+        s->track_inflight[wb] = false;
+    }
     a.wakefn = s->wakefunction;
     a.wakescaling = s->wakescaling;
     a.rf_first = (const int*)plan->rf_first; a.rf_w = (const float4*)plan->rf_w;
@@ -1587,9 +1594,33 @@ launched:
     s->cur ^= 1;
     s->pcur ^= 1;
     if (s->np) {
-        st = ivs_track_step_launch(ctx, s->particles, s->np, s->members, s->n, s->has_wake ? s->wake : nullptr,
-                                   s->rf, s->drift, s->has_fp ? s->fpw : nullptr, nullptr, s->desc.fptrack,
-                                   s->desc.e1, s->desc.dp, s->desc.seed, s->track_counter, s->status);
+        if (s->track_overlap) {
+            // the particles' step runs beside the NEXT fused step (it only needs this step's wake
+            // potential and the static tables), on a low-priority stream that fills the SMs the step
+            // kernel's last round of CTAs leaves idle
+            IVS_CUDA(ctx, cudaEventRecord(s->ev_step, ctx->stream));
+            IVS_CUDA(ctx, cudaStreamWaitEvent(s->side, s->ev_step, 0));
+            st = ivs_track_step_launch(ctx, s->particles, s->np, s->members, s->n, s->has_wake ? s->wakebuf[wb] : nullptr,
+                                       s->rf, s->drift, s->has_fp ? s->fpw : nullptr, nullptr, s->desc.fptrack,
+                                       s->desc.e1, s->desc.dp, s->desc.seed, s->track_counter, s->status, wb, s->side);
+            if (st != IVS_OK) return st;
+            IVS_CUDA(ctx, cudaEventRecord(s->ev_track[wb], s->side));
+            s->track_inflight[wb] = true;
+        } else {
+            st = ivs_track_step_launch(ctx, s->particles, s->np, s->members, s->n, s->has_wake ? s->wakebuf[wb] : nullptr,
+                                       s->rf, s->drift, s->has_fp ? s->fpw : nullptr, nullptr, s->desc.fptrack,
+                                       s->desc.e1, s->desc.dp, s->desc.seed, s->track_counter, s->status);
+        }
     }
     return st;
+}
+
+ivs_status ivs_fused_join(ivs_ctx* ctx, ivs_sim* s) {
+    for (int b = 0; b < 2; b++) {
+        if (s->track_inflight[b]) {
+            IVS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_track[b], 0));
+            s->track_inflight[b] = false;
+        }
+    }
+    return IVS_OK;
 }

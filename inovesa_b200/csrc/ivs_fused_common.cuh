@@ -26,6 +26,7 @@ struct fused_args {
     int* host_flag;  // host-mapped copy of "status[0] is set" (read by the host without a sync)
     uint32_t n, it, hl, hr, pitch;
     int has_wake;
+    int wb;          // which of the two wake buffers wake_out is: status[2 + wb] = ordinal of this step
 };
 
 struct stream_args {
@@ -89,6 +90,11 @@ constexpr int kStatusClean = 0x7fffffff;
 __device__ __forceinline__ void step_ctl_begin(const fused_args& g, int* ctl) {
     ctl[0] = *reinterpret_cast<volatile int*>(g.status);
     ctl[1] = (int)atomicAdd(reinterpret_cast<unsigned int*>(g.status) + 1, 1u);
+    // the step's first ticket notes which step fills wake buffer wb: the tracking kernel that reads
+    // the buffer (possibly while the NEXT step runs and overflows) only stands down if this step
+    // or an earlier one overflowed
+    const unsigned int ctas = gridDim.x * gridDim.y;
+    if ((unsigned int)ctl[1] % ctas == 0) g.status[2 + g.wb] = (int)((unsigned int)ctl[1] / ctas);
 }
 __device__ __forceinline__ void step_ctl_overflow(const fused_args& g, const int* ctl) {
     const unsigned int ord = (unsigned int)ctl[1] / (gridDim.x * gridDim.y);

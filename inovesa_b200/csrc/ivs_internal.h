@@ -48,7 +48,7 @@ ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, ui
                                  uint32_t n, const float* wake, const float* rf, const float* drift,
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
                                  float dp, uint64_t seed, unsigned int* step_counter,
-                                 const int* sim_status = nullptr);
+                                 const int* sim_status = nullptr, int wb = -1, cudaStream_t stream = nullptr);
 
 // DynamicRFKickMap: one block that turns the next (phase, amplitude) entry of the device queue into
 // KickMap::_offset and the fused kernels' tap tables (ivs_dynrf.cu)
@@ -79,5 +79,7 @@ struct ivs_fused_plan {
 ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan);
 void ivs_fused_plan_destroy(ivs_fused_plan* plan);
 ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s);
+// tracking launches that overlap the following step (side stream) are joined into the context's stream
+ivs_status ivs_fused_join(ivs_ctx* ctx, ivs_sim* s);
 // new RF kick offsets: rebuild the fused kernels' tap tables in place (same device buffers)
 ivs_status ivs_fused_plan_set_rf(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s, const float* rf_offset);

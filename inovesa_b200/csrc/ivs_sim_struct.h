@@ -11,7 +11,15 @@ struct ivs_sim {
     int cur = 0;                                   // index of the buffer holding grid_t1
     float* profile[2] = {nullptr, nullptr};        // X projection (double buffered for the fused path)
     int pcur = 0;
-    float* wake = nullptr;        // [members][n] offsets applied by the last wake kick
+    float* wake = nullptr;        // [members][n] offsets applied by the last wake kick (== wakebuf[0])
+    // Fused steps with tracked particles alternate between two wake buffers (index = cur of the step)
+    // so that the tracking kernel of step t can run on a low-priority side stream while step t + 1
+    // already fills the other buffer; ev_track[b] = "the tracking launch that reads buffer b is done"
+    float* wakebuf[2] = {nullptr, nullptr};
+    bool track_overlap = false;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_step = nullptr, ev_track[2] = {nullptr, nullptr};
+    bool track_inflight[2] = {false, false};
     float* rf = nullptr;          // [n]
     float* drift = nullptr;       // [n]
     float* fpw = nullptr;         // [n][5]

@@ -97,6 +97,8 @@ ivs_status capture(ivs_sim* s, uint32_t steps, cudaGraphExec_t* out) {
         st = enqueue_step(s);
         s->steps_done++;
     }
+    if (st == IVS_OK) st = ivs_fused_join(ctx, s);  // the side stream's launches rejoin the captured stream
+    s->track_inflight[0] = s->track_inflight[1] = false;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
     // capture only records; restore the bookkeeping it advanced
     s->cur = cur0; s->pcur = pcur0; ctx->launches = launches0; s->steps_done = done0; s->fused_enqueued = enq0;
@@ -171,6 +173,21 @@ ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* d, ivs_sim** out) {
     S_TRY(dalloc(ctx, &s->profile[0], (size_t)m * n));
     S_TRY(dalloc(ctx, &s->profile[1], (size_t)m * n));
     S_TRY(dalloc(ctx, &s->wake, (size_t)m * n));
+    s->wakebuf[0] = s->wakebuf[1] = s->wake;
+    // tracked particles of a fused run step on a side stream, overlapping the next step (not with a
+    // DynamicRFKickMap, whose per-step kernel rewrites the RF offsets the particles read)
+    s->track_overlap = !unfused && d->n_particles > 0 && !(d->flags & IVS_SIM_TRACK_INLINE);
+    if (s->track_overlap) {
+        S_TRY(dalloc(ctx, &s->wakebuf[1], (size_t)m * n));
+        S_TRY(ivs_memset_zero(ctx, s->wakebuf[1], (size_t)m * n * sizeof(float)));
+        int lo = 0, hi = 0;
+        cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least urgent
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_track[0], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_track[1], cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail(ivs_check_cuda(ctx, e, "side stream of the tracking kernel"));
+    }
     S_TRY(dalloc(ctx, &s->rf, n));
     S_TRY(dalloc(ctx, &s->drift, n));
     S_TRY(dalloc(ctx, &s->fpw, (size_t)n * 5));
@@ -252,6 +269,10 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
     cudaStreamSynchronize(s->ctx->stream);
     drop_graphs(s);
     ivs_fused_plan_destroy(&s->plan);
+    if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+    if (s->ev_step) cudaEventDestroy(s->ev_step);
+    for (int b = 0; b < 2; b++) if (s->ev_track[b]) cudaEventDestroy(s->ev_track[b]);
+    if (s->wakebuf[1] && s->wakebuf[1] != s->wake) cudaFree(s->wakebuf[1]);
     float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
                      s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
                      (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power,
@@ -299,7 +320,7 @@ static ivs_status enqueue_steps(ivs_sim* s, uint32_t nsteps) {
         if (!unfused) s->fused_enqueued++;
         left--;
     }
-    return IVS_OK;
+    return ivs_fused_join(ctx, s);
 }
 
 static ivs_status reset_status(ivs_sim* s) {
@@ -351,6 +372,9 @@ static ivs_status settle(ivs_sim* s) {
                                      s->rf, (int*)s->plan.rf_first, s->plan.rf_w, (int*)(s->rf_pos + 1), -16, 12));
         }
         IVS_TRY(enqueue_unfused_step(s));
+        // the kernel sequence leaves its wake in buffer 0: both buffers hold the last step's wake
+        if (s->wakebuf[1] != s->wake)
+            IVS_CUDA(ctx, cudaMemcpyAsync(s->wakebuf[1], s->wake, (size_t)s->members * s->n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
         s->steps_done++;
         s->fallback_steps++;
         if (redo > 1) IVS_TRY(enqueue_steps(s, (uint32_t)(redo - 1)));
@@ -368,6 +392,9 @@ ivs_status ivs_sim_step(ivs_sim* s, uint32_t nsteps) {
     return enqueue_steps(s, nsteps);
 }
 
+// the wake buffer the last executed step filled (fused steps with tracked particles alternate)
+static float* last_wake(const ivs_sim* s) { return s->track_overlap ? s->wakebuf[s->cur ^ 1] : s->wake; }
+
 uint64_t ivs_sim_steps_done(const ivs_sim* s) { return s ? s->steps_done : 0; }
 uint64_t ivs_sim_fallback_steps(const ivs_sim* s) { return s ? s->fallback_steps : 0; }
 
@@ -377,7 +404,7 @@ ivs_status ivs_sim_state(ivs_sim* s, void** d_grid, void** d_profile, void** d_w
     IVS_TRY(settle(s));
     if (d_grid) *d_grid = s->grid[s->cur];
     if (d_profile) *d_profile = s->profile[s->pcur];
-    if (d_wake) *d_wake = s->wake;
+    if (d_wake) *d_wake = last_wake(s);
     if (d_particles) *d_particles = s->particles;
     return IVS_OK;
 }
@@ -389,7 +416,7 @@ ivs_status ivs_sim_download(ivs_sim* s, float* grid, float* profile, float* wake
     IVS_TRY(settle(s));
     if (grid) IVS_CUDA(ctx, cudaMemcpyAsync(grid, s->grid[s->cur], m * n * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (profile) IVS_CUDA(ctx, cudaMemcpyAsync(profile, s->profile[s->pcur], m * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (wake) IVS_CUDA(ctx, cudaMemcpyAsync(wake, s->wake, m * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (wake) IVS_CUDA(ctx, cudaMemcpyAsync(wake, last_wake(s), m * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (particles && s->np) IVS_CUDA(ctx, cudaMemcpyAsync(particles, s->particles, m * s->np * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     IVS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IVS_OK;
@@ -516,6 +543,12 @@ ivs_status ivs_sim_set_rf_modulation(ivs_sim* s, const ivs_rf_model* model, cons
     const bool was = s->dyn_rf;
     if (s->rf_seq) { cudaFree(s->rf_seq); s->rf_seq = nullptr; }
     s->dyn_rf = count != 0;
+    // the per-step RF kernel rewrites the offsets the particles read: their step runs in line then
+    if (s->side) {
+        if (s->track_overlap && s->dyn_rf && s->wakebuf[s->cur ^ 1] != s->wake)  // the last step's wake moves to buffer 0
+            IVS_CUDA(ctx, cudaMemcpyAsync(s->wake, s->wakebuf[1], (size_t)s->members * s->n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        s->track_overlap = !s->dyn_rf;
+    }
     s->rf_seq_len = count;
     s->rf_step0 = s->steps_done;
     if (s->dyn_rf) {

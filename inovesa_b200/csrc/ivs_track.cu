@@ -169,11 +169,17 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
                                   const float* __restrict__ drift, const float* __restrict__ w5,
                                   const float* __restrict__ grid, uint32_t fptrack, float e1,
                                   float sigma, uint64_t seed, unsigned int* counter,
-                                  const int* __restrict__ sim_status) {
+                                  const int* sim_status, int wb) {
     constexpr int P = kTrackPerThread;
     // the fused step this launch belongs to (or an earlier one) left its staged pad and will be
     // redone by the host: the particles stay where they are (ivs_fused.cu, step_ctl_begin)
-    if (sim_status && *sim_status != 0x7fffffff) return;
+    // (wb >= 0: this launch may overlap the NEXT fused step; it stands down only if the step that
+    // filled wake buffer wb, or an earlier one, is the one that overflowed)
+    if (sim_status) {
+        const volatile int* st = sim_status;
+        const int first_bad = st[0];
+        if (wb < 0 ? first_bad != 0x7fffffff : first_bad <= st[2 + wb]) return;
+    }
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t member = blockIdx.y;
     const bool stochastic = w5 && fptrack == 3;
@@ -248,13 +254,15 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
 ivs_status ivs_track_step_launch(ivs_ctx* ctx, float* particles, uint32_t np, uint32_t members,
                                  uint32_t n, const float* wake, const float* rf, const float* drift,
                                  const float* fpw, const float* grid_fp_in, uint32_t fptrack, float e1,
-                                 float dp, uint64_t seed, unsigned int* step_counter, const int* sim_status) {
+                                 float dp, uint64_t seed, unsigned int* step_counter, const int* sim_status,
+                                 int wb, cudaStream_t stream) {
     if (np == 0) return IVS_OK;
+    if (!stream) stream = ctx->stream;
     const uint32_t quarter = ivs_div_up(np, kTrackPerThread);
     const float sigma = sqrtf(2.0f * e1) / dp;  // uniform, in the reference's fp32 operations
-    track_step_kernel<<<dim3(ivs_div_up(quarter, 256), members), 256, 0, ctx->stream>>>(
+    track_step_kernel<<<dim3(ivs_div_up(quarter, 256), members), 256, 0, stream>>>(
         (float2*)particles, np, quarter, n, wake, rf, drift, fpw, grid_fp_in, fptrack, e1, sigma, seed,
-        step_counter, sim_status);
+        step_counter, sim_status, wb);
     IVS_LAUNCHED(ctx);
     return IVS_OK;
 }
