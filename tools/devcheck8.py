@@ -17,6 +17,7 @@ from devcheck import CASES, states  # noqa: E402
 
 if __name__ == "__main__":
     capi.load()
+    NEW = getattr(capi, "SIM_" + os.environ.get("IVS_DEV_FLAG", "STREAM8"))  # the kernel under test
     sizes = [int(a) for a in sys.argv[1:]] or [256, 512, 768, 1024, 2048, 2049]
     ok = True
     for mode in (capi.ARITH_FMA, capi.ARITH_STRICT):
@@ -26,9 +27,9 @@ if __name__ == "__main__":
                 for members, strips in ((1, 0), (3, 0), (2, 5)):
                     t0 = time.time()
                     a = states(ctx, p, capi.SIM_QPT2, [1, 7, 24], members)
-                    b = states(ctx, p, capi.SIM_STREAM8, [1, 7, 24], members) if strips == 0 else None
+                    b = states(ctx, p, NEW, [1, 7, 24], members) if strips == 0 else None
                     if b is None:
-                        sim = capi.Simulation(ctx, p, members, flags=capi.SIM_STREAM8, strips=strips)
+                        sim = capi.Simulation(ctx, p, members, flags=NEW, strips=strips)
                         b = []
                         for k in [1, 7, 24]:
                             sim.step(k)
