@@ -50,6 +50,12 @@ namespace {
 #ifndef IVS_S8_LAG
 #define IVS_S8_LAG 4
 #endif
+#ifndef IVS_S8_PROBE_NOSTAGE
+#define IVS_S8_PROBE_NOSTAGE 0  // timing probes (wrong results): no copies into the ring / no global stores
+#endif
+#ifndef IVS_S8_PROBE_NOSTORE
+#define IVS_S8_PROBE_NOSTORE 0
+#endif
 #ifndef IVS_S8_UNROLL2
 #define IVS_S8_UNROLL2 0
 #endif
@@ -119,7 +125,6 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
     // per input row: wake taps, RF taps, (f1 + f2, f2, -, -)
     float4* tab = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 48));
     float4* mail = reinterpret_cast<float4*>(carve((size_t)NW * 2 * kMail8 * 16));  // [warp][side][slot]
-    float4* zeroq = reinterpret_cast<float4*>(carve(16));                           // the quad beyond the grid's ends
 
     const float* gin = g.in + (size_t)member * n * n;
 
@@ -137,24 +142,25 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
 #pragma unroll
         for (int c = 0; c < 8; c++) dwl[c] = __ldg(&g.dr_w[ycol + c]);
     }
-    // stencil stage: quads (cb / 4) + 32 j + lane, j = 0, 1
-    float w5[2][4][5];
-    float4 ws4[2];
+    // stencil stage: the same 8 columns (the lane's own drifted values never leave the lane)
+    float w5[8][5];
+    float ws8[8];
+    {
+        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)ycol * 5);
+        float t[40];
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const uint32_t qf = (cb >> 2) + 32 * j + lane;
-        const float4* wp = reinterpret_cast<const float4*>(g.fp_w5 + (size_t)qf * 20);
-        float t[20];
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < 10; k++) {
             const float4 v = __ldg(wp + k);
             t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
         }
 #pragma unroll
-        for (int c = 0; c < 4; c++)
+        for (int c = 0; c < 8; c++)
 #pragma unroll
-            for (int k = 0; k < 5; k++) w5[j][c][k] = t[c * 5 + k];
-        ws4[j] = __ldg(reinterpret_cast<const float4*>(g.ws) + qf);
+            for (int k = 0; k < 5; k++) w5[c][k] = t[c * 5 + k];
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(g.ws + ycol));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(g.ws + ycol) + 1);
+        ws8[0] = wa.x; ws8[1] = wa.y; ws8[2] = wa.z; ws8[3] = wa.w;
+        ws8[4] = wb.x; ws8[5] = wb.y; ws8[6] = wb.z; ws8[7] = wb.w;
     }
     // last step's profile and the first batch of the wake-function window are requested in the same
     // round trip (T = n / 8 threads: 8 profile entries and 10 window entries each).
@@ -184,10 +190,9 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
     // another path and re-enqueues what follows): nothing may be written any more
     if (ctl[0] != kStatusClean) return;
 
-    // ---- set-up: mailboxes, the zero quad, per-row tables, last step's profile and the wake-function
+    // ---- set-up: mailboxes, per-row tables, last step's profile and the wake-function
     // window in shared memory
     for (uint32_t i = tid; i < NW * 2 * kMail8; i += T) mail[i] = make_float4(0, 0, 0, 0);  // seq 0 = nothing posted
-    if (tid == 0) zeroq[0] = make_float4(0, 0, 0, 0);
     if (tid < RIN) {
         tab[3 * tid + 1] = pre_w2;
         tab[3 * tid + 2] = make_float4(0.0f, __int_as_float(pre_f2), 0.0f, 0.0f);
@@ -317,21 +322,15 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
     const uint32_t post_me = mail_b + (warp * 2 + (lane == 0 ? 0 : 1)) * kMail8 * 16;
     const bool edge_l = lane == 0 && warp > 0, edge_r = lane == 31 && warp + 1 < NW;
     const bool edge = edge_l || edge_r;
-    // the two quads beyond the block's ends: the neighbour's post, or zeros beyond the grid
-    const bool spec_l = lane == 0, spec_r = lane == 31;
-    const uint32_t spec_base = edge_l   ? mail_b + ((warp - 1) * 2 + 1) * kMail8 * 16
-                               : edge_r ? mail_b + ((warp + 1) * 2 + 0) * kMail8 * 16
-                                        : smem_u32(zeroq);
-    const uint32_t spec_mask = edge ? (kMail8 - 1) * 16 : 0;
-    // stencil-stage offsets inside a FIFO row: own quad (j = 0), its left and right neighbours
-    const uint32_t own_off = (lane & 1) ? kOddB + (lane >> 1) * 16 : (lane >> 1) * 16;
-    const int nb_l = (lane & 1) ? -(int)kOddB : (int)kOddB - 16;
-    const int nb_r = (lane & 1) ? 16 - (int)kOddB : (int)kOddB;
+    // the two cells beyond each end of the block come from the neighbour warps' posts (zeros beyond the grid)
+    const uint32_t peek = edge_l   ? mail_b + ((warp - 1) * 2 + 1) * kMail8 * 16
+                          : edge_r ? mail_b + ((warp + 1) * 2 + 0) * kMail8 * 16
+                                   : mail_b;
     const bool edge_warp = warp == 0 || warp + 1 == NW;
     const bool strip_edge = xs < 0 || xs + (int)RIN > (int)n;  // some of the strip's input rows lie outside the grid
     // staging: this lane's cell of every group of 32 staged cells (see the header comment)
     const uint32_t st_dst = ((lane >> 2) & 1) * kOddB + ((lane >> 3) * 4 + (lane & 3)) * 4;
-    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + (cb >> 2) + lane;
+    float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + (cb >> 2) + 2 * lane;
 
     auto run = [&](auto nt_tag) {
         constexpr int NT = decltype(nt_tag)::value;
@@ -371,7 +370,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             const float* src = srow + fs;
             // rows outside the grid (first and last strip of a member) are not copied: their RF taps are
             // zeros and the slots of such a strip were cleared during the set-up
-            if (!strip_edge || (uint32_t)sx < n) {
+            if (!IVS_S8_PROBE_NOSTAGE && (!strip_edge || (uint32_t)sx < n)) {
                 // cells outside the grid are zeros (src-size 0: nothing is read).  Only the first 32 cells
                 // can lie left of the grid and only the last 64 right of it (|f1 + f2| <= 32), and only in
                 // the grid's first and last block; the three guards are the same code for every block so
@@ -399,32 +398,35 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
         for (int c = 0; c < 8; c++)
 #pragma unroll
             for (int t = 0; t < NT - 1; t++) P[c][t] = 0.0f;
-        float pprev[2] = {0.0f, 0.0f};  // this lane's part of the sums of the row the stencil handled last
-        // The row sums' butterfly (xor 16, 8, 4, 2, 1: the same tree per 128-column segment as everywhere
-        // else) is spread over five iterations, one level each: every iteration issues five independent
-        // shuffle + add pairs for five different rows, so no add ever waits for its shuffle.
+        float pprev[2] = {0.0f, 0.0f};  // this lane's part of the sums of the row the stencil handled last (its two quads)
+        // The row sums follow the same tree per 128-column segment as everywhere else: over the
+        // segment's 32 quads, partner quad index xor 16, 8, 4, 2, 1.  Here quad Q of a segment sits in
+        // lane Q / 2 of a half-warp (first or second quad of the lane), so the partners are lanes xor 8,
+        // 4, 2, 1 and finally the lane's other quad.  The first level also transposes: lanes with bit 3
+        // clear go on with the first quads' sums, the others with the second quads', which makes the
+        // last level one more exchange with lane xor 8.  The five levels are spread over five
+        // iterations, one level each for five different rows: every iteration issues five independent
+        // shuffle + add pairs, so no add ever waits for its shuffle.
         // lvl[k] = the sum after k + 1 levels of the row handled k + 2 stencil steps ago.
         float lvl[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        // where the row sums reduced next go: lane 0 holds segment 2 warp's, lane 16 the next one's
+        // where the finished sums go: lane 0 holds segment 2 warp's, lane 16 the next one's
         uint32_t redp = smem_u32(red) + (warp * 2 + (lane >= 16 ? 1 : 0)) * 4 - 5 * NSEG * 4;
         const bool red_lane = (lane & 15) == 0;
         const size_t gstride = (size_t)nq;
-
         auto rowsum_step = [&]() {
-            const bool upper = (lane & 16) != 0;
-            // first level: the two segments' sums are transposed into the two half-warps
-            const float send = upper ? pprev[0] : pprev[1];
-            const float keep = upper ? pprev[1] : pprev[0];
-            const float s16 = __shfl_xor_sync(0xffffffffu, send, 16);
-            const float s8 = __shfl_xor_sync(0xffffffffu, lvl[0], 8);
-            const float s4 = __shfl_xor_sync(0xffffffffu, lvl[1], 4);
-            const float s2 = __shfl_xor_sync(0xffffffffu, lvl[2], 2);
-            const float s1 = __shfl_xor_sync(0xffffffffu, lvl[3], 1);
-            const float done = __fadd_rn(lvl[3], s1);
-            lvl[3] = __fadd_rn(lvl[2], s2);
-            lvl[2] = __fadd_rn(lvl[1], s4);
-            lvl[1] = __fadd_rn(lvl[0], s8);
-            lvl[0] = __fadd_rn(keep, s16);
+            const bool second = (lane & 8) != 0;
+            const float send = second ? pprev[0] : pprev[1];
+            const float keep = second ? pprev[1] : pprev[0];
+            const float t1 = __shfl_xor_sync(0xffffffffu, send, 8);
+            const float t2 = __shfl_xor_sync(0xffffffffu, lvl[0], 4);
+            const float t3 = __shfl_xor_sync(0xffffffffu, lvl[1], 2);
+            const float t4 = __shfl_xor_sync(0xffffffffu, lvl[2], 1);
+            const float t5 = __shfl_xor_sync(0xffffffffu, lvl[3], 8);
+            const float done = __fadd_rn(lvl[3], t5);
+            lvl[3] = __fadd_rn(lvl[2], t4);
+            lvl[2] = __fadd_rn(lvl[1], t3);
+            lvl[1] = __fadd_rn(lvl[0], t2);
+            lvl[0] = __fadd_rn(keep, t1);
             return done;
         };
         // What crosses from one iteration to the next: the wake-kicked cells k1 of the row the next
@@ -490,21 +492,17 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             __syncwarp();  // ... and everybody's; the FIFO row written an iteration ago is visible; slot it-1 is free
             if (STAGE) stage(it + kSlots8 - 1);
             else if (KICK) cp_async_commit();  // keeps the group count in step
-            float4 o0, o1, r0q, l1q, l0q, r1q;
-            uint32_t la = 0, ra = 0;
+            // the stencil's row: the lane's own 8 drifted values out of its FIFO entry (written by this
+            // lane kLag8 iterations ago), the edge lanes' neighbours out of the mailbox
+            float4 fa, fb, mb;
+            uint32_t pa = 0;
             if (FP) {
-                const uint32_t fo = frow + own_off;
-                o0 = lds128(fo);
-                o1 = lds128(fo + 256);
-                r0q = lds128(fo + nb_r);
-                l1q = lds128(fo + 256 + nb_l);
-                const uint32_t sp_a = spec_base + ((orow * 16) & spec_mask);
-                la = spec_l ? sp_a : fo + nb_l;
-                ra = spec_r ? sp_a : fo + 256 + nb_r;
-                l0q = lds128_volatile(la);
-                r1q = lds128_volatile(ra);
+                fa = lds128(frow + lane * 16);
+                fb = lds128(frow + kOddB + lane * 16);
+                pa = peek + ((orow * 16) & ((kMail8 - 1) * 16));
+                mb = make_float4(0, 0, 0, 0);
+                if (edge) mb = lds128_volatile(pa);
             }
-            __syncwarp();  // the stencil's reads of FIFO row `frow` precede the drift's writes to it
             // one level of the row sums' butterfly for each of the last five rows (see lvl above)
             float ps = 0.0f;
             if (FP) ps = rowsum_step();
@@ -514,7 +512,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 const float seq = __uint_as_float(prow + 1);
                 const uint32_t post_a = post_me + (prow & (kMail8 - 1)) * 16;
                 // has the neighbours' post for the stencil's row arrived?  Asked here, used after the drift
-                if (FP) arrived = __all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == orow + 1);
+                if (FP) arrived = __all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? mb.x : mb.z) == orow + 1);
                 float kq[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) kq[c] = tap4<FMA>(k1[c], k1[c + 1], k1[c + 2], k1[c + 3], w2);  // RF kick, same loop
@@ -541,53 +539,49 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
             }
             if (FP) {
                 const uint32_t want = orow + 1;
-                if (!KICK) arrived = __all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want);
+                if (!KICK) arrived = __all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? mb.x : mb.z) == want);
                 if (!arrived) {
                     // the neighbour is more than kLag8 - 1 rows behind: poll
                     uint32_t tries = 0;
                     do {
-                        if (edge_l) l0q = lds128_volatile(la);
-                        if (edge_r) r1q = lds128_volatile(ra);
+                        if (edge) mb = lds128_volatile(pa);
                         if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
-                    } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == want));
+                    } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? mb.x : mb.z) == want));
                 }
+                // the two cells left and right of the lane's 8: the neighbour lanes', the posts at the
+                // block's ends (left post = (seq, -, z, w), right post = (x, y, seq, -)), zeros beyond the grid
+                float lz = __shfl_up_sync(0xffffffffu, fb.z, 1), lw = __shfl_up_sync(0xffffffffu, fb.w, 1);
+                float rx = __shfl_down_sync(0xffffffffu, fa.x, 1), ry = __shfl_down_sync(0xffffffffu, fa.y, 1);
+                if (lane == 0) { lz = mb.z; lw = mb.w; }
+                if (lane == 31) { rx = mb.x; ry = mb.y; }
                 // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
-                float o[2][4];
-#define IVS_FP_COL(j, c)                                                 \
-                {                                                        \
-                    float v = __fmul_rn(fin[c], w5[j][c][0]);            \
-                    v = madd<FMA>(fin[1 + c], w5[j][c][1], v);           \
-                    v = madd<FMA>(fin[2 + c], w5[j][c][2], v);           \
-                    v = madd<FMA>(fin[3 + c], w5[j][c][3], v);           \
-                    v = madd<FMA>(fin[4 + c], w5[j][c][4], v);           \
-                    o[j][c] = v;                                         \
+                const float fin[12] = {lz, lw, fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, rx, ry};
+                float o[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    float v = __fmul_rn(fin[c], w5[c][0]);
+                    v = madd<FMA>(fin[1 + c], w5[c][1], v);
+                    v = madd<FMA>(fin[2 + c], w5[c][2], v);
+                    v = madd<FMA>(fin[3 + c], w5[c][3], v);
+                    v = madd<FMA>(fin[4 + c], w5[c][4], v);
+                    o[c] = v;
                 }
-                {
-                    const float fin[8] = {l0q.z, l0q.w, o0.x, o0.y, o0.z, o0.w, r0q.x, r0q.y};
-                    IVS_FP_COL(0, 0)
-                    IVS_FP_COL(0, 1)
-                    IVS_FP_COL(0, 2)
-                    IVS_FP_COL(0, 3)
-                    gout[0] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
-                }
-                {
-                    const float fin[8] = {l1q.z, l1q.w, o1.x, o1.y, o1.z, o1.w, r1q.x, r1q.y};
-                    IVS_FP_COL(1, 0)
-                    IVS_FP_COL(1, 1)
-                    IVS_FP_COL(1, 2)
-                    IVS_FP_COL(1, 3)
-                    gout[32] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
-                }
-#undef IVS_FP_COL
+#if IVS_S8_PROBE_NOSTORE
+                if (o[0] == 123.456f) gout[0] = make_float4(o[0], o[1], o[2], o[3]);
+                if (o[4] == 123.456f) gout[1] = make_float4(o[4], o[5], o[6], o[7]);
+#else
+                gout[0] = make_float4(o[0], o[1], o[2], o[3]);
+                gout[1] = make_float4(o[4], o[5], o[6], o[7]);
+#endif
                 gout += gstride;
                 if (red_lane && orow >= 5) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
                 redp += NSEG * 4;
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    float p = __fmul_rn(o[j][0], ws4[j].x);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
-                    p = __fadd_rn(p, __fmul_rn(o[j][1], ws4[j].y));
-                    p = __fadd_rn(p, __fmul_rn(o[j][2], ws4[j].z));
-                    p = __fadd_rn(p, __fmul_rn(o[j][3], ws4[j].w));
+                    float p = __fmul_rn(o[4 * j], ws8[4 * j]);  // src/PS/PhaseSpace.cpp:316-319 (products rounded)
+                    p = __fadd_rn(p, __fmul_rn(o[4 * j + 1], ws8[4 * j + 1]));
+                    p = __fadd_rn(p, __fmul_rn(o[4 * j + 2], ws8[4 * j + 2]));
+                    p = __fadd_rn(p, __fmul_rn(o[4 * j + 3], ws8[4 * j + 3]));
                     pprev[j] = p;
                 }
             }

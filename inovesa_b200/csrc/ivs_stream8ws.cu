@@ -8,12 +8,17 @@
 //                applied by the copy, warp-private ring), wake kick + RF kick on 8 adjacent columns
 //                per lane, drift as running sums, drifted row -> the block's row FIFO in shared memory;
 //   stencil warp reads the FIFO row in the quad-per-lane mapping (neighbour quads from the same row,
-//                the two quads beyond the block's ends from the neighbour blocks' FIFO rows),
+//                the two quads beyond the block's ends from the neighbour blocks' mailboxes),
 //                Fokker-Planck, STG.128, Simpson-weighted row sums.
 //
 // A FIFO row changes hands through a pair of mbarriers (full: the kick warp's lane 0 arrives after the
-// warp's stores; empty: the up to three stencil warps that read the row arrive after their loads),
-// which also carry the release / acquire ordering between the warps.  Nothing else couples warps.
+// warp's stores; empty: the block's stencil warp arrives after its loads), which also carry the
+// release / acquire ordering between the two warps of a block.  Blocks only meet in the mailboxes
+// (kMailW rows deep, sequence stamp = row, as in ivs_stream8.cu): a stencil warp needs the two
+// neighbour kick warps to have posted its row, nothing ever waits for another block's stencil warp.
+// A kick warp runs at most kDepthW rows ahead of its own stencil warp and that one never ahead of the
+// neighbours' kick warps, so a post is read long before its mailbox entry comes round again
+// (kMailW > 2 kDepthW).
 //
 // Why: stream8_step_kernel needs 255 registers per thread, i.e. 8 warps per SM, two per scheduler,
 // and is bound by the latency of each warp's own instruction stream (51 % of the issue slots used).
@@ -43,6 +48,7 @@ namespace {
 #endif
 constexpr int kSlotsW = IVS_WS_SLOTS;  // staged rows per kick warp (ring depth, a power of two)
 constexpr int kDepthW = IVS_WS_DEPTH;  // rows of a block's FIFO (a power of two)
+constexpr int kMailW = 32;             // mailbox depth per block edge (> 2 kDepthW)
 constexpr uint32_t kSlotB = 1152;      // bytes per slot / FIFO row: even quads at 0 (33 quads), odd quads at kOddB
 constexpr uint32_t kOddB = 576;        // 144 floats: 16 banks away from the even half
 
@@ -81,11 +87,26 @@ template <int REGS>
 __device__ __forceinline__ void reg_dealloc() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
 }
-// blocking wait on an mbarrier phase (a row that never comes is a bug: trap instead of hanging the GPU)
+// blocking wait on an mbarrier phase; the warp is suspended by the hardware (up to the hint, in ns) instead
+// of spinning in the issue slots of the warps it waits for (a row that never comes is a bug: trap
+// instead of hanging the GPU)
+#ifndef IVS_WS_HINT
+#define IVS_WS_HINT 2000
+#endif
+#ifndef IVS_WS_SLEEP
+#define IVS_WS_SLEEP 100
+#endif
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t phase) {
     uint32_t tries = 0;
-    while (!mbar_try(bar, phase)) {
-        if (++tries > (1u << 22)) __trap();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(bar), "r"(phase), "r"((uint32_t)IVS_WS_HINT)
+            : "memory");
+        if (ok) break;
+        if (++tries > (1u << 20)) __trap();
     }
 }
 
@@ -122,6 +143,7 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
     // per input row: wake taps, RF taps, (f1 + f2, f2, -, -)
     float4* tab = reinterpret_cast<float4*>(carve((size_t)(sa.max_rin + 1) * 48));
     float4* zeroq = reinterpret_cast<float4*>(carve(16));                        // the quad beyond the grid's ends
+    float4* mail = reinterpret_cast<float4*>(carve((size_t)NB * 2 * kMailW * 16));   // [block][side][row mod kMailW]
     uint64_t* full = reinterpret_cast<uint64_t*>(carve((size_t)NB * kDepthW * 8));   // [block][row mod kDepthW]
     uint64_t* empty = reinterpret_cast<uint64_t*>(carve((size_t)NB * kDepthW * 8));
 
@@ -130,9 +152,8 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
     if (tid == 0) step_ctl_begin(g, ctl);
     if (tid < NB * kDepthW) {
         const uint32_t blk = tid / kDepthW;
-        const uint32_t readers = 1 + (blk > 0 ? 1 : 0) + (blk + 1 < NB ? 1 : 0);  // stencil warps that read the row
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(full + tid)), "r"(1u));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + tid)), "r"(readers));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + tid)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // last step's profile and the first batch of the wake-function window are requested in the same
@@ -166,6 +187,7 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
     // ---- set-up: the zero quad, per-row tables, last step's profile and the wake-function
     // window in shared memory
     if (tid == 0) zeroq[0] = make_float4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < NB * 2 * kMailW; i += T) mail[i] = make_float4(0, 0, 0, 0);  // seq 0 = nothing posted
     if (tid < RIN) {
         tab[3 * tid + 1] = pre_w2;
         tab[3 * tid + 2] = make_float4(0.0f, __int_as_float(pre_f2), 0.0f, 0.0f);
@@ -275,10 +297,13 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
 
     const uint32_t tab_b = smem_u32(tab);
     const uint32_t full_b = smem_u32(full), empty_b = smem_u32(empty);
-    if (warp < NB) {
+    // The schedulers favour the warp with the highest index among the eligible ones: the kick warps,
+    // whose row takes longer, are the upper half of the CTA, so a stencil warp that polls for its
+    // neighbours never takes an issue slot a kick warp could use.
+    if (warp >= NB) {
         // =============================== kick warps ============================================
         reg_alloc<IVS_WS_KREGS>();
-        const uint32_t blk = warp;
+        const uint32_t blk = warp - NB;
         const uint32_t cb = blk * 256;
         const uint32_t ycol = cb + 8 * lane;  // this lane's columns: ycol + 0..7
         int dfs[8];
@@ -307,6 +332,9 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
         const uint32_t fifo_w = smem_u32(fifo) + blk * (kDepthW * kSlotB);
         const uint32_t full_w = full_b + blk * (kDepthW * 8), empty_w = empty_b + blk * (kDepthW * 8);
         const bool edge_warp = blk == 0 || blk + 1 == NB;
+        // mailboxes: lane 0 posts (x, y) of the block's first quad for the left neighbour, lane 31 (z, w) of
+        // its last quad for the right neighbour
+        const uint32_t post_me = smem_u32(mail) + (blk * 2 + (lane == 0 ? 0 : 1)) * kMailW * 16;
         const bool strip_edge = xs < 0 || xs + (int)RIN > (int)n;  // some of the strip's input rows lie outside the grid
         // staging: this lane's cell of every group of 32 staged cells (see ivs_stream8.cu)
         const uint32_t st_dst = ((lane >> 2) & 1) * kOddB + ((lane >> 3) * 4 + (lane & 3)) * 4;
@@ -445,6 +473,13 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
                     const uint32_t frow = fifo_w + slot * kSlotB + lane * 16;
                     sts128(frow, d[0], d[1], d[2], d[3]);
                     sts128(frow + kOddB, d[4], d[5], d[6], d[7]);
+                    {
+                        const float seq = __uint_as_float(orow + 1);
+                        const bool l0 = lane == 0;
+                        sts128_volatile_if(post_me + (orow & (kMailW - 1)) * 16,
+                                           make_float4(l0 ? d[0] : seq, l0 ? d[1] : 0.0f, l0 ? seq : d[6], l0 ? 0.0f : d[7]),
+                                           l0 || lane == 31);
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_addr(full_w + slot * 8);
                 }
@@ -474,7 +509,7 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
     } else {
         // =============================== stencil warps =========================================
         reg_dealloc<IVS_WS_FREGS>();
-        const uint32_t blk = warp - NB;
+        const uint32_t blk = warp;
         const uint32_t cb = blk * 256;
         // quads (cb / 4) + 32 j + lane, j = 0, 1
         float w5[2][4][5];
@@ -502,12 +537,14 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
         const uint32_t own_off = (lane & 1) ? kOddB + (lane >> 1) * 16 : (lane >> 1) * 16;
         const int nb_l = (lane & 1) ? -(int)kOddB : (int)kOddB - 16;
         const int nb_r = (lane & 1) ? 16 - (int)kOddB : (int)kOddB;
-        // the two quads beyond the block's ends: quad 63 of the left block's FIFO row (odd half, entry
-        // 31), quad 0 of the right block's; zeros beyond the grid (stride 0)
+        // the two quads beyond the block's ends: the neighbour kick warps' posts, or zeros beyond the grid
         const bool spec_l = lane == 0, spec_r = lane == 31;
-        const uint32_t spec_base = spec_l ? (has_l ? fifo_w - kDepthW * kSlotB + kOddB + 31 * 16 : smem_u32(zeroq))
-                                          : (has_r ? fifo_w + kDepthW * kSlotB : smem_u32(zeroq));
-        const uint32_t spec_stride = (spec_l ? has_l : has_r) ? kSlotB : 0;
+        const bool edge_l = spec_l && has_l, edge_r = spec_r && has_r, edge = edge_l || edge_r;
+        const uint32_t mail_b = smem_u32(mail);
+        const uint32_t spec_base = edge_l   ? mail_b + ((blk - 1) * 2 + 1) * kMailW * 16
+                                   : edge_r ? mail_b + ((blk + 1) * 2 + 0) * kMailW * 16
+                                            : smem_u32(zeroq);
+        const uint32_t spec_mask = edge ? (kMailW - 1) * 16 : 0;
         float4* gout = reinterpret_cast<float4*>(g.out + ((size_t)member * n + xa) * n) + (cb >> 2) + lane;
         const size_t gstride = (size_t)nq;
         float pprev[2] = {0.0f, 0.0f};
@@ -533,16 +570,24 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
 #pragma unroll 1
         for (uint32_t orow = 0; orow < S; orow++) {
             const uint32_t slot = orow & (kDepthW - 1), par = (orow / kDepthW) & 1;
-            // the row of this block and of its neighbours (their edge quads) must have been written
-            mbar_wait_addr(full_w + slot * 8, par);
-            if (has_l) mbar_wait_addr(full_w - kDepthW * 8 + slot * 8, par);
-            if (has_r) mbar_wait_addr(full_w + kDepthW * 8 + slot * 8, par);
+            mbar_wait_addr(full_w + slot * 8, par);  // the block's kick warp has written the row
             const uint32_t fo = fifo_w + slot * kSlotB + own_off;
             const float4 o0 = lds128(fo), o1 = lds128(fo + 256);
             const float4 r0q = lds128(fo + nb_r), l1q = lds128(fo + 256 + nb_l);
-            const uint32_t sp_a = spec_base + slot * spec_stride;
-            const float4 l0q = lds128(spec_l ? sp_a : fo + nb_l);
-            const float4 r1q = lds128(spec_r ? sp_a : fo + 256 + nb_r);
+            const uint32_t sp_a = spec_base + ((orow * 16) & spec_mask);
+            const uint32_t la = spec_l ? sp_a : fo + nb_l;
+            const uint32_t ra = spec_r ? sp_a : fo + 256 + nb_r;
+            float4 l0q = lds128_volatile(la), r1q = lds128_volatile(ra);
+            if (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == orow + 1)) {
+                // a neighbour block's kick warp has not posted this row yet: poll
+                uint32_t tries = 0;
+                do {
+                    __nanosleep(IVS_WS_SLEEP);
+                    if (edge_l) l0q = lds128_volatile(la);
+                    if (edge_r) r1q = lds128_volatile(ra);
+                    if (++tries > (1u << 22)) __trap();  // a neighbour that never posts is a bug
+                } while (!__all_sync(0xffffffffu, !edge || __float_as_uint(edge_l ? l0q.x : r1q.z) == orow + 1));
+            }
             const float ps = rowsum_step();
             // Fokker-Planck (src/SM/FokkerPlanckMap.cpp:197-211)
             float o[2][4];
@@ -574,11 +619,7 @@ __global__ void __launch_bounds__(512, 1) stream8ws_step_kernel(const stream_arg
 #undef IVS_FP_COL
             // the loads have delivered (their values were used): the row may be overwritten
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_addr(empty_w + slot * 8);
-                if (has_l) mbar_arrive_addr(empty_w - kDepthW * 8 + slot * 8);
-                if (has_r) mbar_arrive_addr(empty_w + kDepthW * 8 + slot * 8);
-            }
+            if (lane == 0) mbar_arrive_addr(empty_w + slot * 8);
             gout += gstride;
             if (red_lane && orow >= 5) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
             redp += NSEG * 4;
@@ -620,7 +661,7 @@ size_t stream8ws_smem(uint32_t n, uint32_t S0, uint32_t H, uint32_t* wwin_len_ou
     if (wwin_len_out) *wwin_len_out = wwin_len;
     return a16((size_t)NB * kSlotsW * kSlotB) + a16((size_t)NB * kDepthW * kSlotB) + a16((size_t)(n + n / 32) * 8) +
            a16((size_t)wwin_len * 8) + a16((size_t)NSEG * max_rin * 8) + a16((size_t)S0 * NSEG * 4) +
-           a16((size_t)(max_rin + 1) * 48) + 16 + 2 * a16((size_t)NB * kDepthW * 8);
+           a16((size_t)(max_rin + 1) * 48) + 16 + a16((size_t)NB * 2 * kMailW * 16) + 2 * a16((size_t)NB * kDepthW * 8);
 }
 
 }  // namespace
