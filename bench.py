@@ -152,7 +152,7 @@ def run_ours(args):
     members = args.members
     arith = capi.ARITH_STRICT if args.arith == "strict" else capi.ARITH_FMA
     flags = capi.SIM_UNFUSED if args.unfused else 0
-    flags |= {0: 0, 1: capi.SIM_QPT1, 2: capi.SIM_QPT2, 8: capi.SIM_STREAM8, 16: capi.SIM_WARPSPEC}[args.qpt]
+    flags |= {0: 0, 1: capi.SIM_QPT1, 2: capi.SIM_QPT2, 8: capi.SIM_STREAM8}[args.qpt]
     ctx = capi.Context(local_rank, arith)
     stream = torch.cuda.ExternalStream(ctx.lib.ivs_ctx_stream(ctx.h), device=local_rank)
     d = capi.derive(p)
@@ -466,7 +466,7 @@ def main():
                     help="also time BASELINE configs[3] (256 x 256^2 scan, 256/N members per GPU)")
     ap.add_argument("--no-scan", dest="scan", action="store_false")
     ap.add_argument("--repeats", type=int, default=7, help="timed blocks of --steps steps; the median counts")
-    ap.add_argument("--qpt", type=int, default=0, choices=[0, 1, 2, 8, 16], help="tuning: quads of columns per thread")
+    ap.add_argument("--qpt", type=int, default=0, choices=[0, 1, 2, 8], help="tuning: quads of columns per thread")
     ap.add_argument("--strips", type=int, default=0, help="tuning: strips per member (0 = planner)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1412,8 +1412,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
     if (want8 && !(s->desc.flags & IVS_SIM_TILED) && n % 256 == 0 && n <= 2048) {
         size_t keep_smem = plan->smem;
         uint32_t keep_threads = plan->threads;
-        if (((s->desc.flags & IVS_SIM_WARPSPEC) && ivs_stream8ws_plan(ctx, s, plan, dr_first.data())) ||
-            ivs_stream8_plan(ctx, s, plan, dr_first.data())) {
+        if (ivs_stream8_plan(ctx, s, plan, dr_first.data())) {
             if (!plan->fp5) {
                 std::vector<float> fps(fpw);  // out-of-grid taps zeroed, as for the streaming kernel
                 fps[0] = fps[1] = 0.0f;
@@ -1551,7 +1550,7 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
     a.has_wake = s->has_wake ? 1 : 0;
     ivs_status st;
     if (plan->stream8) {
-        st = plan->stream8ws ? ivs_stream8ws_launch(ctx, plan, s, a) : ivs_stream8_launch(ctx, plan, s, a);
+        st = ivs_stream8_launch(ctx, plan, s, a);
         goto launched;
     }
     if (plan->stream) {

@@ -44,10 +44,6 @@ struct stream_args {
 bool ivs_stream8_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan, const int* dr_first);
 ivs_status ivs_stream8_launch(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_sim* s,
                               const ivs_fused_detail::fused_args& a);
-// the same with kick and stencil on different warps (ivs_stream8ws.cu)
-bool ivs_stream8ws_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan, const int* dr_first);
-ivs_status ivs_stream8ws_launch(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_sim* s,
-                                const ivs_fused_detail::fused_args& a);
 
 namespace {
 using ivs_fused_detail::fused_args;

@@ -72,7 +72,6 @@ struct ivs_fused_plan {
     bool stream = false;  // streaming kernel (independent warps, qpt quads of columns per thread)
     uint32_t qpt = 1;
     bool stream8 = false; // column-block kernel (ivs_stream8.cu): 8 adjacent columns per lane, private rings
-    bool stream8ws = false; // ... with kick and stencil on different warps (ivs_stream8ws.cu)
     uint32_t strip = 0, kslots = 0, max_strip = 0, max_rin = 0, wwin_len = 0;
     void* fp5 = nullptr;  // Fokker-Planck weights, out-of-grid taps zeroed (streaming kernel)
     bool ready = false;

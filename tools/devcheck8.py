@@ -17,7 +17,9 @@ from devcheck import CASES, states  # noqa: E402
 
 if __name__ == "__main__":
     capi.load()
-    NEW = getattr(capi, "SIM_" + os.environ.get("IVS_DEV_FLAG", "STREAM8"))  # the kernel under test
+    NEW = 0  # the kernel under test
+    for f in os.environ.get("IVS_DEV_FLAG", "STREAM8").split("+"):
+        NEW |= getattr(capi, "SIM_" + f)
     sizes = [int(a) for a in sys.argv[1:]] or [256, 512, 768, 1024, 2048, 2049]
     ok = True
     for mode in (capi.ARITH_FMA, capi.ARITH_STRICT):
