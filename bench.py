@@ -290,16 +290,21 @@ def run_ours(args):
         single_run = {}
         for key, wl in (("256", "config1"), ("512", "config2"), ("1024", "config3"), ("2048", "config5")):
             p1 = workload_params(wl)
-            one = capi.Simulation(ctx, p1, 1, flags=flags)
-            k1 = max(args.steps, 256)
-            one.step(64)
-            ms1, _ = timed_median(one.step, k1, 3)
-            one.close()
             n1 = p1.grid_size
-            single_run[key] = {"us_per_step": ms1 * 1e3 / k1, "steps_per_s": k1 / (ms1 * 1e-3),
+            k1 = max(args.steps, 256)
+            entry = {}
+            # default: the steps of one ivs_sim_step call inside one persistent kernel (grid-wide barrier
+            # between steps); "per_step_launch": the same through the 16-step CUDA graph, one launch per step
+            for name, fl in (("persistent", flags), ("per_step_launch", flags | capi.SIM_NO_PERSISTENT)):
+                one = capi.Simulation(ctx, p1, 1, flags=fl)
+                one.step(64)
+                ms1, _ = timed_median(one.step, k1, 3)
+                one.close()
+                entry[name] = {"us_per_step": ms1 * 1e3 / k1, "steps_per_s": k1 / (ms1 * 1e-3),
                                "cell_updates_per_s": float(n1) * n1 * k1 / (ms1 * 1e-3)}
+            single_run[key] = dict(entry["persistent"], per_step_launch=entry["per_step_launch"])
         single_run["note"] = ("one simulation per grid size (BASELINE configs 1, 2, 3, 5), state L2-resident "
-                              "(no flush): the latency-bound view")
+                              "(no flush): the latency-bound view; %d steps per ivs_sim_step call" % max(args.steps, 256))
 
     # BASELINE.json configs[3]: the bunch-current scan of 256 independent 256^2 runs, 256 / N per GPU
     scan = None

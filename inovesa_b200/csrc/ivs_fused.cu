@@ -1428,6 +1428,7 @@ ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan)
             plan->threads = keep_threads;
         }
     }
+    ivs_resident_plan(ctx, s, plan);
     // tile height: minimise (rounds of CTAs over the machine) x (rows staged per CTA)
     const uint32_t halo = plan->halo_lo + plan->halo_hi;
     const int candidates[3] = {16, 8, 4};
@@ -1514,12 +1515,44 @@ void ivs_fused_plan_destroy(ivs_fused_plan* plan) {
         }
     }
 #endif
-    void** bufs[] = {&plan->rf_first, &plan->rf_w, &plan->dr_first, &plan->dr_w, &plan->fp_base, &plan->fp_w, &plan->fp5};
+    void** bufs[] = {&plan->rf_first, &plan->rf_w, &plan->dr_first, &plan->dr_w, &plan->fp_base, &plan->fp_w, &plan->fp5, &plan->res_tags};
     for (void** b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
     }
     plan->ready = false;
+}
+
+// Many steps in ONE cooperative launch of the persistent kernel (ivs_resident.cu): for runs that fit
+// the machine at once and that have nothing between two steps but the step itself
+// (no tracked particles, no DynamicRFKickMap).  The two grids and profiles swap roles inside the kernel.
+ivs_status ivs_fused_enqueue_run(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s, uint32_t nsteps) {
+    if (!plan->ready || !plan->resident || s->np || s->dyn_rf)
+        return ivs_fail(ctx, IVS_ERR_UNSUPPORTED, "persistent step kernel does not apply");
+    if (nsteps == 0) return IVS_OK;
+    fused_args a;
+    a.in = s->grid[s->cur];
+    a.out = s->grid[s->cur ^ 1];
+    a.rho_in = s->profile[s->pcur];
+    a.rho_out = s->profile[s->pcur ^ 1];
+    a.wake_out = s->wakebuf[0];
+    a.wb = 0;
+    a.wakefn = s->wakefunction;
+    a.wakescaling = s->wakescaling;
+    a.rf_first = (const int*)plan->rf_first; a.rf_w = (const float4*)plan->rf_w;
+    a.dr_first = (const int*)plan->dr_first; a.dr_w = (const float4*)plan->dr_w;
+    a.fp_base = (const int*)plan->fp_base; a.fp_w = (const float4*)plan->fp_w;
+    a.fp_w5 = s->fpw;
+    a.ws = s->ws;
+    a.status = s->status;
+    a.host_flag = s->host_flag;
+    a.n = s->n; a.it = s->it; a.hl = plan->halo_lo; a.hr = plan->halo_hi; a.pitch = s->n + 2 * kPad;
+    a.has_wake = s->has_wake ? 1 : 0;
+    const ivs_status st = ivs_resident_run(ctx, plan, s, a, nsteps);
+    if (st != IVS_OK) return st;
+    s->cur ^= (int)(nsteps & 1u);
+    s->pcur ^= (int)(nsteps & 1u);
+    return IVS_OK;
 }
 
 ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s) {

@@ -44,6 +44,10 @@ struct stream_args {
 bool ivs_stream8_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan, const int* dr_first);
 ivs_status ivs_stream8_launch(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_sim* s,
                               const ivs_fused_detail::fused_args& a);
+// the persistent kernel for runs that fit the machine at once (ivs_resident.cu)
+bool ivs_resident_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan);
+ivs_status ivs_resident_run(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_sim* s,
+                            const ivs_fused_detail::fused_args& a, uint32_t nsteps);
 
 namespace {
 using ivs_fused_detail::fused_args;

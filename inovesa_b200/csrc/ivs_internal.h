@@ -72,6 +72,12 @@ struct ivs_fused_plan {
     bool stream = false;  // streaming kernel (independent warps, qpt quads of columns per thread)
     uint32_t qpt = 1;
     bool stream8 = false; // column-block kernel (ivs_stream8.cu): 8 adjacent columns per lane, private rings
+    // the whole run fits the machine at once: many steps per (cooperative) launch of the persistent
+    // kernel (ivs_resident.cu), res_rows output rows per CTA
+    bool resident = false;
+    uint32_t res_rows = 0, res_wwin = 0;
+    size_t res_smem = 0;
+    void* res_tags = nullptr;  // [2][members][n] row sums published step by step (value, step tag)
     uint32_t strip = 0, kslots = 0, max_strip = 0, max_rin = 0, wwin_len = 0;
     void* fp5 = nullptr;  // Fokker-Planck weights, out-of-grid taps zeroed (streaming kernel)
     bool ready = false;
@@ -79,6 +85,8 @@ struct ivs_fused_plan {
 ivs_status ivs_fused_plan_create(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan);
 void ivs_fused_plan_destroy(ivs_fused_plan* plan);
 ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s);
+// nsteps steps in one launch of the persistent kernel (plan->resident, no tracked particles, static RF)
+ivs_status ivs_fused_enqueue_run(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s, uint32_t nsteps);
 // tracking launches that overlap the following step (side stream) are joined into the context's stream
 ivs_status ivs_fused_join(ivs_ctx* ctx, ivs_sim* s);
 // new RF kick offsets: rebuild the fused kernels' tap tables in place (same device buffers)

@@ -292,6 +292,14 @@ static ivs_status enqueue_steps(ivs_sim* s, uint32_t nsteps) {
     const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
     const uint32_t lps = launches_per_step(s);
     uint32_t left = nsteps;
+    // a run whose CTAs are all resident at once steps inside ONE persistent kernel (grid-wide barrier
+    // instead of the kernel boundary); nothing else happens between two such steps
+    if (!unfused && s->plan.resident && !s->np && !s->dyn_rf && left > 1) {
+        IVS_TRY(ivs_fused_enqueue_run(ctx, &s->plan, s, left));
+        s->steps_done += left;
+        s->fused_enqueued += left;
+        return IVS_OK;
+    }
     if (use_graph) {
         const uint32_t K = ivs_sim::kGraphSteps;  // even: a replay leaves the parity as it was
         while (left >= K) {

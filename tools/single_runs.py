@@ -21,11 +21,15 @@ CASES = [
 
 if __name__ == "__main__":
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+    only = sys.argv[2:]  # labels to run (default: all)
     capi.load()
     with capi.Context(0, capi.ARITH_FMA) as ctx:
         for name, kw in CASES:
             p = kara_params(**kw)
-            for flags, label in ((0, "fused"), (capi.SIM_UNFUSED, "unfused")):
+            for flags, label in ((0, "fused"), (capi.SIM_NO_PERSISTENT, "per-step"), (capi.SIM_TILED, "tiled"),
+                                 (capi.SIM_UNFUSED, "unfused")):
+                if only and label not in only:
+                    continue
                 sim = capi.Simulation(ctx, p, 1, flags=flags)
                 sim.step(64)
                 ctx.sync()
