@@ -55,6 +55,7 @@ struct resident_args {
     uint32_t ord0;      // ordinal (since the host's last reset of the status words) of the run's first step
     uint32_t tickets_per_step;  // CTAs of a step-kernel launch of the same simulation (see step_ctl_begin)
     uint2* tags;        // [2][members][n] published row sums (value, step tag), zeroed before the launch
+    uint2* cta_tags;    // [2][CTAs] one word per CTA and step (ensembles: members do not read each other's row sums)
 };
 
 __device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
@@ -188,6 +189,11 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
     const uint32_t q = segw * 32 + lane;
     uint2* const tags = ra.tags + (size_t)member * n * kTagStride;  // [2][members][n] (value, step tag), one per line
     const size_t tag_stride = (size_t)gridDim.y * n * kTagStride;
+    // ensembles: a CTA only reads its own member's row sums, but a step that leaves the staged pad in one
+    // member has to end the run for all of them at the same step: every CTA also publishes one word per
+    // step, and every CTA reads all of those
+    const uint32_t n_ctas = gridDim.x * gridDim.y, cta_id = blockIdx.y * gridDim.x + blockIdx.x;
+    const bool ensemble = gridDim.y > 1;
     // a step enqueued before this run left the supported range of displacements (the host redoes it on
     // another path and re-enqueues what follows): nothing may be written.  (status[0] = ordinal of the first
     // such step: one of THIS run is at least ord0, so every CTA decides the same whenever it looks.)
@@ -214,6 +220,10 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
         } else {
             const uint2* tsrc = tags + (size_t)(odd ? 0 : 1) * tag_stride;  // step - 1 published with parity (step - 1) & 1
             for (uint32_t i = tid; i < n; i += T) rho[i + (i >> 5)] = (double)await_row_sum(tsrc + (size_t)i * kTagStride, step, flags);
+            if (ensemble) {
+                const uint2* csrc = ra.cta_tags + (size_t)(odd ? 0 : 1) * n_ctas * kTagStride;
+                for (uint32_t i = tid; i < n_ctas; i += T) await_row_sum(csrc + (size_t)i * kTagStride, step, flags);
+            }
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
         // a step that left the staged pad ends the run for everybody; the host redoes it and what follows
@@ -387,6 +397,9 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
             if (step + 1 < nsteps)
                 publish_row_sum(tags + (size_t)(odd ? 1 : 0) * tag_stride + (size_t)(xa + i) * kTagStride, v, (step + 1) | *reinterpret_cast<volatile uint32_t*>(&ovf));
         }
+        if (ensemble && tid == 0 && step + 1 < nsteps)
+            publish_row_sum(ra.cta_tags + ((size_t)(odd ? 1 : 0) * n_ctas + cta_id) * kTagStride, 0.0f,
+                            (step + 1) | *reinterpret_cast<volatile uint32_t*>(&ovf));
         RES_MARK(4);
     }
     // the step kernels count the steps by CTA tickets (step_ctl_begin): leave the counter as they would have
@@ -409,6 +422,11 @@ size_t resident_smem(uint32_t n, uint32_t rows, uint32_t H, uint32_t* wwin_len_o
            a16((size_t)n * 16) + a16((size_t)n * 4) + a16((size_t)n * 20) + a16((size_t)n * 4) +
            a16((size_t)(n + n / 32) * 8) + a16((size_t)wwin_len * 8) +
            a16((size_t)rows * NSEG * 4) + a16((size_t)max_rin * 48) + 16;
+}
+
+// row sums [2][members][n] + one word per CTA [2][at most a CTA per SM], kTagStride words apart
+size_t resident_tag_bytes(const ivs_ctx* ctx, uint32_t members, uint32_t n) {
+    return ((size_t)2 * members * n + (size_t)2 * ctx->sm_count) * kTagStride * sizeof(uint2);
 }
 
 const void* resident_kernel(const ivs_ctx* ctx) {
@@ -436,7 +454,7 @@ bool ivs_resident_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem) != cudaSuccess) return false;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kResThreads, sb) != cudaSuccess || per_sm < 1) return false;
-    if (!plan->res_tags && cudaMalloc(&plan->res_tags, (size_t)2 * s->members * n * kTagStride * sizeof(uint2)) != cudaSuccess) return false;
+    if (!plan->res_tags && cudaMalloc(&plan->res_tags, resident_tag_bytes(ctx, s->members, n)) != cudaSuccess) return false;
     plan->resident = true;
     plan->res_rows = rows;
     plan->res_smem = sb;
@@ -457,8 +475,9 @@ ivs_status ivs_resident_run(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_
     ra.tickets_per_step = plan->stream8 || plan->stream ? ivs_div_up(s->n, plan->strip) * s->members
                                                         : ivs_div_up(s->n, plan->tx) * s->members;
     ra.tags = (uint2*)plan->res_tags;
+    ra.cta_tags = ra.tags + (size_t)2 * s->members * s->n * kTagStride;
     const dim3 grid(ivs_div_up(s->n, plan->res_rows), s->members);
-    IVS_CUDA(ctx, cudaMemsetAsync(plan->res_tags, 0, (size_t)2 * s->members * s->n * kTagStride * sizeof(uint2), ctx->stream));
+    IVS_CUDA(ctx, cudaMemsetAsync(plan->res_tags, 0, resident_tag_bytes(ctx, s->members, s->n), ctx->stream));
     void* args[] = {(void*)&ra, (void*)&nsteps};
     IVS_CUDA(ctx, cudaLaunchCooperativeKernel(resident_kernel(ctx), grid, dim3(kResThreads), args, plan->res_smem, ctx->stream));
     IVS_LAUNCHED(ctx);

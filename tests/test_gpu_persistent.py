@@ -77,3 +77,18 @@ def test_persistent_run_recovers_from_displacements_beyond_the_pad(capi, ctx_str
             assert np.array_equal(x, y), (k, what)
     assert a.fallback_steps == b.fallback_steps > 0
     a.close(); b.close()
+
+
+def test_persistent_ensemble_stops_as_one_when_a_member_overflows(capi, ctx_fma):
+    """the members of an ensemble do not read each other's row sums, but a step that leaves the pad in ONE
+    member must end the run for ALL of them at the same step (the host rewinds the whole batch)"""
+    p = kara_params(grid_size=256)
+    currents = [50e-6, 10e-3, 100e-6, 200e-6]
+    a = capi.Simulation(ctx_fma, p, 4, bunch_currents=currents)
+    b = capi.Simulation(ctx_fma, p, 4, bunch_currents=currents, flags=capi.SIM_NO_PERSISTENT)
+    for k in (20, 7):
+        a.step(k); b.step(k)
+        for x, y, what in zip(a.download(), b.download(), ("grid", "profile", "wake")):
+            assert np.array_equal(x, y), (k, what)
+    assert a.fallback_steps == b.fallback_steps > 0
+    a.close(); b.close()
