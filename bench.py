@@ -41,10 +41,11 @@ from inovesa_b200.params import kara_params  # noqa: E402
 
 f32 = np.float32
 ALGO_BYTES_PER_CELL = 8.0  # one fp32 read + one fp32 write of the grid per step
-# dram__bytes_read.sum + dram__bytes_write.sum of one stream_step_kernel launch on the benchmark
-# batch (26 x 2048^2), from the ncu --set full capture summarised in profiles/ (updated per round)
+# dram__bytes_read.sum + dram__bytes_write.sum of one stream8_step_kernel launch on the benchmark
+# batch (26 x 2048^2), from the ncu --set full capture kept in profiles/r2_ncu_stream8_step_dram.txt
+# (updated per round)
 TRAFFIC_MEMBERS = 26
-TRAFFIC_BYTES_PER_LAUNCH = 865557760  # r1: 457.5 MB read + 408.0 MB written; algorithmic 872.4 MB
+TRAFFIC_BYTES_PER_LAUNCH = 848426240  # r2: 448.5 MB read + 399.9 MB written; algorithmic 872.4 MB
 
 
 def workload_params(name):
@@ -359,7 +360,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if not args.unfused and members == TRAFFIC_MEMBERS and n == 2048 else None,
                          "peak_source": peak_src,
-                         "kernel": "stream_step_kernel" if not args.unfused else "kick/drift/fokker_planck/project sequence",
+                         "kernel": ("stream8_step_kernel" if args.qpt in (0, 8) else "stream_step_kernel") if not args.unfused else "kick/drift/fokker_planck/project sequence",
                          "us_per_launch": ms_kernel * 1e3 / args.steps,
                          "algorithmic_bytes_per_launch": cells_per_step * ALGO_BYTES_PER_CELL},
             "clocks": clocks,

@@ -400,8 +400,10 @@ ivs_status ivs_field_launch(ivs_ctx* ctx, const float* profile, uint32_t n, uint
     g.obs = nullptr; g.projy = nullptr; g.ws = nullptr; g.qmin = g.pmin = g.dp = 0.0f;
     if (o) { g.obs = o->obs; g.projy = o->projy; g.ws = o->ws; g.qmin = o->qmin; g.pmin = o->pmin; g.dp = o->dp; }
     const size_t smem = sizeof(float2) * (nmax / 2) * 3;  // two buffers of nmax/2 and the twiddle table
-    if (smem > 40 * 1024)  // the kernel's static shared memory counts against the 48 KB default as well
+    if (smem > 40 * 1024 && !(ctx->optin & 2u)) {  // the kernel's static shared memory counts against the 48 KB default as well
         IVS_CUDA(ctx, cudaFuncSetAttribute(field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFieldMaxSmem));
+        ctx->optin |= 2u;  // once per context (the call costs more than the kernel)
+    }
     // one radix-8 butterfly per thread and stage up to nmax = 8192, two at 16384
     uint32_t threads = nmax / 16;
     threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);

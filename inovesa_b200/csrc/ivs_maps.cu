@@ -418,9 +418,12 @@ ivs_status ivs_rotate(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, f
         cap_rows = (uint32_t)(((size_t)kIvsMaxOptinSmem - 1024) / ((size_t)pitch * sizeof(float)));
         smem = (size_t)cap_rows * pitch * sizeof(float);
     }
-    if (smem > 40 * 1024) {
+    // once per context: the attribute belongs to the kernel (two API calls of 15 us each otherwise)
+    const bool opted_in = (ctx->optin & 1u) != 0;
+    if (smem > 40 * 1024 && !opted_in) {
         IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
         IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        ctx->optin |= 1u;
     }
     return launch(ctx, rotate_tile_kernel<true>, rotate_tile_kernel<false>,
                   dim3(ivs_div_up(n, kRotTY), ivs_div_up(n, kRotTX)), dim3(kRotTY), smem, (const float*)d_in,
