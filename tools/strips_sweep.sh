@@ -4,9 +4,8 @@
 wl=$1; m=$2; shift 2
 mkdir -p gpurun_out
 for P in "$@"; do
-  IVS_PLAN_DEBUG=1 IVS_FORCE_STRIPS=$P python bench.py --workload $wl --members $m --particles 0 --steps 200 --warmup 20 \
-      --no-cpu-baseline --no-single-run --e2e-steps 3 > gpurun_out/strips_$P.json 2> gpurun_out/strips_$P.err
-  grep -m1 "ivs plan" gpurun_out/strips_$P.err
+  python bench.py --workload $wl --members $m --strips $P --particles 0 --steps 200 --warmup 20 \
+      --no-cpu-baseline --no-single-run --no-scan --e2e-steps 3 > gpurun_out/strips_$P.json 2> gpurun_out/strips_$P.err
   python - $P gpurun_out/strips_$P.json <<'PY'
 import json, sys
 try:
