@@ -86,15 +86,17 @@ IVS_HD void ivs_calc_coefficients(float f, uint32_t it, float* ic) {
         ic[0] = IVS_SUB(1.0f, f);
         ic[1] = f;
         break;
+    // (x / 2 as x * 0.5f: scaling by a power of two is exact, so the two round alike everywhere,
+    // and the product is one instruction where the IEEE division is a subroutine)
     case 3:
-        ic[0] = IVS_DIV(IVS_MUL(f, IVS_SUB(f, 1.0f)), 2.0f);
+        ic[0] = IVS_MUL(IVS_MUL(f, IVS_SUB(f, 1.0f)), 0.5f);
         ic[1] = IVS_SUB(1.0f, IVS_MUL(f, f));
-        ic[2] = IVS_DIV(IVS_MUL(f, IVS_ADD(f, 1.0f)), 2.0f);
+        ic[2] = IVS_MUL(IVS_MUL(f, IVS_ADD(f, 1.0f)), 0.5f);
         break;
     default:
         ic[0] = IVS_MUL(IVS_MUL(IVS_MUL(IVS_SUB(f, 1.0f), IVS_SUB(f, 2.0f)), f), (float)(-1. / 6.));
-        ic[1] = IVS_DIV(IVS_MUL(IVS_MUL(IVS_ADD(f, 1.0f), IVS_SUB(f, 1.0f)), IVS_SUB(f, 2.0f)), 2.0f);
-        ic[2] = IVS_DIV(IVS_MUL(IVS_MUL(IVS_SUB(2.0f, f), f), IVS_ADD(f, 1.0f)), 2.0f);
+        ic[1] = IVS_MUL(IVS_MUL(IVS_MUL(IVS_ADD(f, 1.0f), IVS_SUB(f, 1.0f)), IVS_SUB(f, 2.0f)), 0.5f);
+        ic[2] = IVS_MUL(IVS_MUL(IVS_MUL(IVS_SUB(2.0f, f), f), IVS_ADD(f, 1.0f)), 0.5f);
         ic[3] = IVS_MUL(IVS_MUL(IVS_MUL(f, IVS_ADD(f, 1.0f)), IVS_SUB(f, 1.0f)), (float)(1. / 6.));
         break;
     }

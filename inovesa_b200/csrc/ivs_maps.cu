@@ -188,16 +188,17 @@ rotate_kernel(const float* __restrict__ in, float* __restrict__ out, rot_params 
 // Taps outside the grid are {index 0, weight 0} in the reference's table (:247-249): their source
 // value is in[0], read once per thread, so every sum (and the clamp) sees the same operands.
 constexpr int kRotTX = 32, kRotTY = 128;
+constexpr int kRotGY = 4;  // row groups of a CTA: thread (c, g) forms the rows g, g + kRotGY, ... of column c
 
 __device__ __forceinline__ uint32_t rot_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool FMA>
-__global__ void __launch_bounds__(kRotTY)
+__global__ void __launch_bounds__(kRotTY * kRotGY)
 rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_params p, uint32_t cap_rows,
                    uint32_t pitch) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int box[4];  // first row, rows, first column (multiple of 4), columns (multiple of 4)
+    __shared__ int box[5];  // first row, rows, first column (multiple of 4), columns (multiple of 4), box not clipped by the grid
     const uint32_t n = p.n, it = p.it;
     const uint32_t tx0 = blockIdx.y * kRotTX, ty0 = blockIdx.x * kRotTY;
     const uint32_t lo = (it - 1) / 2;
@@ -208,7 +209,8 @@ rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_pa
         x1r = IVS_ADD(IVS_DIV(IVS_SUB(IVS_MUL(p.cos_dt, ax), IVS_MUL(p.sin_dt, ay)), p.d0), p.zb0);
         y1r = IVS_ADD(IVS_DIV(IVS_ADD(IVS_MUL(p.sin_dt, ax), IVS_MUL(p.cos_dt, ay)), p.d1), p.zb1);
     };
-    if (threadIdx.x == 0) {
+    const uint32_t tlin = threadIdx.y * kRotTY + threadIdx.x;
+    if (tlin == 0) {
         const uint32_t xe = min(tx0 + kRotTX, n) - 1, ye = min(ty0 + kRotTY, n) - 1;
         float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
         const uint32_t cx[2] = {tx0, xe}, cy[2] = {ty0, ye};
@@ -225,12 +227,14 @@ rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_pa
         int r1 = (int)floorf(fmaxf(fminf(xmax, big), -big)) + 1 + (int)(it - 1 - lo);
         int c0 = (int)floorf(fmaxf(fminf(ymin, big), -big)) - 1 - (int)lo;
         int c1 = (int)floorf(fmaxf(fminf(ymax, big), -big)) + 1 + (int)(it - 1 - lo);
+        // (one cell of slack on every side of the corners' stencils: unclipped means every cell's are inside)
+        const bool unclipped = r0 >= 0 && c0 >= 0 && r1 <= (int)n - 1 && c1 <= (int)n - 1;
         r0 = max(r0, 0); c0 = max(c0, 0) & ~3;
         r1 = min(r1, (int)n - 1); c1 = min(c1 | 3, (int)n - 1);
         int rows = r1 - r0 + 1, cols = c1 - c0 + 1;
         if (rows <= 0 || cols <= 0) rows = cols = 0;
         if ((uint32_t)rows > cap_rows || (uint32_t)cols > pitch || (cols & 3)) rows = -1;  // cannot be staged: gather from global
-        box[0] = r0; box[1] = rows; box[2] = c0; box[3] = cols;
+        box[0] = r0; box[1] = rows; box[2] = c0; box[3] = cols; box[4] = (unclipped && rows > 0) ? 1 : 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rot_smem_u32(&bar)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (rows > 0)
@@ -240,7 +244,7 @@ rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_pa
     __syncthreads();
     const int r0 = box[0], rows = box[1], c0 = box[2], cols = box[3];
     if (rows > 0) {
-        for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        for (int r = tlin; r < rows; r += kRotTY * kRotGY) {
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              rot_smem_u32(tile + (size_t)r * pitch)),
                          "l"(in + (size_t)(r0 + r) * n + c0), "r"((uint32_t)cols * 4u), "r"(rot_smem_u32(&bar))
@@ -258,14 +262,40 @@ rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_pa
     }
     if (y0 >= n) return;
     const bool staged = rows >= 0;
-    for (uint32_t x0 = tx0; x0 < min(tx0 + kRotTX, n); x0++) {
+    // every tap of every cell of the tile inside the staged box and the grid (the box was clipped to the
+    // grid only if it reached beyond it): the common case, no test per tap
+    const bool interior = rows > 0 && box[4] != 0;
+    for (uint32_t x0 = tx0 + threadIdx.y; x0 < min(tx0 + kRotTX, n); x0 += kRotGY) {
         float x1r, y1r;
         source(x0, y0, x1r, y1r);
         const float xi = truncf(x1r), yi = truncf(y1r);
         const float xf = IVS_SUB(x1r, xi), yf = IVS_SUB(y1r, yi);
         const uint32_t x1 = (uint32_t)(long long)xi, y1 = (uint32_t)(long long)yi;
         float v = 0.0f;
-        if (x1 < n && y1 < n) {
+        if (interior && it == 4) {
+            // cubic interpolation, all 16 taps valid: straight-line code (same operations, same order)
+            float icq[4], icp[4];
+            ivs_calc_coefficients(xf, 4, icq);
+            ivs_calc_coefficients(yf, 4, icp);
+            const float* t0 = tile + (size_t)((int)x1 - 1 - r0) * pitch + ((int)y1 - 1 - c0);
+            float ceil = 1.17549435e-38f /* FLT_MIN */, flor = 3.402823466e+38f /* FLT_MAX */;
+#pragma unroll
+            for (int i1 = 0; i1 < 4; i1++) {
+#pragma unroll
+                for (int j1 = 0; j1 < 4; j1++) {
+                    const float src = t0[(size_t)i1 * pitch + j1];
+                    v = madd<FMA>(src, IVS_MUL(icq[i1], icp[j1]), v);
+                    if (p.clamp && i1 >= 1 && i1 <= 2 && j1 >= 1 && j1 <= 2) {
+                        ceil = (ceil < src) ? src : ceil;  // std::max(ceil, src)
+                        flor = (src < flor) ? src : flor;  // std::min(flor, src)
+                    }
+                }
+            }
+            if (p.clamp) {
+                const float m = (v < ceil) ? v : ceil;  // std::min(ceil, v)
+                v = (m < flor) ? flor : m;              // std::max(m, flor)
+            }
+        } else if (x1 < n && y1 < n) {
             float icq[4], icp[4];
             ivs_calc_coefficients(xf, it, icq);
             ivs_calc_coefficients(yf, it, icp);
@@ -426,7 +456,7 @@ ivs_status ivs_rotate(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, f
         ctx->optin |= 1u;
     }
     return launch(ctx, rotate_tile_kernel<true>, rotate_tile_kernel<false>,
-                  dim3(ivs_div_up(n, kRotTY), ivs_div_up(n, kRotTX)), dim3(kRotTY), smem, (const float*)d_in,
+                  dim3(ivs_div_up(n, kRotTY), ivs_div_up(n, kRotTX)), dim3(kRotTY, kRotGY), smem, (const float*)d_in,
                   (float*)d_out, p, cap_rows, pitch);
 }
 
