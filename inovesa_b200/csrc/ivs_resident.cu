@@ -11,17 +11,19 @@
 // however short the strip).  Here a CTA (one per SM, cooperative launch) keeps a block of rows for the
 // whole run and does every map as one block-wide pass over ALL its rows at once:
 //
-//   boundary | wait for every block's row sums of the last step (they carry the step's tag: the profile
-//            | IS the grid-wide barrier, see publish_row_sum) -> profile in shared memory
-//   sync     | stage the drift halo rows (cp.async.cg, 16 B: L2 -> shared memory; the block's own rows are
-//            | already there), beside it the wake potential (Toeplitz product in double: one chain of 32 x'
-//            | per lane, 4 NSEG lanes per row, a row's taps by its first lane)
+//   boundary | wait for every block's row sums of the last step (8-byte words carrying the step's tag:
+//            | the profile IS the grid-wide barrier, see publish_row_sum) -> profile in shared memory
+//   sync     | the wake potential (Toeplitz product in double: one chain of 32 x' per lane, 4 NSEG lanes
+//            | per row, a row's taps by its first lane); beside it the warps without a row of it wait for
+//            | the neighbouring blocks' "rows are out" flags and stage the drift halo rows (cp.async.cg, 16 B:
+//            | L2 -> shared memory; the block's own rows are already there)
 //   sync     | wake kick + RF kick, a thread per quad of cells: 4 aligned LDS.128, shifted by the row's
 //            | displacement mod 4, 7 wake-kicked cells -> 4 RF-kicked
 //   sync     | drift + Fokker-Planck, a thread per quad, a warp per 128 columns of a row: 4 LDS.128 of kicked
 //            | rows, stencil neighbours by shuffle, STG.128 + the row in place for the next step,
 //            | Simpson-weighted sums by warp butterfly
-//   sync     | row sums of the segments added in order -> published (value, step tag) with a release
+//   sync     | row sums of the segments added in order -> published (relaxed); one thread releases the
+//            | "rows are out" flag
 //
 // The tables of the maps, the window of the wake function and the zero pads live in shared memory for the
 // whole run; a warp keeps one segment of 128 columns, so a lane's drift and Fokker-Planck weights are
@@ -31,10 +33,10 @@
 // reference's order, the same summation trees for the wake potential and the row sums), so a run of k
 // steps equals k launches of any of them bit for bit (tests/test_gpu_persistent.py).
 //
-// Measured (B200, tools/single_runs.py): 4.3 / 5.1 / 8.9 us per step at 256^2 / 512^2 / 1024^2 against
+// Measured (B200, tools/single_runs.py): 3.2 / 4.2 / 8.3 us per step at 256^2 / 512^2 / 1024^2 against
 // 8.9 / 9.6 / 10.9 us with one launch of the column-block kernel per step (CUDA graph).  Where the time
-// goes at 256^2 (clocks of one CTA, -DIVS_RES_CLOCKS=1): boundary 2590, wake + taps 2370, kicks 680,
-// drift + Fokker-Planck 1150, publishing (the release waits for the block's rows to reach L2) 2170.
+// goes at 256^2 (clocks of one CTA, -DIVS_RES_CLOCKS=1): boundary 1400 - 1800, wake + taps + halo copies 2100,
+// kicks 550, drift + Fokker-Planck 1250, row sums 700 (profiles/r2_experiments.txt has the road there).
 #include <algorithm>
 #include <cstdio>
 #include <vector>
@@ -56,20 +58,39 @@ struct resident_args {
     uint32_t tickets_per_step;  // CTAs of a step-kernel launch of the same simulation (see step_ctl_begin)
     uint2* tags;        // [2][members][n] published row sums (value, step tag), zeroed before the launch
     uint2* cta_tags;    // [2][CTAs] one word per CTA and step (ensembles: members do not read each other's row sums)
+    uint32_t* rows_out; // [CTAs] step count up to which a CTA's rows are in L2 (kTagStride words apart)
 };
 
 __device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// The step boundary.  Nothing of step k + 1 may start before every CTA has finished step k: the wake
-// potential needs every block's row sums, the drift the neighbouring blocks' rows.  Instead of a counter
-// barrier followed by a read of the new profile, the profile IS the barrier: a row sum is published as one
-// 8-byte word (value, step tag) with a release at GPU scope after the CTA's rows are written; every CTA
-// polls the n words of the step it waits for with acquire loads until all carry the step's tag -- one trip
-// through L2 instead of three.  Two tag arrays alternate (a CTA can be one step ahead of another, never two).
+// The step boundary.  Two things of step k + 1 wait for step k: the wake potential needs EVERY block's row
+// sums, the drift the NEIGHBOURING blocks' rows.  Instead of a counter barrier followed by a read of the new
+// profile, the profile IS the barrier: a row sum is published as one 8-byte word (value, step tag) with a
+// relaxed store (value and tag travel together, nothing else hangs on it); every CTA polls the n words of
+// the step it waits for until all carry the step's tag -- one trip through L2 instead of three -- and goes
+// on to the wake potential.  The rows take the slower road beside it: publish_rows_out / await_rows_out,
+// release / acquire, awaited only by the warps that copy the halo rows, just before they do.
+// Two tag arrays alternate (a CTA can be one step ahead of another, never two: it needs every CTA's row
+// sums of a step to leave it; by then every CTA's copies of that step's input rows have landed, so the
+// next step may overwrite them).
 __device__ __forceinline__ void publish_row_sum(uint2* slot, float v, uint32_t tag) {
-    asm volatile("st.release.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+// "the rows of step `tag - 1` of this CTA are in L2": a release store by one thread after the CTA barrier
+// that follows the stores (its 1500 - 2000 cycles are nobody's critical path); the readers of those rows
+// (the neighbouring blocks) poll it with acquire loads before they copy
+__device__ __forceinline__ void publish_rows_out(uint32_t* flag, uint32_t tag) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void await_rows_out(const uint32_t* flag, uint32_t tag) {
+    uint32_t t;
+    // acquire loads: a relaxed poll followed by an acquire fence costs 1300 cycles more per step (the fence
+    // holds back the warp's next shared-memory accesses as well)
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(t) : "l"(flag) : "memory");
+    } while (t < tag);
 }
 // bit 31 of the tag: the publishing CTA's wake kick left the staged pad in that step (every CTA reads every
 // word of a step, so all of them learn it at the same boundary and end the run together)
@@ -193,6 +214,13 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
     // member has to end the run for all of them at the same step: every CTA also publishes one word per
     // step, and every CTA reads all of those
     const uint32_t n_ctas = gridDim.x * gridDim.y, cta_id = blockIdx.y * gridDim.x + blockIdx.x;
+    // the blocks that own this block's halo rows
+    const uint32_t nb_lo = (uint32_t)max(xs, 0) / ra.rows, nb_hi = min((uint32_t)(xs + (int)RIN) - 1u, n - 1u) / ra.rows;
+    // the copies are dealt to the warps that form no row of the wake potential when there are at least four
+    // of them (they reach the copies first), else to all warps
+    const uint32_t wake_warps = g.has_wake ? min((RIN + RPW - 1) / RPW, NW) : 0u;
+    const uint32_t copy_warp0 = NW - wake_warps >= 4 ? wake_warps : 0u, copy_warps = NW - copy_warp0;
+    const uint32_t copy_first = warp >= copy_warp0 ? 0u : 0xffffff00u;  // warps before copy_warp0 take no copies
     const bool ensemble = gridDim.y > 1;
     // a step enqueued before this run left the supported range of displacements (the host redoes it on
     // another path and re-enqueues what follows): nothing may be written.  (status[0] = ordinal of the first
@@ -224,7 +252,6 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
                 const uint2* csrc = ra.cta_tags + (size_t)(odd ? 0 : 1) * n_ctas * kTagStride;
                 for (uint32_t i = tid; i < n_ctas; i += T) await_row_sum(csrc + (size_t)i * kTagStride, step, flags);
             }
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
         // a step that left the staged pad ends the run for everybody; the host redoes it and what follows
         // (ivs_step.cu, settle)
@@ -234,16 +261,6 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
             steps_run = step;
             break;
         }
-        // ---- stage the rows (16-byte copies, L2 only: the rows were written by other SMs a step ago); a
-        // warp copies one segment of 128 cells.  After the first step only the drift halo comes from L2: the
-        // block's own rows were put in place by the last step's Fokker-Planck pass.
-        for (uint32_t w = warp; w < RIN * NSEG; w += NW) {
-            const uint32_t r = w / NSEG, qq = (w - r * NSEG) * 32 + lane;
-            const int x = xs + (int)r;
-            if ((uint32_t)x < n && (step == 0 || r < hl || r >= hl + S))
-                cp_async16_cg(A_b + (r * pitchA + kResPad + 4 * qq) * 4, gin + (size_t)x * n + 4 * qq);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
         // ---- wake potential and wake-kick taps of the block's rows while the copies fly
         // W[x] = scaling * sum_x' rho[x'] w[x-x']  (src/PS/ElectricField.cpp:186-253 as a Toeplitz product),
         // summed as in the step kernels: chains of 32 x', blocks of a segment of 128 as (b0 + b1) + (b2 + b3),
@@ -284,7 +301,23 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
                 }
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // ---- stage the rows (16-byte copies, L2 only: the rows were written by other SMs a step ago); a
+        // warp copies one segment of 128 cells.  After the first step only the drift halo comes from L2 (the
+        // block's own rows were put in place by the last step's Fokker-Planck pass), once the blocks that
+        // own those rows have said that they are out.  The warps that had no row of the wake potential to
+        // form get here first.
+        if (step && warp >= copy_warp0) {
+            for (uint32_t b = nb_lo + lane; b <= nb_hi; b += 32)
+                if (b != blockIdx.x) await_rows_out(ra.rows_out + (size_t)(blockIdx.y * gridDim.x + b) * kTagStride, step);
+            __syncwarp();
+        }
+        for (uint32_t w = copy_first + (warp + NW - copy_warp0) % NW; w < RIN * NSEG; w += copy_warps) {
+            const uint32_t r = w / NSEG, qq = (w - r * NSEG) * 32 + lane;
+            const int x = xs + (int)r;
+            if ((uint32_t)x < n && (step == 0 || r < hl || r >= hl + S))
+                cp_async16_cg(A_b + (r * pitchA + kResPad + 4 * qq) * 4, gin + (size_t)x * n + 4 * qq);
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncthreads();  // rows staged, taps known
         RES_MARK(1);
 
@@ -387,6 +420,7 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_run_kernel(const resi
             }
         }
         __syncthreads();
+        if (tid == 32 && step + 1 < nsteps) publish_rows_out(ra.rows_out + (size_t)cta_id * kTagStride, step + 1);
         RES_MARK(3);
         // ---- the block's row sums: segments added in order; published for the next step (value + step tag,
         // released after this CTA's rows: the barrier above orders them before it)
@@ -426,7 +460,7 @@ size_t resident_smem(uint32_t n, uint32_t rows, uint32_t H, uint32_t* wwin_len_o
 
 // row sums [2][members][n] + one word per CTA [2][at most a CTA per SM], kTagStride words apart
 size_t resident_tag_bytes(const ivs_ctx* ctx, uint32_t members, uint32_t n) {
-    return ((size_t)2 * members * n + (size_t)2 * ctx->sm_count) * kTagStride * sizeof(uint2);
+    return ((size_t)2 * members * n + (size_t)3 * ctx->sm_count) * kTagStride * sizeof(uint2);
 }
 
 const void* resident_kernel(const ivs_ctx* ctx) {
@@ -476,6 +510,7 @@ ivs_status ivs_resident_run(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_
                                                         : ivs_div_up(s->n, plan->tx) * s->members;
     ra.tags = (uint2*)plan->res_tags;
     ra.cta_tags = ra.tags + (size_t)2 * s->members * s->n * kTagStride;
+    ra.rows_out = reinterpret_cast<uint32_t*>(ra.cta_tags + (size_t)2 * ctx->sm_count * kTagStride);
     const dim3 grid(ivs_div_up(s->n, plan->res_rows), s->members);
     IVS_CUDA(ctx, cudaMemsetAsync(plan->res_tags, 0, resident_tag_bytes(ctx, s->members, s->n), ctx->stream));
     void* args[] = {(void*)&ra, (void*)&nsteps};
