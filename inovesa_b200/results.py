@@ -194,9 +194,12 @@ def unit_factors(derived):
     return volts, wph, wph * float(f32(2.99792458e8 / float(f32(d.bl_f))))
 
 
-def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0, wake_impedance=None):
+def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0, wake_impedance=None,
+                   renormalize=0, progress=None):
     """main()'s loop with its out-step cadence (src/main.cpp:948-1053) on a `capi.Simulation`
-    with one member: returns the filled ResultFile.  Time axis in synchrotron periods."""
+    with one member: returns the filled ResultFile.  Time axis in synchrotron periods.
+    renormalize > 0: the charge is renormalised before every renormalize-th step (:953-955);
+    progress(done, steps): called at every out-step."""
     d, n = derived, params.grid_size
     axis_q = d.qmin + np.arange(n, dtype=f32) * f32(d.dq)
     axis_p = d.pmin + np.arange(n, dtype=f32) * f32(d.dp)
@@ -226,11 +229,23 @@ def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0,
             rf.append_tracks(parts[0])
         if save_phase_space and k % save_phase_space == 0:
             rf.append_phase_space(t, grid[0])
+        if progress is not None:
+            progress(done, steps)
         if done >= steps:
             break
-        nxt = min(outstep, steps - done)
-        sim.step(nxt)
-        done += nxt
+        nxt = min(outstep, steps - done) if outstep > 0 else steps - done
+        if renormalize > 0:
+            # grid_t1->integrateAndNormalize() at the top of every renormalize-th step
+            end = done + nxt
+            while done < end:
+                if done % renormalize == 0:
+                    sim.renormalize()
+                run = min(end, (done // renormalize + 1) * renormalize) - done
+                sim.step(run)
+                done += run
+        else:
+            sim.step(nxt)
+            done += nxt
         k += 1
     if not save_phase_space or (k % save_phase_space) != 0:
         rf.append_phase_space(done / float(d.steps), sim.download()[0][0])  # always at the end (:1084-1086)

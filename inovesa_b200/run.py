@@ -1,0 +1,122 @@
+"""The reference's main() (src/main.cpp:60-1110) on the B200 step: program options (options.py, the
+reference's names and config-file format), derived scalars, start distribution, maps, the
+simulation loop with its out-step cadence and the result file.
+
+    python -m inovesa_b200.run -c ring.cfg -T 2 -o result.h5 [--GridSize 512 ...]
+
+Writes `<output>.cfg` (the options that were set, as the reference does) and the result file:
+real HDF5 where h5py is importable, else `<output>.npz` + `<output>.layout.json` with the same
+dataset paths, shapes and attributes (results.py).  Needs a B200 and the built libivs.so; there
+is no CPU fallback.
+"""
+import sys
+import time
+
+import numpy as np
+
+from . import capi
+from .options import OptionError, ProgramOptions
+from .results import run_and_record
+
+f32 = np.float32
+TWO_PI = 6.283185307179586
+
+
+def read_tracking_file(path):
+    """start positions of the particles to track, one `x y` pair (grid points) per line
+    (src/main.cpp:801-824)"""
+    pts = []
+    for line in open(path):
+        t = line.split("#", 1)[0].split()
+        if len(t) >= 2:
+            pts.append((float(t[0]), float(t[1])))
+    return np.asarray(pts, f32).reshape(-1, 2)
+
+
+def rf_noise(opts, params, d, laststep, seed):
+    """the queue of (phase, amplitude) pairs of a DynamicRFKickMap, or None for the static map
+    (src/main.cpp:332-346,594-621)"""
+    phase_noise = max(0.0, opts["RFPhaseSpread"] / 360.0 * TWO_PI)
+    ampl_noise = max(0.0, opts["RFAmplitudeSpread"])
+    mod_ampl = max(0.0, opts["RFPhaseModAmplitude"] / 360.0 * TWO_PI)
+    mod_step = opts["RFPhaseModFrequency"] * d.dt
+
+    def normal(x):  # std::fpclassify(x) == FP_NORMAL
+        return x != 0.0 and np.isfinite(x) and abs(x) >= np.finfo(np.float64).tiny
+
+    if not (normal(phase_noise) or normal(ampl_noise) or (normal(mod_ampl) and normal(mod_step))):
+        return None
+    m = capi.rf_model(params, d)
+    return capi.rf_modulation(laststep, phase_noise, ampl_noise, mod_ampl, mod_step, d.revolutionpart,
+                              m.syncphase, seed=seed)
+
+
+def main(argv=None, out=sys.stdout):
+    argv = sys.argv[1:] if argv is None else argv
+    say = lambda msg: print(msg, file=out, flush=True)  # noqa: E731
+    try:
+        opts = ProgramOptions().parse(argv)
+        bad = opts.unsupported()
+        if bad:
+            raise OptionError("not supported by this driver: " + "; ".join(bad))
+        params = opts.ring_params()
+    except OptionError as e:
+        say("Error: %s" % e)
+        return 1
+    d = capi.derive(params)
+    laststep = int(np.floor(d.steps * opts["rotations"] + 0.5)) if opts["rotations"] > 0 else 0
+    ofname = opts["output"]
+    if ofname and not ofname.endswith((".h5", ".hdf5")):
+        say("Unkown filetype for output.")  # (sic, src/main.cpp:880)
+        return 0
+    if opts["gui"]:
+        say("Warning: no GUI in this build; running without.")
+    if opts["InterpolateClamped"]:
+        say("Note: the reference's CPU path never clamps kick maps (src/SM/KickMap.cpp:194-271); ignored.")
+    n = params.grid_size
+    say("Grid %d x %d, %g steps per synchrotron period, %d steps, bunch current %g A" % (
+        n, n, d.steps, laststep, params.bunch_current))
+    say("Natural bunch length %.4g m, energy spread %.4g eV, padded profile %d bins" % (d.bl, d.dE, d.padded_bins))
+    parts = read_tracking_file(opts["tracking"]) if opts["tracking"] else None
+    ctx = capi.Context(0, capi.ARITH_FMA)
+    grid = capi.initial_grid(d, n, params.zoom)
+    sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts)
+    if opts["RenormalizeCharge"] >= 0:
+        sim.renormalize()  # the initial renormalisation (src/main.cpp:528-532)
+    seq = rf_noise(opts, params, d, laststep, seed=1)
+    if seq is not None:
+        say("Building dynamic, %s RFKickMap..." % ("linear" if params.linear_rf else "nonlinear"))
+        sim.set_rf_modulation(seq)
+    zw, nz = capi.wake_impedance(params, d)
+    say("Starting the simulation.")
+    t0 = time.time()
+
+    def progress(done, steps):
+        if opts["verbose"] or done == steps:
+            say("%8.3f T_s  (%d / %d steps, %.1f s)" % (done / d.steps, done, steps, time.time() - t0))
+
+    rf = run_and_record(sim, params, d, laststep, outstep=opts["outstep"], save_phase_space=opts["SavePhaseSpace"],
+                        wake_impedance=zw if nz else None, renormalize=opts["RenormalizeCharge"], progress=progress)
+    dt = time.time() - t0
+    if sim.fallback_steps:
+        say("%d steps were redone through the kernel sequence (displacement beyond the fused kernel's pad)." % sim.fallback_steps)
+    say("Finished %d steps in %.2f s (%.0f steps/s)." % (laststep, dt, laststep / max(dt, 1e-9)))
+    if ofname:
+        open(ofname + ".cfg", "w").write(opts.save_text())
+        say('Saved configuiration to "%s.cfg".' % ofname)  # (sic)
+        try:
+            rf.to_hdf5(ofname)
+            say('Saved results to "%s".' % ofname)
+        except ImportError:
+            rf.save(ofname)
+            say('No HDF5 library in this environment: saved results to "%s.npz" + "%s.layout.json" '
+                "(same dataset paths, shapes and attributes)." % (ofname, ofname))
+    else:
+        say("Will not save results.")
+    sim.close()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,75 @@
+"""The main()-equivalent driver (inovesa_b200/run.py) end to end on the device: a config file in the
+reference's format, the loop with its out-step cadence, the result file with the reference's layout,
+the saved configuration -- and the same physics as driving the simulation object by hand."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from inovesa_b200 import run
+from inovesa_b200.params import kara_params
+
+pytestmark = pytest.mark.gpu
+
+CFG = """
+GridSize = 256
+StepsPerTs = 1000
+rotations = 0.25
+outstep = 50
+BunchCurrent = 5e-5
+RevolutionFrequency = 2.7157e6
+HarmonicNumber = 184
+BeamEnergy = 1.3e9
+BeamEnergySpread = 4.7e-4
+AcceleratingVoltage = 1.4e6
+SynchrotronFrequency = 8.5e3
+BendingRadius = 5.559
+VacuumGap = -1
+"""
+
+
+def test_driver_runs_a_config_and_writes_the_result_layout(tmp_path, capi, ctx_fma):
+    cfg = tmp_path / "kara.cfg"
+    cfg.write_text(CFG)
+    out = tmp_path / "result.h5"
+    log = io.StringIO()
+    rc = run.main(["-c", str(cfg), "-o", str(out), "--SavePhaseSpace", "2"], out=log)
+    text = log.getvalue()
+    assert rc == 0, text
+    assert "Finished 250 steps" in text
+    assert os.path.exists(str(out) + ".cfg") and "GridSize=256" in open(str(out) + ".cfg").read()
+    try:
+        import h5py  # noqa: F401
+        pytest.skip("h5py present: the HDF5 file itself is checked in test_results_layout.py")
+    except ImportError:
+        pass
+    layout = json.load(open(str(out) + ".layout.json"))
+    data = np.load(str(out) + ".npz")
+    # 250 steps with an out-step every 50: rows at 0, 50, ..., 250 (src/main.cpp:961-1033 + the final save)
+    # (rows are [time][bunch][x] as in the reference's file, src/IO/HDF5File.cpp:60-75)
+    assert data["BunchProfile.data"].shape == (6, 1, 256)
+    assert layout["datasets"]["/BunchProfile/data"]["shape"] == [6, 1, 256]
+    assert data["CSR.Spectrum.data"].shape[0] == 6 and np.abs(data["CSR.Spectrum.data"]).max() > 0
+    assert np.allclose(data["Info.AxisValues_t"], np.arange(6) * 0.05)
+    # the same physics as the simulation object driven by hand
+    p = kara_params(grid_size=256, steps_per_Ts=1000, gap=-1.0, bunch_current=5e-5)
+    sim = capi.Simulation(ctx_fma, p, 1)
+    sim.renormalize()
+    sim.step(250)
+    prof = sim.download()[1][0]
+    sim.close()
+    assert np.array_equal(data["BunchProfile.data"][-1, 0], prof)
+
+
+def test_driver_refuses_what_it_cannot_do(tmp_path):
+    log = io.StringIO()
+    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3"], out=log) == 1
+    assert "multi-bunch" in log.getvalue()
+    log = io.StringIO()
+    assert run.main(["-c", "/dev/null", "-Z", "file.dat"], out=log) == 1
+    assert "Impedance" in log.getvalue()
+    log = io.StringIO()
+    assert run.main(["-c", str(tmp_path / "missing.cfg")], out=log) == 1
+    assert "does not exist" in log.getvalue()
