@@ -219,7 +219,8 @@ enum {
     IVS_SIM_QPT1 = 16u,         /* tuning: the streaming kernel (shared TMA ring) with one quad of columns per thread ... */
     IVS_SIM_QPT2 = 32u,         /* ... or two, instead of the column-block kernel */
     IVS_SIM_NO_PERSISTENT = 256u, /* one launch per step (CUDA graph) even where the whole run fits the machine at once and
-                                    ivs_sim_step would run its steps inside one persistent kernel (same results) */
+                                    ivs_sim_step would run its steps inside one persistent kernel (same results);
+                                    implied by IVS_SIM_TILED, _QPT1, _QPT2, _STREAM8 and _NO_GRAPH */
     IVS_SIM_TRACK_INLINE = 128u, /* tracked particles step in the context's stream after every fused step instead of
                                    on a side stream beside the next step (same results) */
     IVS_SIM_STREAM8 = 64u       /* the column-block kernel (8 adjacent columns per lane, warp-private rings): the

@@ -473,7 +473,9 @@ const void* resident_kernel(const ivs_ctx* ctx) {
 bool ivs_resident_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan) {
     plan->resident = false;
     const uint32_t n = s->n;
-    if ((s->desc.flags & IVS_SIM_NO_PERSISTENT) || n % 128 != 0 || n > 1024 || !plan->fp5) return false;
+    // a step kernel that was asked for by name (or direct launches) is what runs
+    const uint32_t named = IVS_SIM_NO_PERSISTENT | IVS_SIM_TILED | IVS_SIM_QPT1 | IVS_SIM_QPT2 | IVS_SIM_STREAM8 | IVS_SIM_NO_GRAPH;
+    if ((s->desc.flags & named) || n % 128 != 0 || n > 1024 || !plan->fp5) return false;
     if (s->members > (uint32_t)ctx->sm_count) return false;
     int coop = 0;
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) != cudaSuccess || !coop) return false;

@@ -26,7 +26,7 @@ if __name__ == "__main__":
     with capi.Context(0, capi.ARITH_FMA) as ctx:
         for name, kw in CASES:
             p = kara_params(**kw)
-            for flags, label in ((0, "fused"), (capi.SIM_NO_PERSISTENT, "per-step"), (capi.SIM_TILED, "tiled"),
+            for flags, label in ((0, "fused"), (capi.SIM_NO_PERSISTENT, "per-step"), (capi.SIM_TILED, "tiled"), (capi.SIM_QPT2, "ring-2q"),
                                  (capi.SIM_UNFUSED, "unfused")):
                 if only and label not in only:
                     continue
