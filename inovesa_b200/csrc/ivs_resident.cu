@@ -47,6 +47,7 @@ namespace {
 
 constexpr int kResThreads = 512;
 constexpr int kTagStride = 8;  // published row sums sit 64 B apart: the polls of 148 CTAs spread over the L2 slices (1, 4, 16 measured slower)
+constexpr uint32_t kMaxPolls = 1u << 24;  // about 10 s of polling: a step takes microseconds
 constexpr int kResPad = 32;  // zero cells left and right of a staged row: wake first tap in [-16, 8], RF in [-16, 12]
 
 struct resident_args {
@@ -88,8 +89,10 @@ __device__ __forceinline__ void await_rows_out(const uint32_t* flag, uint32_t ta
     uint32_t t;
     // acquire loads: a relaxed poll followed by an acquire fence costs 1300 cycles more per step (the fence
     // holds back the warp's next shared-memory accesses as well)
+    uint32_t tries = 0;
     do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(t) : "l"(flag) : "memory");
+        if (++tries > kMaxPolls) __trap();
     } while (t < tag);
 }
 // bit 31 of the tag: the publishing CTA's wake kick left the staged pad in that step (every CTA reads every
@@ -97,9 +100,10 @@ __device__ __forceinline__ void await_rows_out(const uint32_t* flag, uint32_t ta
 __device__ __forceinline__ float await_row_sum(const uint2* slot, uint32_t tag, uint32_t& flags) {
     // relaxed polls (acquire polls measured the same, sleeping between polls 10 % slower); the caller's
     // acquire fence after its last word orders what follows
-    uint32_t v, t;
+    uint32_t v, t, tries = 0;
     do {
         asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(slot) : "memory");
+        if (++tries > kMaxPolls) __trap();  // a block that never publishes is a bug: fail, do not hang
     } while ((t & 0x7fffffffu) != tag);
     flags |= t;
     return __uint_as_float(v);
@@ -516,7 +520,14 @@ ivs_status ivs_resident_run(ivs_ctx* ctx, const ivs_fused_plan* plan, const ivs_
     const dim3 grid(ivs_div_up(s->n, plan->res_rows), s->members);
     IVS_CUDA(ctx, cudaMemsetAsync(plan->res_tags, 0, resident_tag_bytes(ctx, s->members, s->n), ctx->stream));
     void* args[] = {(void*)&ra, (void*)&nsteps};
-    IVS_CUDA(ctx, cudaLaunchCooperativeKernel(resident_kernel(ctx), grid, dim3(kResThreads), args, plan->res_smem, ctx->stream));
+    const cudaError_t e = cudaLaunchCooperativeKernel(resident_kernel(ctx), grid, dim3(kResThreads), args, plan->res_smem, ctx->stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
+        // the device cannot hold the whole grid right now (shared with other work, MPS limits ...): not an
+        // error, the caller goes on with one launch per step
+        cudaGetLastError();
+        return IVS_ERR_UNSUPPORTED;
+    }
+    IVS_CUDA(ctx, e);
     IVS_LAUNCHED(ctx);
     return IVS_OK;
 }

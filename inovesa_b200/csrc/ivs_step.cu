@@ -295,10 +295,14 @@ static ivs_status enqueue_steps(ivs_sim* s, uint32_t nsteps) {
     // a run whose CTAs are all resident at once steps inside ONE persistent kernel (grid-wide barrier
     // instead of the kernel boundary); nothing else happens between two such steps
     if (!unfused && s->plan.resident && !s->np && !s->dyn_rf && left > 1) {
-        IVS_TRY(ivs_fused_enqueue_run(ctx, &s->plan, s, left));
-        s->steps_done += left;
-        s->fused_enqueued += left;
-        return IVS_OK;
+        const ivs_status st = ivs_fused_enqueue_run(ctx, &s->plan, s, left);
+        if (st == IVS_OK) {
+            s->steps_done += left;
+            s->fused_enqueued += left;
+            return IVS_OK;
+        }
+        if (st != IVS_ERR_UNSUPPORTED) return st;
+        s->plan.resident = false;  // the cooperative launch was refused: one launch per step from now on
     }
     if (use_graph) {
         const uint32_t K = ivs_sim::kGraphSteps;  // even: a replay leaves the parity as it was

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Randomised sweep: streaming kernel vs tile kernel vs unfused kernel sequence on random
+"""Randomised sweep: the default step path (persistent kernel where the run fits the machine, else
+the column-block kernel) vs one launch per step vs tile kernel vs unfused kernel sequence on random
 parameter combinations (interpolation order, Fokker-Planck type / derivation, RF model, drift
 polynomial, steps per period, current, grid size).  A development aid; tests/ has the fixed cases."""
 import os
@@ -39,7 +40,8 @@ if __name__ == "__main__":
                 cur = [max(kw["bunch_current"], 1e-9) * (1 + 0.3 * i) for i in range(members)]
                 out = {}
                 err = None
-                for name, flags in (("stream", 0), ("tiled", capi.SIM_TILED), ("unfused", capi.SIM_UNFUSED)):
+                for name, flags in (("stream", 0), ("perstep", capi.SIM_NO_PERSISTENT), ("tiled", capi.SIM_TILED),
+                                    ("unfused", capi.SIM_UNFUSED)):
                     try:
                         sim = capi.Simulation(ctx, p, members, flags=flags, bunch_currents=cur)
                         sim.step(steps)
@@ -53,11 +55,12 @@ if __name__ == "__main__":
                     continue
                 e_t = rel_l1(out["stream"][0], out["tiled"][0])
                 e_u = rel_l1(out["stream"][0], out["unfused"][0])
-                ok = e_t < 1e-6 and e_u < 1e-5 and np.all(np.isfinite(out["stream"][0]))
+                same = all(np.array_equal(a, b) for a, b in zip(out["stream"][:3], out["perstep"][:3]))  # bit for bit
+                ok = same and e_t < 1e-6 and e_u < 1e-5 and np.all(np.isfinite(out["stream"][0]))
                 bad += not ok
-                print("%2d mode %d n %4d it %d der %d fp %d lin %d I %.0e gap %+.0f spT %4d m %d s %2d: vs tiled %.1e vs unfused %.1e %s"
+                print("%2d mode %d n %4d it %d der %d fp %d lin %d I %.0e gap %+.0f spT %4d m %d s %2d: vs tiled %.1e vs unfused %.1e persistent == per-step %s %s"
                       % (k, mode, kw["grid_size"], kw["interpolation"], kw["derivation"], kw["fp_type"], kw["linear_rf"],
-                         kw["bunch_current"], kw["gap"], kw["steps_per_Ts"], members, steps, e_t, e_u, "ok" if ok else "MISMATCH"),
+                         kw["bunch_current"], kw["gap"], kw["steps_per_Ts"], members, steps, e_t, e_u, same, "ok" if ok else "MISMATCH"),
                       flush=True)
     print("FUZZ OK" if not bad else "FUZZ: %d mismatches" % bad)
     sys.exit(1 if bad else 0)

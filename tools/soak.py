@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Soak test of the streaming step kernel: many steps on several shapes, watching for traps
+"""Soak test of the step kernels (column-block, persistent): many steps on several shapes, watching for traps
 (a stalled barrier or mailbox traps instead of hanging), NaNs and charge drift."""
 import os
 import sys
@@ -18,6 +18,11 @@ CASES = [
     (dict(grid_size=512, bunch_current=400e-6), 37, 100000),
     (dict(grid_size=256), 256, 100000),
     (dict(grid_size=256, bunch_current=600e-6), 3, 200000),
+    # the persistent kernel (one cooperative launch per call)
+    (dict(grid_size=256), 1, 400000),
+    (dict(grid_size=512, bunch_current=300e-6, gap=0.032), 4, 200000),
+    (dict(grid_size=1024, steps_per_Ts=4000, gap=0.032, wall_conductivity=5.8e7, collimator=0.008), 1, 100000),
+    (dict(grid_size=768, steps_per_Ts=2000), 2, 100000),
 ]
 
 if __name__ == "__main__":
