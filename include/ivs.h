@@ -229,7 +229,12 @@ enum {
 
 ivs_status ivs_sim_create(ivs_ctx* ctx, const ivs_sim_desc* desc, ivs_sim** out);
 ivs_status ivs_sim_destroy(ivs_sim* sim);
-/* advance every member by nsteps (asynchronous) */
+/* Advance every member by nsteps (asynchronous): the loop body of main() (src/main.cpp:948-1053).
+ * A run that fits the machine at once -- grid up to 1024 x 1024, at most one block of rows per SM and
+ * member, no tracked particles, no DynamicRFKickMap -- does all nsteps inside ONE cooperative launch
+ * of the persistent kernel (csrc/ivs_resident.cu); everything else replays 16-step CUDA graphs of the
+ * fused step kernel (+ tracking / DynamicRFKickMap kernels), captured when the simulation was
+ * created.  The results do not depend on the route or on how the steps are split over calls. */
 ivs_status ivs_sim_step(ivs_sim* sim, uint32_t nsteps);
 /* steps taken so far */
 uint64_t ivs_sim_steps_done(const ivs_sim* sim);
