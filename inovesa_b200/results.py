@@ -160,11 +160,23 @@ class ResultFile:
         np.savez_compressed(path + ".npz", **{p.strip("/").replace("/", "."): a for p, a in d.items()})
         json.dump(self.layout(), open(path + ".layout.json", "w"), indent=1)
 
-    def to_hdf5(self, path):
-        try:
-            import h5py
-        except ImportError as e:  # not available in this image: say so, do not fake it
-            raise ImportError("h5py is needed to write HDF5; use ResultFile.save() for the npz + layout substitute") from e
+    def to_hdf5(self, path, native=None):
+        """write the HDF5 file: through h5py where it is importable (chunked, shuffled, deflated, extensible
+        like the reference's), else -- or with native=True -- through the pure-Python writer of h5native.py
+        (same groups, datasets, attributes and soft links, contiguous storage)"""
+        if native is None:
+            try:
+                import h5py  # noqa: F401
+                native = False
+            except ImportError:
+                native = True
+        if native:
+            from .h5native import write_hdf5
+            attrs = {p: {k: np.float64(v) for k, v in kv.items()} for p, kv in self.attrs.items()}
+            attrs["/Info/Parameters"] = {k: (v if isinstance(v, (int, float, str, bool, np.generic)) else str(v))
+                                         for k, v in self.parameters.items()}
+            return write_hdf5(path, self.datasets(), attrs, groups=GROUPS, soft_links=SOFT_LINKS)
+        import h5py
         with h5py.File(path, "w") as f:
             for g in GROUPS:
                 f.require_group(g)

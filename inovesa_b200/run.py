@@ -4,10 +4,9 @@ simulation loop with its out-step cadence and the result file.
 
     python -m inovesa_b200.run -c ring.cfg -T 2 -o result.h5 [--GridSize 512 ...]
 
-Writes `<output>.cfg` (the options that were set, as the reference does) and the result file:
-real HDF5 where h5py is importable, else `<output>.npz` + `<output>.layout.json` with the same
-dataset paths, shapes and attributes (results.py).  Needs a B200 and the built libivs.so; there
-is no CPU fallback.
+Writes `<output>.cfg` (the options that were set, as the reference does) and the HDF5 result file
+in the reference's layout (results.py: through h5py where it is importable, else through the
+pure-Python writer of h5native.py).  Needs a B200 and the built libivs.so; there is no CPU fallback.
 """
 import sys
 import time
@@ -104,13 +103,8 @@ def main(argv=None, out=sys.stdout):
     if ofname:
         open(ofname + ".cfg", "w").write(opts.save_text())
         say('Saved configuiration to "%s.cfg".' % ofname)  # (sic)
-        try:
-            rf.to_hdf5(ofname)
-            say('Saved results to "%s".' % ofname)
-        except ImportError:
-            rf.save(ofname)
-            say('No HDF5 library in this environment: saved results to "%s.npz" + "%s.layout.json" '
-                "(same dataset paths, shapes and attributes)." % (ofname, ofname))
+        rf.to_hdf5(ofname)  # h5py where it exists, else the pure-Python writer (h5native.py)
+        say('Saved results to "%s".' % ofname)
     else:
         say("Will not save results.")
     sim.close()

@@ -49,7 +49,7 @@ def test_paths_shapes_and_links_follow_the_reference():
     assert lay["datasets"]["/BunchLength/data"]["attrs"] == {"Meter": 8.2e-4, "Second": 8.2e-4 / 2.99792458e8}
 
 
-def test_save_round_trip_and_hdf5_gate(tmp_path):
+def test_save_round_trip_and_hdf5_file(tmp_path):
     rf = make()
     rf.add_parameter("grid_size", 16)
     rf.append_time_step(0.0, np.ones(16), 1.0, 0.0, np.ones(16), 1.0, 0.0)
@@ -59,14 +59,9 @@ def test_save_round_trip_and_hdf5_gate(tmp_path):
     assert z["BunchProfile.data"].shape == (1, 1, 16)
     lay = json.load(open(base + ".layout.json"))
     assert lay["group_attrs"]["/Info/Parameters"]["grid_size"] == 16
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(ImportError):
-            rf.to_hdf5(base + ".h5")
-    else:
-        rf.to_hdf5(base + ".h5")
-        assert os.path.getsize(base + ".h5") > 0
+    # through h5py where it exists, else through the pure-Python writer (tests/test_h5native.py reads it back)
+    rf.to_hdf5(base + ".h5")
+    assert open(base + ".h5", "rb").read(8) == b"\x89HDF\r\n\x1a\n"
 
 
 def test_unit_factors_equal_the_reference_objects(ref, capi):
