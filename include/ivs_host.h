@@ -93,6 +93,15 @@ int ivs_drift_slip(uint32_t n, float qmin, float qmax, float pmin, float pmax, f
 int ivs_make_impedance(size_t nfreqs, float fmax, double R_bend, double f_rev, double gap,
                        int use_csr, double s, double xi, double collimator, float* z,
                        int* nonzero);
+/* Impedance::readData (src/Z/Impedance.cpp:94-111): an impedance table from a text file of
+ * `line-number real imag` records (whitespace separated; a record whose line number repeats the
+ * previous one is skipped).  Up to `cap` complex<float> values are stored in z (interleaved re,im),
+ * *count = records in the file.  IVS_ERR_INVALID_ARGUMENT if the file cannot be opened. */
+int ivs_read_impedance_file(const char* path, float* z, size_t cap, size_t* count);
+/* `*rv += Impedance(impedance_file, fmax)` (src/Z/ImpedanceFactory.cpp:70-75): adds the first nfreqs
+ * records of the file to z.  A file with fewer records than nfreqs is refused (the reference reads past
+ * the end of its vector there). */
+int ivs_add_impedance_file(const char* path, float* z, size_t nfreqs);
 /* the wake impedance (src/main.cpp:717-721) and the radiation impedance (:724-727) */
 int ivs_wake_impedance(const ivs_ring_params* p, const ivs_derived* d, float* z, int* nonzero);
 int ivs_radiation_impedance(const ivs_ring_params* p, const ivs_derived* d, float* z);

@@ -90,6 +90,8 @@ SIGNATURES = {
     "ivs_make_impedance": (ci, [sz, cf, cd, cd, cd, ci, cd, cd, cd, _fp, C.POINTER(ci)]),
     "ivs_wake_impedance": (ci, [C.POINTER(RingParams), C.POINTER(Derived), _fp, C.POINTER(ci)]),
     "ivs_radiation_impedance": (ci, [C.POINTER(RingParams), C.POINTER(Derived), _fp]),
+    "ivs_read_impedance_file": (ci, [C.c_char_p, P, sz, C.POINTER(sz)]),
+    "ivs_add_impedance_file": (ci, [C.c_char_p, _fp, sz]),
     "ivs_initial_grid": (ci, [C.POINTER(Derived), u32, cd, _fp]),
     "ivs_gaussian_projection": (ci, [u32, cf, cf, cd, _fp]),
     "ivs_haissinski_grid": (ci, [C.POINTER(Derived), u32, _fp, P, u32, cf, u32, cd, _fp, C.POINTER(cd)]),
@@ -168,11 +170,28 @@ def make_impedance(nfreqs, fmax, R_bend, f_rev, gap, use_csr=1, s=0.0, xi=0.0, c
     return z, bool(nz.value)
 
 
-def wake_impedance(params, d):
+def wake_impedance(params, d, impedance_file=None):
+    """makeImpedance for the wake (src/main.cpp:717-721, src/Z/ImpedanceFactory.cpp:21-84); impedance_file:
+    a table of `line-number real imag` records added on top (:70-75)"""
     z = np.zeros((d.padded_bins, 2), f32)
     nz = ci(0)
     load().ivs_wake_impedance(C.byref(params), C.byref(d), z.reshape(-1), C.byref(nz))
+    if impedance_file:
+        rc = load().ivs_add_impedance_file(str(impedance_file).encode(), z.reshape(-1), d.padded_bins)
+        if rc:
+            raise IvsError(rc, "impedance file %s: cannot be read or has fewer than %d records" % (impedance_file, d.padded_bins))
+        return z, True
     return z, bool(nz.value)
+
+
+def read_impedance_file(path, cap=1 << 20):
+    """Impedance::readData (src/Z/Impedance.cpp:94-111): complex64 array"""
+    z = np.zeros((cap, 2), f32)
+    n = sz(0)
+    rc = load().ivs_read_impedance_file(str(path).encode(), z.ctypes.data_as(P), cap, C.byref(n))
+    if rc:
+        raise IvsError(rc, "impedance file %s cannot be opened" % path)
+    return z[: min(n.value, cap)].copy().view(np.complex64).reshape(-1)
 
 
 def radiation_impedance(params, d):
@@ -478,7 +497,7 @@ class Simulation:
     """
 
     def __init__(self, ctx, params, members=1, grid=None, particles=None, flags=0, tables=None,
-                 bunch_currents=None, seed=0, strips=0):
+                 bunch_currents=None, seed=0, strips=0, impedance_file=None):
         self.ctx, self.lib = ctx, ctx.lib
         self.params = params
         self.d = d = derive(params)
@@ -496,7 +515,7 @@ class Simulation:
         if "zwake" in t:
             zw = None if t["zwake"] is None else np.ascontiguousarray(t["zwake"], f32)
         else:
-            zw, nz = wake_impedance(params, d)
+            zw, nz = wake_impedance(params, d, impedance_file)
             zw = zw if nz else None
         self.nmax = d.padded_bins
         if grid is None:

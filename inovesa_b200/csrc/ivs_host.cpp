@@ -11,6 +11,8 @@
 #include <cmath>
 #include <complex>
 #include <cstring>
+#include <fstream>
+#include <limits>
 #include <vector>
 
 #include "../../include/ivs.h"
@@ -510,6 +512,39 @@ int ivs_wake_impedance(const ivs_ring_params* o, const ivs_derived* d, float* z,
     if (!o || !d) return IVS_ERR_INVALID_ARGUMENT;
     return ivs_make_impedance(d->padded_bins, d->fmax, d->R_bend, d->f_rev, o->gap, o->use_csr != 0,
                               o->wall_conductivity, o->wall_susceptibility, o->collimator, z, nonzero);
+}
+
+// Impedance::readData (src/Z/Impedance.cpp:94-111): `lineno real imag` records; the loop runs while the
+// stream is good, so the last record is extracted once more at the end of the file -- its repeated line
+// number is what keeps it from being stored twice, and what makes any repeated number skip its record
+int ivs_read_impedance_file(const char* path, float* z, size_t cap, size_t* count) {
+    if (!path || (!z && cap)) return IVS_ERR_INVALID_ARGUMENT;
+    std::ifstream is(path);
+    if (!is) return IVS_ERR_INVALID_ARGUMENT;
+    size_t lineno = 0, old_lineno = std::numeric_limits<size_t>::max(), n = 0;
+    float real = 0, imag = 0;
+    while (is.good()) {
+        is >> lineno >> real >> imag;
+        if (lineno != old_lineno) {
+            if (n < cap) { z[2 * n] = real; z[2 * n + 1] = imag; }
+            n++;
+        }
+        old_lineno = lineno;
+    }
+    if (count) *count = n;
+    return IVS_OK;
+}
+
+// src/Z/ImpedanceFactory.cpp:70-75 with Impedance::operator+= (src/Z/Impedance.cpp:67-76)
+int ivs_add_impedance_file(const char* path, float* z, size_t nfreqs) {
+    if (!z) return IVS_ERR_INVALID_ARGUMENT;
+    std::vector<float> f(2 * nfreqs);
+    size_t count = 0;
+    const int rc = ivs_read_impedance_file(path, f.data(), nfreqs, &count);
+    if (rc != IVS_OK) return rc;
+    if (count < nfreqs) return IVS_ERR_INVALID_ARGUMENT;
+    for (size_t i = 0; i < 2 * nfreqs; i++) z[i] += f[i];  // complex<float> += complex<float>
+    return IVS_OK;
 }
 
 // src/main.cpp:724-727

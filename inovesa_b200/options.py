@@ -4,7 +4,7 @@ precedence (command line over config file over defaults; the compatibility names
 `SyncFreq`, `steps` are aliases, :284-292,365-368).
 
 Options of subsystems that are out of scope here (GUI, OpenCL device, PNG / HDF5 start
-distributions, impedance files) are accepted where the reference ignores them without OpenCL / GUI
+distributions) are accepted where the reference ignores them without OpenCL / GUI
 support, and refused with a message where they would change the physics.
 """
 import os
@@ -240,8 +240,6 @@ class ProgramOptions:
     def unsupported(self):
         """options that would change the result and that this driver cannot honour"""
         bad = []
-        if self.values["Impedance"]:
-            bad.append("Impedance (impedance from a file, src/Z/Impedance.cpp:94-111)")
         if self.values["InitialDistFile"]:
             bad.append("InitialDistFile (start distribution from a PNG / HDF5 / text file)")
         return bad

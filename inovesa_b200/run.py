@@ -79,14 +79,17 @@ def main(argv=None, out=sys.stdout):
     parts = read_tracking_file(opts["tracking"]) if opts["tracking"] else None
     ctx = capi.Context(0, capi.ARITH_FMA)
     grid = capi.initial_grid(d, n, params.zoom)
-    sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts)
+    zfile = opts["Impedance"] or None
+    if zfile:
+        say('Reading impedance from: "%s"' % zfile)
+    sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts, impedance_file=zfile)
     if opts["RenormalizeCharge"] >= 0:
         sim.renormalize()  # the initial renormalisation (src/main.cpp:528-532)
     seq = rf_noise(opts, params, d, laststep, seed=1)
     if seq is not None:
         say("Building dynamic, %s RFKickMap..." % ("linear" if params.linear_rf else "nonlinear"))
         sim.set_rf_modulation(seq)
-    zw, nz = capi.wake_impedance(params, d)
+    zw, nz = capi.wake_impedance(params, d, zfile)
     say("Starting the simulation.")
     t0 = time.time()
 

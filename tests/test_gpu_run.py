@@ -65,8 +65,8 @@ def test_driver_refuses_what_it_cannot_do(tmp_path):
     assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3"], out=log) == 1
     assert "multi-bunch" in log.getvalue()
     log = io.StringIO()
-    assert run.main(["-c", "/dev/null", "-Z", "file.dat"], out=log) == 1
-    assert "Impedance" in log.getvalue()
+    assert run.main(["-c", "/dev/null", "-i", "start.png"], out=log) == 1
+    assert "InitialDistFile" in log.getvalue()
     log = io.StringIO()
     assert run.main(["-c", str(tmp_path / "missing.cfg")], out=log) == 1
     assert "does not exist" in log.getvalue()

@@ -103,3 +103,34 @@ def test_invalid_arguments(capi):
     assert lib.ivs_fokker_planck_weights(8, 1.0, -1.0, 1e-3, 3, 4, w) == capi.ERR_INVALID_ARGUMENT
     assert lib.ivs_fokker_planck_weights(8, -1.0, 1.0, 1e-3, 3, 5, w) == capi.ERR_INVALID_ARGUMENT
     assert lib.ivs_simpson_weights(1, 0.1, w) == capi.ERR_INVALID_ARGUMENT
+
+
+def test_impedance_from_a_file(tmp_path, capi):
+    """Impedance(std::string datafile, f_max) (src/Z/Impedance.cpp:51-57,94-111) on the reference's own
+    fixture and expectation (test/impedance.dat, test/TestImpedance.cpp:35-48: z[i] = (i - 2, 2.5 - i)),
+    the repeated-line-number rule, and `*rv += Impedance(file, fmax)` (src/Z/ImpedanceFactory.cpp:70-75)"""
+    import numpy as np
+    f = tmp_path / "impedance.dat"
+    f.write_text("1\t-2\t 2.5\n2\t-1\t 1.5\n3\t0\t 0.5\n4\t1\t-0.5\n5\t2\t-1.5\n6\t3\t-2.5\n")
+    z = capi.read_impedance_file(f)
+    assert z.dtype == np.complex64 and len(z) == 6
+    assert np.array_equal(z, np.array([complex(i - 2, 2.5 - i) for i in range(6)], np.complex64))
+    # a record whose line number repeats the previous one is skipped; no newline at the end of the file
+    g = tmp_path / "dup.dat"
+    g.write_text("1 1.0 0.0\n1 9.0 9.0\n2 2.0 -1.0\n7 3.5e0 4")
+    assert np.array_equal(capi.read_impedance_file(g), np.array([1, 2 - 1j, 3.5 + 4j], np.complex64))
+    with pytest.raises(capi.IvsError):
+        capi.read_impedance_file(tmp_path / "missing.dat")
+    # added on top of the generated wake impedance; a file shorter than the table is refused
+    from inovesa_b200.params import kara_params
+    p = kara_params(grid_size=16, padding=2.0)
+    d = capi.derive(p)
+    base, _ = capi.wake_impedance(p, d)
+    n = d.padded_bins
+    h = tmp_path / "full.dat"
+    h.write_text("".join("%d %r %r\n" % (i + 1, 0.25 * i, -0.5 * i) for i in range(n + 3)))
+    both, nz = capi.wake_impedance(p, d, h)
+    extra = np.stack([0.25 * np.arange(n), -0.5 * np.arange(n)], 1).astype(np.float32)
+    assert nz and np.array_equal(both, base + extra)
+    with pytest.raises(capi.IvsError):
+        capi.wake_impedance(p, d, f)

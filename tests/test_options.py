@@ -81,5 +81,5 @@ def test_refusals():
     with pytest.raises(OptionError):
         o.ring_params()  # two bunches
     o = ProgramOptions().parse(["-Z", "impedance.dat", "-i", "start.png"], read_file=lambda _: None)
-    assert len(o.unsupported()) == 2
+    assert len(o.unsupported()) == 1 and o["Impedance"] == "impedance.dat"  # impedance files are read
     assert all(len(v) == 4 for v in OPTIONS.values())
