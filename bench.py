@@ -157,6 +157,8 @@ def run_ours(args):
     arith = capi.ARITH_STRICT if args.arith == "strict" else capi.ARITH_FMA
     flags = capi.SIM_UNFUSED if args.unfused else 0
     flags |= {0: 0, 1: capi.SIM_QPT1, 2: capi.SIM_QPT2, 8: capi.SIM_STREAM8}[args.qpt]
+    if args.track_inline:
+        flags |= capi.SIM_TRACK_INLINE
     ctx = capi.Context(local_rank, arith)
     stream = torch.cuda.ExternalStream(ctx.lib.ivs_ctx_stream(ctx.h), device=local_rank)
     d = capi.derive(p)
@@ -511,6 +513,8 @@ def main():
     ap.add_argument("--repeats", type=int, default=7, help="timed blocks of --steps steps; the median counts")
     ap.add_argument("--qpt", type=int, default=0, choices=[0, 1, 2, 8], help="tuning: quads of columns per thread")
     ap.add_argument("--strips", type=int, default=0, help="tuning: strips per member (0 = planner)")
+    ap.add_argument("--track-inline", action="store_true",
+                    help="tuning: tracking kernel in the step stream instead of on the side stream")
     ap.add_argument("--e2e-steps", type=int, default=20, help="steps of the upload-every-step loop")
     ap.add_argument("--e2e-job-steps", type=int, default=1000,
                     help="steps of the end-to-end job (upload once, out-steps every 100, final download)")

@@ -171,36 +171,45 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
                                   float sigma, uint64_t seed, unsigned int* counter,
                                   const int* sim_status, int wb) {
     constexpr int P = kTrackPerThread;
-    // the fused step this launch belongs to (or an earlier one) left its staged pad and will be
-    // redone by the host: the particles stay where they are (ivs_fused.cu, step_ctl_begin)
-    // (wb >= 0: this launch may overlap the NEXT fused step; it stands down only if the step that
-    // filled wake buffer wb, or an earlier one, is the one that overflowed)
-    if (sim_status) {
-        const volatile int* st = sim_status;
-        const int first_bad = st[0];
-        if (wb < 0 ? first_bad != 0x7fffffff : first_bad <= st[2 + wb]) return;
-    }
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t member = blockIdx.y;
     const bool stochastic = w5 && fptrack == 3;
-    __shared__ unsigned long long skey;
-    if (stochastic) {
-        if (threadIdx.x == 0) {
-            const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(counter);
-            skey = mix64(seed ^ mix64(step));
-        }
-        __syncthreads();
-    }
-    if (i < quarter) {
-        float2* base = particles + (size_t)member * np;
-        float2 p[P];
-        bool on[P];
+    // The particles are requested first; the run's status words and the step counter are read by ONE
+    // thread per block while they travel (every thread reading those three words -- the same lines for
+    // 650 000 threads -- costs more than the block barrier that hands them round)
+    float2* base = particles + (size_t)member * np;
+    float2 p[P];
+    bool on[P];
+    const bool mine = i < quarter;
 #pragma unroll
-        for (int k = 0; k < P; k++) {
-            const uint32_t j = i + k * quarter;
-            on[k] = j < np;
-            p[k] = base[on[k] ? j : i];
+    for (int k = 0; k < P; k++) {
+        const uint32_t j = i + k * quarter;
+        on[k] = mine && j < np;
+        if (mine) p[k] = base[on[k] ? j : i];
+    }
+    __shared__ unsigned long long skey_s;
+    __shared__ int stand_down;
+    if (threadIdx.x == 0) {
+        // the fused step this launch belongs to (or an earlier one) left its staged pad and will be
+        // redone by the host: the particles stay where they are (ivs_fused.cu, step_ctl_begin)
+        // (wb >= 0: this launch may overlap the NEXT fused step; it stands down only if the step that
+        // filled wake buffer wb, or an earlier one, is the one that overflowed)
+        int down = 0;
+        if (sim_status) {
+            const volatile int* st = sim_status;
+            const int first_bad = st[0];
+            down = wb < 0 ? first_bad != 0x7fffffff : first_bad <= st[2 + wb];
         }
+        stand_down = down;
+        if (stochastic) {
+            const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(counter);
+            skey_s = mix64(seed ^ mix64(step));
+        }
+    }
+    __syncthreads();
+    if (stand_down) return;
+    const unsigned long long skey = stochastic ? skey_s : 0ull;
+    if (mine) {
         if (wake) {
             const float* wm = wake + (size_t)member * n;
 #pragma unroll
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(256) track_step_kernel(float2* __restrict__ pa
             if (on[k]) base[i + k * quarter] = p[k];
     }
     if (stochastic) {
-        __syncthreads();  // every thread of the block has used skey
+        __syncthreads();  // every thread of the block has read skey_s
         if (threadIdx.x == 0) {
             const unsigned int total = gridDim.x * gridDim.y;
             if (atomicAdd(counter + 2, 1u) == total - 1) {  // the last block: everybody has read the step
