@@ -56,6 +56,9 @@ namespace {
 #ifndef IVS_S8_PROBE_NOSTORE
 #define IVS_S8_PROBE_NOSTORE 0
 #endif
+#ifndef IVS_S8_STCS
+#define IVS_S8_STCS 1  // streaming (evict-first) stores of the output rows: 246.4 us against 247.5 with plain stores
+#endif
 #ifndef IVS_S8_UNROLL2
 #define IVS_S8_UNROLL2 0
 #endif
@@ -570,8 +573,13 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args 
                 if (o[0] == 123.456f) gout[0] = make_float4(o[0], o[1], o[2], o[3]);
                 if (o[4] == 123.456f) gout[1] = make_float4(o[4], o[5], o[6], o[7]);
 #else
+#if IVS_S8_STCS
+                __stcs(gout, make_float4(o[0], o[1], o[2], o[3]));
+                __stcs(gout + 1, make_float4(o[4], o[5], o[6], o[7]));
+#else
                 gout[0] = make_float4(o[0], o[1], o[2], o[3]);
                 gout[1] = make_float4(o[4], o[5], o[6], o[7]);
+#endif
 #endif
                 gout += gstride;
                 if (red_lane && orow >= 5) asm volatile("st.shared.f32 [%0], %1;" ::"r"(redp), "f"(ps) : "memory");
