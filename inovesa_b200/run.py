@@ -21,14 +21,21 @@ f32 = np.float32
 TWO_PI = 6.283185307179586
 
 
-def read_tracking_file(path):
-    """start positions of the particles to track, one `x y` pair (grid points) per line
-    (src/main.cpp:801-824)"""
+def read_tracking_file(path, d, n):
+    """start positions of the particles to track: `q p` pairs in axis units (natural bunch lengths /
+    energy spreads), turned into grid coordinates by PhaseSpace::x() / y() -- (q - qmin) / dq clamped
+    to [0, n - 1], fp32 -- as src/main.cpp:762-771 and inc/PS/PhaseSpace.hpp:272-283 do; reading stops at
+    the first token that is not a number, like `while (trackingfile >> q >> p)`"""
     pts = []
-    for line in open(path):
-        t = line.split("#", 1)[0].split()
-        if len(t) >= 2:
-            pts.append((float(t[0]), float(t[1])))
+    toks = open(path).read().split()
+    for k in range(0, len(toks) - 1, 2):
+        try:
+            q, p = f32(float(toks[k])), f32(float(toks[k + 1]))
+        except ValueError:
+            break
+        x = min(max(f32(0.0), f32(f32(q - f32(d.qmin)) / f32(d.dq))), f32(n - 1.0))
+        y = min(max(f32(0.0), f32(f32(p - f32(d.pmin)) / f32(d.dp))), f32(n - 1.0))
+        pts.append((x, y))
     return np.asarray(pts, f32).reshape(-1, 2)
 
 
@@ -76,7 +83,11 @@ def main(argv=None, out=sys.stdout):
     say("Grid %d x %d, %g steps per synchrotron period, %d steps, bunch current %g A" % (
         n, n, d.steps, laststep, params.bunch_current))
     say("Natural bunch length %.4g m, energy spread %.4g eV, padded profile %d bins" % (d.bl, d.dE, d.padded_bins))
-    parts = read_tracking_file(opts["tracking"]) if opts["tracking"] else None
+    parts = read_tracking_file(opts["tracking"], d, n) if opts["tracking"] not in ("", "/dev/null") else None
+    if parts is not None:
+        say("Will do particle tracking with %d particles." % len(parts))
+        if not len(parts):
+            parts = None
     ctx = capi.Context(0, capi.ARITH_FMA)
     grid = capi.initial_grid(d, n, params.zoom)
     zfile = opts["Impedance"] or None

@@ -83,3 +83,17 @@ def test_refusals():
     o = ProgramOptions().parse(["-Z", "impedance.dat", "-i", "start.png"], read_file=lambda _: None)
     assert len(o.unsupported()) == 1 and o["Impedance"] == "impedance.dat"  # impedance files are read
     assert all(len(v) == 4 for v in OPTIONS.values())
+
+
+def test_tracking_file_positions_become_grid_coordinates(tmp_path):
+    """src/main.cpp:762-771: `q p` pairs in axis units -> PhaseSpace::x(q), y(p) (inc/PS/PhaseSpace.hpp:272-283)"""
+    import numpy as np
+    from types import SimpleNamespace
+    from inovesa_b200.run import read_tracking_file
+    f = tmp_path / "track.txt"
+    f.write_text("0 0\\n-6 6\\n1.5 -2.25\\n100 -100\\nend\\n")
+    d = SimpleNamespace(qmin=-6.0, pmin=-6.0, dq=12.0 / 255, dp=12.0 / 255)
+    p = read_tracking_file(f, d, 256)
+    dq = np.float32(12.0 / 255)
+    want = [[np.float32(6.0) / dq, np.float32(6.0) / dq], [0, 255], [np.float32(7.5) / dq, np.float32(3.75) / dq], [255, 0]]
+    assert p.dtype == np.float32 and np.array_equal(p, np.asarray(want, np.float32))
