@@ -91,7 +91,7 @@ def test_tracking_file_positions_become_grid_coordinates(tmp_path):
     from types import SimpleNamespace
     from inovesa_b200.run import read_tracking_file
     f = tmp_path / "track.txt"
-    f.write_text("0 0\\n-6 6\\n1.5 -2.25\\n100 -100\\nend\\n")
+    f.write_text("0 0\n-6 6\n1.5 -2.25\n100 -100\nend\n")
     d = SimpleNamespace(qmin=-6.0, pmin=-6.0, dq=12.0 / 255, dp=12.0 / 255)
     p = read_tracking_file(f, d, 256)
     dq = np.float32(12.0 / 255)
