@@ -45,10 +45,10 @@ from inovesa_b200.params import kara_params  # noqa: E402
 f32 = np.float32
 ALGO_BYTES_PER_CELL = 8.0  # one fp32 read + one fp32 write of the grid per step
 # dram__bytes_read.sum + dram__bytes_write.sum of one stream8_step_kernel launch on the benchmark
-# batch (26 x 2048^2), from the ncu --set full capture kept in profiles/r2_ncu_stream8_step_dram.txt
+# batch (26 x 2048^2), from the ncu --set full capture kept in profiles/r2_ncu_raw_metrics.txt
 # (updated per round)
 TRAFFIC_MEMBERS = 26
-TRAFFIC_BYTES_PER_LAUNCH = 848426240  # r2: 448.5 MB read + 399.9 MB written; algorithmic 872.4 MB
+TRAFFIC_BYTES_PER_LAUNCH = 843513344  # r2: 448.5 MB read + 395.0 MB written; algorithmic 872.4 MB
 
 
 def workload_params(name):
