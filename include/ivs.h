@@ -211,8 +211,8 @@ typedef struct ivs_sim_desc {
 } ivs_sim_desc;
 
 enum {
-    IVS_SIM_WAKE_FFT = 1u,      /* per-step wake potential through the FFT kernel instead of the
-                                   Toeplitz product (same operator) */
+    /* 1u: reserved (was IVS_SIM_WAKE_FFT, never implemented: the kernel sequence of IVS_SIM_UNFUSED is the
+       path that forms the wake potential with the FFT kernel) */
     IVS_SIM_UNFUSED = 2u,       /* run the step as the reference's kernel sequence (debug / parity) */
     IVS_SIM_NO_GRAPH = 4u,      /* launch kernels directly instead of replaying a CUDA graph */
     IVS_SIM_TILED = 8u,         /* fused step as the tile kernel instead of the streaming pipeline */

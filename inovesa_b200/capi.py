@@ -20,7 +20,7 @@ f32 = np.float32
 IVS_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_HALO, ERR_NO_DEVICE = 1, 2, 3, 4, 5
 ARITH_FMA, ARITH_STRICT = 0, 1
-SIM_WAKE_FFT, SIM_UNFUSED, SIM_NO_GRAPH, SIM_TILED, SIM_QPT1, SIM_QPT2, SIM_STREAM8, SIM_TRACK_INLINE, SIM_NO_PERSISTENT = 1, 2, 4, 8, 16, 32, 64, 128, 256
+SIM_UNFUSED, SIM_NO_GRAPH, SIM_TILED, SIM_QPT1, SIM_QPT2, SIM_STREAM8, SIM_TRACK_INLINE, SIM_NO_PERSISTENT = 2, 4, 8, 16, 32, 64, 128, 256
 
 P, u32, u64, cf, cd, ci, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_int, C.c_size_t
 _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
