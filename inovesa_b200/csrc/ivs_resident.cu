@@ -486,7 +486,7 @@ bool ivs_resident_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan) {
     const uint32_t H = plan->halo_lo + plan->halo_hi;
     const uint32_t blocks = std::min<uint32_t>((uint32_t)ctx->sm_count / s->members, n);  // per member
     const uint32_t rows = ivs_div_up(n, blocks);
-    if (rows + H > 64) return false;  // one pass of the wake product
+    // (what bounds the block of rows is shared memory: rows + halo staged and kicked rows of n cells each)
     uint32_t wwin_len = 0;
     const size_t sb = resident_smem(n, rows, H, &wwin_len);
     if (sb > (size_t)kIvsMaxOptinSmem) return false;

@@ -24,6 +24,9 @@ CASES = [
     (dict(grid_size=512, interpolation=3, derivation=3), 1),           # quadratic taps, 3-point stencil
     (dict(grid_size=512, steps_per_Ts=500), 1),                        # displacements of several cells, wide drift halo
     (dict(grid_size=2048, steps_per_Ts=4000, linear_rf=0, alpha1=2e-4, alpha2=3e-3), 1),  # too large: one launch per step
+    # ensembles whose members get few blocks of many rows each (64 + halo, 32 + halo)
+    (dict(grid_size=256, bunch_current=80e-6), 30),
+    (dict(grid_size=512, steps_per_Ts=2000), 9),
     # grid sizes that are multiples of 128 but not of 256: 1, 3, 5, 7 segments per row
     (dict(grid_size=128), 1),
     (dict(grid_size=384, steps_per_Ts=2000), 2),
