@@ -253,3 +253,58 @@ def write_hdf5(path, datasets, attrs=None, groups=(), soft_links=None):
     with open(path, "wb") as f:
         f.write(out)
     return eof
+
+
+# ---- reading back what write_hdf5 wrote (start distributions from an earlier result file) -----
+
+def read_dataset(path, dataset):
+    """the array of one dataset of a file written by write_hdf5 (superblock v2, compact groups, contiguous
+    little-endian data); files of libhdf5 with chunked storage need h5py"""
+    f = open(path, "rb").read()
+    if f[:8] != b"\x89HDF\r\n\x1a\n":
+        raise ValueError("%s is not an HDF5 file" % path)
+    if f[8] != 2 or f[9] != 8 or f[10] != 8:
+        raise ValueError("%s: superblock version %d is not what this reader knows (use h5py)" % (path, f[8]))
+    if struct.unpack_from("<I", f, 44)[0] != lookup3(f[:44]):
+        raise ValueError("%s: superblock checksum" % path)
+    addr = struct.unpack_from("<Q", f, 36)[0]
+
+    def messages(a):
+        if f[a:a + 4] != b"OHDR" or f[a + 4] != 2 or f[a + 5] != 0x02:
+            raise ValueError("%s: object header at %d is not of the kind write_hdf5 writes (use h5py)" % (path, a))
+        size = struct.unpack_from("<I", f, a + 6)[0]
+        end = a + 10 + size
+        if struct.unpack_from("<I", f, end)[0] != lookup3(f[a:end]):
+            raise ValueError("%s: object header checksum at %d" % (path, a))
+        p = a + 10
+        while p < end:
+            mtype, msize, _ = struct.unpack_from("<BHB", f, p)
+            yield mtype, f[p + 4:p + 4 + msize]
+            p += 4 + msize
+
+    for name in _split(dataset):
+        nxt = None
+        for mtype, b in messages(addr):
+            if mtype != 0x06 or b[1] & 0x08:  # hard links only
+                continue
+            n = b[2]
+            if b[3:3 + n].decode() == name:
+                nxt = struct.unpack_from("<Q", b, 3 + n)[0]
+        if nxt is None:
+            raise KeyError("%s: no %s" % (path, dataset))
+        addr = nxt
+    shape = dt = lay = None
+    for mtype, b in messages(addr):
+        if mtype == 0x01:
+            shape = struct.unpack_from("<%dQ" % b[1], b, 4) if b[1] else ()
+        elif mtype == 0x03:
+            size = struct.unpack_from("<I", b, 4)[0]
+            cls = b[0] & 15
+            dt = np.dtype("<f%d" % size) if cls == 1 else np.dtype("<%s%d" % ("i" if b[1] & 8 else "u", size)) if cls == 0 else None
+        elif mtype == 0x08:
+            lay = struct.unpack_from("<BBQQ", b, 0)
+    if shape is None or dt is None or lay is None or lay[1] != 1:
+        raise ValueError("%s: %s is not a contiguous numeric dataset (use h5py)" % (path, dataset))
+    if lay[3] == 0:
+        return np.zeros(shape, dt)
+    return np.frombuffer(f[lay[2]:lay[2] + lay[3]], dt).reshape(shape).copy()

@@ -240,8 +240,9 @@ class ProgramOptions:
     def unsupported(self):
         """options that would change the result and that this driver cannot honour"""
         bad = []
-        if self.values["InitialDistFile"]:
-            bad.append("InitialDistFile (start distribution from a PNG / HDF5 / text file)")
+        f = self.values["InitialDistFile"]
+        if f and not f.endswith((".h5", ".hdf5")):
+            bad.append("InitialDistFile (start distribution from a PNG or text file; result files (.h5) are read)")
         return bad
 
     def save_text(self):

@@ -39,6 +39,28 @@ def read_tracking_file(path, d, n):
     return np.asarray(pts, f32).reshape(-1, 2)
 
 
+def read_start_distribution(path, step):
+    """makePSFromHDF5 / HDF5File::readPhaseSpace (src/IO/HDF5File.cpp:425-480): row (rows + step) % rows of
+    /PhaseSpace/data of an earlier result file; the grid size is the file's"""
+    try:
+        import h5py
+        with h5py.File(path, "r") as f:
+            ps = np.asarray(f["/PhaseSpace/data"])
+    except ImportError:
+        from .h5native import read_dataset
+        ps = read_dataset(path, "/PhaseSpace/data")
+    if ps.ndim not in (3, 4) or ps.shape[0] == 0:
+        raise OptionError("%s: /PhaseSpace/data holds no phase space" % path)
+    row = ps[(ps.shape[0] + step) % ps.shape[0]]
+    if row.ndim == 3:
+        if row.shape[0] != 1:
+            raise OptionError("%s: %d bunches (multi-bunch runs are not supported)" % (path, row.shape[0]))
+        row = row[0]
+    if row.shape[0] != row.shape[1]:
+        raise OptionError("%s: phase space is not square" % path)
+    return np.ascontiguousarray(row, f32)
+
+
 def rf_noise(opts, params, d, laststep, seed):
     """the queue of (phase, amplitude) pairs of a DynamicRFKickMap, or None for the static map
     (src/main.cpp:332-346,594-621)"""
@@ -69,6 +91,15 @@ def main(argv=None, out=sys.stdout):
     except OptionError as e:
         say("Error: %s" % e)
         return 1
+    grid = None
+    if opts["InitialDistFile"]:  # (.h5 / .hdf5: checked by ProgramOptions.unsupported)
+        say('Reading in initial distribution from: "%s"' % opts["InitialDistFile"])
+        try:
+            grid = read_start_distribution(opts["InitialDistFile"], opts["InitialDistStep"])
+        except (OptionError, OSError, KeyError, ValueError) as e:
+            say("Error reading %s: %s" % (opts["InitialDistFile"], e))
+            return 0  # (EXIT_SUCCESS, src/main.cpp:509-512)
+        params.grid_size = grid.shape[0]
     d = capi.derive(params)
     laststep = int(np.floor(d.steps * opts["rotations"] + 0.5)) if opts["rotations"] > 0 else 0
     ofname = opts["output"]
@@ -89,7 +120,8 @@ def main(argv=None, out=sys.stdout):
         if not len(parts):
             parts = None
     ctx = capi.Context(0, capi.ARITH_FMA)
-    grid = capi.initial_grid(d, n, params.zoom)
+    if grid is None:
+        grid = capi.initial_grid(d, n, params.zoom)
     zfile = opts["Impedance"] or None
     if zfile:
         say('Reading impedance from: "%s"' % zfile)

@@ -60,6 +60,26 @@ def test_driver_runs_a_config_and_writes_the_result_layout(tmp_path, capi, ctx_f
     assert np.array_equal(data["/BunchProfile/data"][-1, 0], prof)
 
 
+def test_driver_resumes_from_a_result_file(tmp_path, capi, ctx_fma):
+    """-i result.h5 (src/IO/HDF5File.cpp:425-480, src/main.cpp:497-512): the last saved phase space of one run is
+    the start distribution of the next; 100 + 100 steps equal 200 steps in one go bit for bit (the initial
+    renormalisation of a resumed run is switched off: it would rescale by the charge's round-off)"""
+    cfg = tmp_path / "kara.cfg"
+    cfg.write_text(CFG.replace("rotations = 0.25", "rotations = 0.1"))
+    a, b, c = (str(tmp_path / n) for n in ("a.h5", "b.h5", "c.h5"))
+    log = io.StringIO()
+    assert run.main(["-c", str(cfg), "-o", a], out=log) == 0, log.getvalue()
+    assert run.main(["-c", str(cfg), "-o", b, "-i", a, "--RenormalizeCharge", "-1", "--GridSize", "64"], out=log) == 0, log.getvalue()
+    assert run.main(["-c", str(cfg), "-o", c, "-T", "0.2"], out=log) == 0, log.getvalue()
+    assert 'Reading in initial distribution from: "%s"' % a in log.getvalue()
+    from inovesa_b200.h5native import read_dataset
+    end_b = read_dataset(b, "/PhaseSpace/data")[-1, 0]
+    end_c = read_dataset(c, "/PhaseSpace/data")[-1, 0]
+    assert end_b.shape == (256, 256)  # the file's grid size, not --GridSize
+    assert np.array_equal(end_b, end_c)
+    assert np.array_equal(read_dataset(b, "/BunchProfile/data")[-1, 0], read_dataset(c, "/BunchProfile/data")[-1, 0])
+
+
 def test_driver_refuses_what_it_cannot_do(tmp_path):
     log = io.StringIO()
     assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3"], out=log) == 1

@@ -41,6 +41,12 @@ def test_round_trip_of_every_supported_thing(tmp_path):
         v = np.asarray(v)
         assert d[k].dtype == v.dtype and d[k].shape == v.shape and np.array_equal(d[k], v), k
     assert l == links
+    # the package's own reader (start distributions from an earlier result file, run.py -i)
+    from inovesa_b200.h5native import read_dataset
+    for k, v in data.items():
+        assert np.array_equal(read_dataset(path, k), np.asarray(v)), k
+    with pytest.raises(KeyError):
+        read_dataset(path, "/A/missing")
     assert a["/A/data"]["Meter"] == 1.5e-3 and a["/A/data"]["Second"] == np.float32(2.0)
     assert a["/A"]["note"] == b"hello" and a["/A"]["n"] == 7
     assert np.array_equal(a["/Info"]["vec"], [0.0, 1.0, 2.0]) and a["/Info"]["flag"] == 1
