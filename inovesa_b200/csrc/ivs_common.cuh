@@ -32,6 +32,7 @@ struct ivs_ctx {
     void* twiddle[16] = {nullptr};
     uint32_t twiddle_n[16] = {0};
     float* scratch = nullptr;  // small device scratch (integrals, flags)
+    uint32_t track_slots = 0, track_slots_n = 0;  // blocks of track_step_staged_kernel resident at once, for tables of track_slots_n
     uint32_t optin = 0;        // kernels already opted in to large dynamic shared memory (bit 0: rotate_tile_kernel, bit 1: field_kernel)
 };
 

@@ -187,6 +187,21 @@ def test_fused_tracking_matches_unfused(capi, ctx_strict, rng):
     assert e.value.code == capi.ERR_UNSUPPORTED
 
 
+def test_tracking_with_staged_tables_equals_tracking_with_gathers(capi, ctx_strict, rng):
+    """The tracking kernel of a fused step stages the kick tables in shared memory when the particle
+    count is even (csrc/ivs_track.cu, track_step_staged_kernel) and gathers them from global memory
+    otherwise (track_step_kernel): one more particle switches the kernel, the others must not notice;
+    both in one launch with several chunks per member and in a batch of members"""
+    p = kara_params(grid_size=256)
+    p.fp_track = 1
+    parts = (rng.random((6001, 2)) * 200 + 28).astype(f32)
+    for members in (1, 3):
+        (_, _, _, even), = _states(capi, ctx_strict, p, 0, [37], particles=parts[:6000], members=members)
+        (_, _, _, odd), = _states(capi, ctx_strict, p, 0, [37], particles=parts, members=members)
+        assert even.shape[-2] == 6000 and odd.shape[-2] == 6001
+        assert np.array_equal(even, odd[..., :6000, :])
+
+
 def test_stochastic_tracking_is_reproducible_and_graph_safe(capi, ctx_fma, rng):
     """FPTracking::stochastic (src/SM/FokkerPlanckMap.cpp:262-266): the generator is keyed on a
     device-side step counter, so replayed CUDA graphs, direct launches and any split of the step
