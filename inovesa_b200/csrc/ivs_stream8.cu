@@ -97,7 +97,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
 }
 
 template <bool FMA>
-__global__ void __launch_bounds__(256, 1) stream8_step_kernel(const stream_args sa) {
+#ifdef IVS_S8_MAXNREG
+__global__ void __maxnreg__(IVS_S8_MAXNREG) stream8_step_kernel(
+#else
+__global__ void __launch_bounds__(256, 1) stream8_step_kernel(
+#endif
+    const stream_args sa) {
     const fused_args& g = sa.f;
     extern __shared__ __align__(128) float smem[];
     __shared__ int ctl[2];
