@@ -147,6 +147,15 @@ ivs_status ivs_moments(ivs_ctx* ctx, const void* d_proj, uint32_t n, float amin,
 ivs_status ivs_wake_potential(ivs_ctx* ctx, const void* d_profile, uint32_t n,
                               const void* d_impedance, uint32_t nmax, float wakescaling,
                               void* d_wake, void* d_formfactor);
+/* ElectricField::wakePotential for a TRAIN of nb bunches (PhaseSpace::nb > 1, src/PS/ElectricField.cpp:
+ * 186-263 with padBunchProfiles :255-263; the filling pattern of src/main.cpp:248-321): d_profiles [nb][n]
+ * floats (each bunch's X projection, carrying its charge fraction), d_windows = the nb * nb * 2 n doubles of
+ * ivs_train_wake_windows (ivs_host.h) on the device, d_wake [nb][n] floats.  The reference transforms one
+ * padded array of nmax = spaced_bins points per step; here the same circular convolution is a Toeplitz
+ * product per pair of bunches against windows of the static wake function, accumulated in double
+ * (agrees with the reference's fp32 transforms to their rounding, ~1e-6 of the largest value). */
+ivs_status ivs_train_wake_potential(ivs_ctx* ctx, const void* d_profiles, uint32_t n, uint32_t nb,
+                                    const void* d_windows, float wakescaling, void* d_wake);
 /* The wake FUNCTION of the same operator, w[m], m = -(n-1)..(n-1) (2n-1 floats, w[0] at
  * index n-1), such that wakePotential()[x] == sum_x' profile[x'] * w[x - x'] exactly in
  * real arithmetic (the zero padding nmax >= 2n removes every circular wrap).  Used by the
@@ -301,6 +310,21 @@ typedef struct ivs_rf_model {
  * ivs_sim_create.  The reference applies a DynamicRFKickMap on the CPU only (no OpenCL path, hpp:75). */
 ivs_status ivs_sim_set_rf_modulation(ivs_sim* sim, const ivs_rf_model* model, const float* phase_ampl,
                                      uint32_t count);
+
+/* Makes the members of a simulation the bunches of ONE train (PhaseSpace::nb = members): from the next
+ * step on, the wake potential of member b is the train's (ivs_train_wake_potential: every bunch acts on
+ * every other through the wake function at their distance bucket * spacing_bins), the other maps stay per
+ * bunch as in SourceMap::apply's loop over PhaseSpace::nb.  bucket: `members` bucket numbers as
+ * src/main.cpp:258-268 enumerates them; z: the wake impedance at the SPACED length nmax (:318-321, :718),
+ * a power of two with bucket * spacing_bins + n <= nmax; wakescaling = ElectricField::_wakescaling of the
+ * whole beam (Ib = sum of the bunch currents, already divided by nmax), applied to every bunch -- the
+ * grids carry the charge fractions (src/PS/PhaseSpace.cpp:17-66 with `filling`).  The simulation must have
+ * been created with IVS_SIM_UNFUSED and a wake impedance (a train steps through the kernel sequence);
+ * else IVS_ERR_UNSUPPORTED.  The kick of bunch b uses bunch b's wake potential, as the reference's OpenCL
+ * kernel does; its CPU loop reads the offsets of bunches > 0 from the wrong place (src/SM/KickMap.cpp:244-259
+ * lacks the factor _ip in the bunch offset), which is not reproduced. */
+ivs_status ivs_sim_set_bunch_train(ivs_sim* sim, const uint32_t* bucket, uint32_t spacing_bins, const float* z,
+                                   uint32_t nmax, float wakescaling);
 
 #ifdef __cplusplus
 }

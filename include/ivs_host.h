@@ -132,6 +132,16 @@ int ivs_rf_modulation(uint64_t seed, uint32_t steps, float phasespread, float am
 int ivs_haissinski_grid(const ivs_derived* d, uint32_t n, const float* rf_offset, const float* zwake,
                         uint32_t nmax, float wakescaling, uint32_t iterations, double relax, float* grid,
                         double* residual);
+/* Wake-function windows of a train of bunches (PhaseSpace::nb > 1, src/main.cpp:248-321): the reference
+ * places the profile of bunch b at bucket[b] * spacing_bins of ONE padded array of nmax = nFreqs bins and
+ * reads its wake potential back from there (src/PS/ElectricField.cpp:236-263), so bunch b' acts on bunch b
+ * through the (circular) wake function at lags (bucket[b] - bucket[b']) * spacing_bins + x - x'.
+ * windows: nb * nb * 2 n doubles, window (b, b') entry m + n - 1 = lag (..) + m, m = -(n-1)..(n-1); input of
+ * ivs_train_wake_potential / ivs_sim_set_bunch_train (ivs.h).  z: nmax complex<float> (ivs_make_impedance
+ * with nfreqs = the spaced length), nmax a power of two.  Returns 0, -1 for bad arguments, -2 if a bunch
+ * does not fit the padded array. */
+int ivs_train_wake_windows(const float* z, uint32_t nmax, uint32_t n, uint32_t nb, const uint32_t* bucket,
+                           uint32_t spacing_bins, double* windows);
 /* Airy functions used by the parallel-plates impedance (src/Z/ParallelPlatesCSR.cpp:48-53);
  * returns 0, or 1 if Bi/Bi' overflow a double (Boost would throw there) */
 int ivs_airy(double x, double* ai, double* aip, double* bi, double* bip);

@@ -14,7 +14,8 @@
 //
 // Deliberate differences, all forced by "many simulations per process, one GPU path":
 //   * the grid size is a constructor argument of PhaseSpace (the reference keeps it in process-wide
-//     statics, inc/PS/PhaseSpace.hpp:336-356); single bunch only (as the reference's OpenCL path);
+//     statics, inc/PS/PhaseSpace.hpp:336-356); single bunch only in this C++ mirror (a train of bunches goes through
+//     ivs_sim_set_bunch_train of the C ABI, ivs.h);
 //   * there is no CPU path: a null handler is std::invalid_argument, a device error is
 //     vfps::DeviceError (the reference's cl::Error), never a silent fall-back;
 //   * host mirrors are stale until syncDevice(dev2cpu) (the reference's syncCLMem contract,

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libivs.so")
 
-CU = ["ivs_api.cu", "ivs_maps.cu", "ivs_reduce.cu", "ivs_field.cu", "ivs_track.cu", "ivs_dynrf.cu",
+CU = ["ivs_api.cu", "ivs_maps.cu", "ivs_reduce.cu", "ivs_field.cu", "ivs_track.cu", "ivs_dynrf.cu", "ivs_train.cu",
       "ivs_step.cu", "ivs_fused.cu", "ivs_stream8.cu", "ivs_resident.cu"]
 CPP = ["ivs_host.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

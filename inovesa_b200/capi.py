@@ -24,6 +24,8 @@ SIM_UNFUSED, SIM_NO_GRAPH, SIM_TILED, SIM_QPT1, SIM_QPT2, SIM_STREAM8, SIM_TRACK
 
 P, u32, u64, cf, cd, ci, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_int, C.c_size_t
 _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_up = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 # name -> (restype, argtypes); every symbol include/*.h declares
 SIGNATURES = {
@@ -59,6 +61,7 @@ SIGNATURES = {
     "ivs_moments": (ci, [P, P, u32, cf, cf, P, P]),
     "ivs_wake_potential": (ci, [P, P, u32, P, u32, cf, P, P]),
     "ivs_wake_function": (ci, [P, P, u32, cf, u32, P]),
+    "ivs_train_wake_potential": (ci, [P, P, u32, u32, P, cf, P]),
     "ivs_csr_power": (ci, [P, P, u32, P, u32, cf, cf, cf, P, P]),
     "ivs_track_kick": (ci, [P, P, u32, P, u32, ci]),
     "ivs_track_fokker_planck": (ci, [P, P, u32, P, u32, P, u32, cf, cf, u64, u64]),
@@ -77,6 +80,7 @@ SIGNATURES = {
     "ivs_sim_renormalize": (ci, [P]),
     "ivs_sim_set_rf_offset": (ci, [P, _fp]),
     "ivs_sim_set_rf_modulation": (ci, [P, C.POINTER(RfModel), P, u32]),
+    "ivs_sim_set_bunch_train": (ci, [P, _up, u32, _fp, u32, cf]),
     "ivs_rf_model_init": (ci, [C.POINTER(RingParams), C.POINTER(Derived), C.POINTER(RfModel)]),
     "ivs_rf_modulation": (ci, [u64, u32, cf, cf, cf, cd, cd, cf, P, _fp]),
     # include/ivs_host.h
@@ -95,6 +99,7 @@ SIGNATURES = {
     "ivs_initial_grid": (ci, [C.POINTER(Derived), u32, cd, _fp]),
     "ivs_gaussian_projection": (ci, [u32, cf, cf, cd, _fp]),
     "ivs_haissinski_grid": (ci, [C.POINTER(Derived), u32, _fp, P, u32, cf, u32, cd, _fp, C.POINTER(cd)]),
+    "ivs_train_wake_windows": (ci, [_fp, u32, u32, u32, _up, u32, _dp]),
     "ivs_airy": (ci, [cd] + [C.POINTER(cd)] * 4),
 }
 
@@ -170,16 +175,23 @@ def make_impedance(nfreqs, fmax, R_bend, f_rev, gap, use_csr=1, s=0.0, xi=0.0, c
     return z, bool(nz.value)
 
 
-def wake_impedance(params, d, impedance_file=None):
+def wake_impedance(params, d, impedance_file=None, nfreqs=None):
     """makeImpedance for the wake (src/main.cpp:717-721, src/Z/ImpedanceFactory.cpp:21-84); impedance_file:
-    a table of `line-number real imag` records added on top (:70-75)"""
-    z = np.zeros((d.padded_bins, 2), f32)
+    a table of `line-number real imag` records added on top (:70-75); nfreqs: the table's length if not the
+    padded profile's (the spaced length of a train of bunches, :718)"""
+    nf = int(d.padded_bins if nfreqs is None else nfreqs)
+    z = np.zeros((nf, 2), f32)
     nz = ci(0)
-    load().ivs_wake_impedance(C.byref(params), C.byref(d), z.reshape(-1), C.byref(nz))
+    if nfreqs is None:
+        load().ivs_wake_impedance(C.byref(params), C.byref(d), z.reshape(-1), C.byref(nz))
+    else:
+        load().ivs_make_impedance(nf, d.fmax, d.R_bend, d.f_rev, params.gap, 1 if params.use_csr else 0,
+                                  params.wall_conductivity, params.wall_susceptibility, params.collimator,
+                                  z.reshape(-1), C.byref(nz))
     if impedance_file:
-        rc = load().ivs_add_impedance_file(str(impedance_file).encode(), z.reshape(-1), d.padded_bins)
+        rc = load().ivs_add_impedance_file(str(impedance_file).encode(), z.reshape(-1), nf)
         if rc:
-            raise IvsError(rc, "impedance file %s: cannot be read or has fewer than %d records" % (impedance_file, d.padded_bins))
+            raise IvsError(rc, "impedance file %s: cannot be read or has fewer than %d records" % (impedance_file, nf))
         return z, True
     return z, bool(nz.value)
 
@@ -222,6 +234,47 @@ def haissinski_grid(params, d, zwake=None, wakescaling=None, iterations=2000, re
     if rc not in (0, 1):
         raise IvsError(rc, "ivs_haissinski_grid")
     return g, res.value
+
+
+def train_layout(params, filling, spacing_bins=None):
+    """The filling pattern of src/main.cpp:248-321: `filling` = one current per bucket (0 = empty).
+    Returns dict(buckets, fractions, Ib, spacing_bins, spaced_bins, wakescaling, params, d): bucket numbers
+    counted from the END of the pattern (:258-268), the bunches' charge fractions, the derived scalars for
+    the whole beam (bunch_current = Ib), the bunch spacing in bins (:304-307), the padded length of the
+    train (:318-321) and ElectricField::_wakescaling for an impedance of that length.  spacing_bins overrides
+    the bunch spacing (1 / f_RF in the reference, :215): the padded length follows as buckets * spacing."""
+    filling = [float(c) for c in filling]
+    buckets = [len(filling) - 1 - i for i, c in enumerate(filling) if c > 0]
+    bunches = [c for c in filling if c > 0]
+    if not bunches:
+        raise ValueError("empty filling pattern")
+    Ib = float(sum(bunches))
+    p2 = RingParams.from_buffer_copy(params)
+    p2.bunch_current = Ib
+    d = derive(p2)
+    n = params.grid_size
+    spacing_ps = (1.0 / d.f_RF) * 2.99792458e8 / d.bl / params.pq_size
+    spaced = int(np.ceil(n * len(filling) * spacing_ps))
+    spacing = int(d.spacing_bins)
+    if spacing_bins is not None:
+        spacing = int(spacing_bins)
+        spaced = max(len(filling) * spacing, max(buckets) * spacing + n)
+    if params.round_padding or spacing_bins is not None:
+        spaced = 1 << max(spaced - 1, 1).bit_length()
+    raw = f32(d.wakescaling) * f32(d.padded_bins)  # exact for the rounded (power-of-two) padding
+    return dict(buckets=buckets, fractions=[c / Ib for c in bunches], Ib=Ib, spacing_bins=spacing,
+                spaced_bins=spaced, wakescaling=float(f32(raw) / f32(spaced)), params=p2, d=d)
+
+
+def train_wake_windows(z, n, buckets, spacing_bins):
+    """wake-function windows [nb][nb][2 n] (double) of a train of bunches (ivs_train_wake_windows)"""
+    z = np.ascontiguousarray(z, f32).reshape(-1, 2)
+    b = np.ascontiguousarray(buckets, np.uint32)
+    w = np.zeros((len(b), len(b), 2 * n), np.float64)
+    rc = load().ivs_train_wake_windows(z.reshape(-1), z.shape[0], n, len(b), b, spacing_bins, w.reshape(-1))
+    if rc != 0:
+        raise IvsError(rc, "ivs_train_wake_windows: " + ("a bunch does not fit the padded profile" if rc == -2 else "bad arguments"))
+    return w
 
 
 def rf_model(params, d):
@@ -428,6 +481,22 @@ class Context:
                 if p is not None:
                     self.free(p)
 
+    def train_wake_potential(self, profiles, windows, wakescaling):
+        """wake potentials [nb][n] of a train of bunches from their profiles [nb][n] and the windows of
+        train_wake_windows"""
+        profiles = np.ascontiguousarray(profiles, f32)
+        windows = np.ascontiguousarray(windows, np.float64)
+        nb, n = profiles.shape
+        assert windows.shape == (nb, nb, 2 * n)
+        d_p, d_w = self.to_device(profiles), self.to_device(windows)
+        d_o = self.malloc(4 * nb * n)
+        try:
+            self.check(self.lib.ivs_train_wake_potential(self.h, d_p, n, nb, d_w, wakescaling, d_o))
+            return self.to_host(d_o, (nb, n))
+        finally:
+            for p in (d_p, d_w, d_o):
+                self.free(p)
+
     def wake_function(self, z, wakescaling, n):
         z = np.ascontiguousarray(z, f32).reshape(-1, 2)
         nmax = z.shape[0]
@@ -596,6 +665,14 @@ class Simulation:
         rf = np.ascontiguousarray(rf, f32)
         assert rf.shape == (self.n,)
         self.ctx.check(self.lib.ivs_sim_set_rf_offset(self.h, rf))
+
+    def set_bunch_train(self, buckets, spacing_bins, z, wakescaling):
+        """the members become the bunches of one train (PhaseSpace::nb = members): z = the wake impedance at
+        the spaced length, wakescaling = the whole beam's (train_layout); needs flags=SIM_UNFUSED"""
+        b = np.ascontiguousarray(buckets, np.uint32)
+        assert b.shape == (self.members,)
+        z = np.ascontiguousarray(z, f32).reshape(-1, 2)
+        self.ctx.check(self.lib.ivs_sim_set_bunch_train(self.h, b, spacing_bins, z.reshape(-1), z.shape[0], wakescaling))
 
     def set_rf_modulation(self, phase_ampl, model=None):
         """make the RF map a DynamicRFKickMap with this queue of (phase, amplitude) pairs; None: static again"""

@@ -210,7 +210,8 @@ ztable z_collimator(size_t n, double outer, double inner) {
 // with the reference's conventions (imaginary part of bin 0 ignored, bins >= nmax/2 zero,
 // src/PS/ElectricField.cpp:229-234), in double.  wakePotential()[x] = scaling sum_x' rho[x'] w[x - x']
 // exactly in real arithmetic, because nmax >= 2n leaves no circular wrap.  Shared with ivs_step.cu.
-std::vector<double> ivs_wake_function_host(const float* z, uint32_t nmax, uint32_t n) {
+// all nmax lags of the (circular) unit wake function: c2r of the Hermitian-extended impedance, in double
+static std::vector<double> wake_function_lags(const float* z, uint32_t nmax) {
     std::vector<std::complex<double>> a(nmax, 0.0);
     a[0] = std::complex<double>(z[0], 0.0);
     for (uint32_t k = 1; k < nmax / 2; k++) {
@@ -235,13 +236,44 @@ std::vector<double> ivs_wake_function_host(const float* z, uint32_t nmax, uint32
             }
         }
     }
+    std::vector<double> r(nmax);
+    for (uint32_t i = 0; i < nmax; i++) r[i] = a[i].real();
+    return r;
+}
+
+std::vector<double> ivs_wake_function_host(const float* z, uint32_t nmax, uint32_t n) {
+    const std::vector<double> a = wake_function_lags(z, nmax);
     std::vector<double> w(2 * n - 1);
     for (int m = -(int)(n - 1); m <= (int)(n - 1); m++)
-        w[m + (int)(n - 1)] = a[(uint32_t)((m + (int)nmax) % (int)nmax)].real();
+        w[m + (int)(n - 1)] = a[(uint32_t)((m + (int)nmax) % (int)nmax)];
     return w;
 }
 
 extern "C" {
+
+// Train of bunches (PhaseSpace::nb > 1): with the profiles at bucket[b] * spacing_bins in ONE padded array
+// (src/PS/ElectricField.cpp:255-263) the circular convolution couples bunch b' to bunch b through the
+// wake function at lags (bucket[b] - bucket[b']) * spacing_bins + (x - x').  windows[(b * nb + b') * 2 n + m
+// + n - 1] = that lag's value for m = x - x' in -(n-1)..(n-1) (entry 2 n - 1 of a window is padding).
+int ivs_train_wake_windows(const float* z, uint32_t nmax, uint32_t n, uint32_t nb, const uint32_t* bucket,
+                           uint32_t spacing_bins, double* windows) {
+    if (!z || !bucket || !windows || n < 2 || nb < 1 || nmax < 2 || (nmax & (nmax - 1))) return -1;
+    for (uint32_t b = 0; b < nb; b++)
+        if ((uint64_t)bucket[b] * spacing_bins + n > nmax) return -2;  // the reference would write past its array
+    const std::vector<double> a = wake_function_lags(z, nmax);
+    for (uint32_t b = 0; b < nb; b++)
+        for (uint32_t c = 0; c < nb; c++) {
+            double* w = windows + ((size_t)b * nb + c) * 2 * n;
+            const int64_t lag0 = ((int64_t)bucket[b] - (int64_t)bucket[c]) * (int64_t)spacing_bins;
+            for (int64_t m = -(int64_t)(n - 1); m <= (int64_t)(n - 1); m++) {
+                int64_t l = (lag0 + m) % (int64_t)nmax;
+                if (l < 0) l += nmax;
+                w[m + (int64_t)(n - 1)] = a[(size_t)l];
+            }
+            w[2 * n - 1] = 0.0;
+        }
+    return 0;
+}
 
 int ivs_airy(double x, double* ai, double* aip, double* bi, double* bip) {
     if (!(x >= 0) || !ai || !aip || !bi || !bip) return -1;

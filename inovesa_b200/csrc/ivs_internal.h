@@ -9,6 +9,9 @@ struct ivs_sim;
 
 // unit wake function of an impedance table in double (ivs_host.cpp): w[m + n - 1], m = -(n-1)..(n-1)
 std::vector<double> ivs_wake_function_host(const float* z, uint32_t nmax, uint32_t n);
+// include/ivs_host.h
+extern "C" int ivs_train_wake_windows(const float* z, uint32_t nmax, uint32_t n, uint32_t nb, const uint32_t* bucket,
+                                      uint32_t spacing_bins, double* windows);
 
 // member-batched launchers (ivs_maps.cu, ivs_reduce.cu, ivs_field.cu, ivs_track.cu)
 ivs_status ivs_kick_y_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n, uint32_t members,
@@ -89,5 +92,7 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
 ivs_status ivs_fused_enqueue_run(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s, uint32_t nsteps);
 // tracking launches that overlap the following step (side stream) are joined into the context's stream
 ivs_status ivs_fused_join(ivs_ctx* ctx, ivs_sim* s);
+ivs_status ivs_train_wake_launch(ivs_ctx* ctx, const float* profiles, uint32_t n, uint32_t nb, const double* windows,
+                                 const float* scaling, float scal, float* wake);
 // new RF kick offsets: rebuild the fused kernels' tap tables in place (same device buffers)
 ivs_status ivs_fused_plan_set_rf(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s, const float* rf_offset);

@@ -52,6 +52,8 @@ struct ivs_sim {
     uint32_t rf_seq_len = 0;
     unsigned int* rf_pos = nullptr;
     uint64_t rf_step0 = 0;
+    // train of bunches (ivs_sim_set_bunch_train): the members are coupled through these wake-function windows
+    double* train_windows = nullptr;  // [members][members][2 n]
     float f_scale = 0, cutoff = 0;
     uint64_t steps_done = 0;
     ivs_fused_plan plan{};

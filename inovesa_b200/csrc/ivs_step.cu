@@ -42,8 +42,12 @@ ivs_status enqueue_unfused_step(ivs_sim* s) {
     const size_t bytes = (size_t)m * n * n * sizeof(float);
     if (s->has_wake) {
         // wkm->update(): ElectricField::wakePotential -> offsets (src/SM/WakePotentialMap.cpp:34-50)
-        IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->impedance, s->nmax, s->wakescaling, 0, s->wake,
-                                 nullptr, nullptr, nullptr, 0, 0, 0, 0));
+        if (s->train_windows) {
+            IVS_TRY(ivs_train_wake_launch(ctx, prof, n, m, s->train_windows, s->wakescaling, 0.0f, s->wake));
+        } else {
+            IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->impedance, s->nmax, s->wakescaling, 0, s->wake,
+                                     nullptr, nullptr, nullptr, 0, 0, 0, 0));
+        }
         IVS_TRY(ivs_kick_y_batched(ctx, t1, t2, n, m, s->wake, n, s->it));
     } else {
         IVS_CUDA(ctx, cudaMemcpyAsync(t2, t1, bytes, cudaMemcpyDeviceToDevice, ctx->stream));  // Identity
@@ -273,6 +277,7 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
     if (s->ev_step) cudaEventDestroy(s->ev_step);
     for (int b = 0; b < 2; b++) if (s->ev_track[b]) cudaEventDestroy(s->ev_track[b]);
     if (s->wakebuf[1] && s->wakebuf[1] != s->wake) cudaFree(s->wakebuf[1]);
+    if (s->train_windows) cudaFree(s->train_windows);
     float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
                      s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
                      (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power,
@@ -515,8 +520,12 @@ ivs_status ivs_sim_fields(ivs_sim* s, float* csr_spectrum, float* wake) {
     if (wake) {
         if (s->has_wake) {
             if (!s->wake_now) IVS_TRY(dalloc(ctx, &s->wake_now, (size_t)m * n));
-            IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->impedance, s->nmax, s->wakescaling, 0, s->wake_now,
-                                     nullptr, nullptr, nullptr, 0, 0, 0, 0));
+            if (s->train_windows) {
+                IVS_TRY(ivs_train_wake_launch(ctx, prof, n, m, s->train_windows, s->wakescaling, 0.0f, s->wake_now));
+            } else {
+                IVS_TRY(ivs_field_launch(ctx, prof, n, m, s->impedance, s->nmax, s->wakescaling, 0, s->wake_now,
+                                         nullptr, nullptr, nullptr, 0, 0, 0, 0));
+            }
             IVS_TRY(ivs_download(ctx, wake, s->wake_now, (size_t)m * n * sizeof(float)));
         } else {
             for (size_t i = 0; i < (size_t)m * n; i++) wake[i] = 0.0f;
@@ -586,6 +595,39 @@ ivs_status ivs_sim_set_rf_modulation(ivs_sim* s, const ivs_rf_model* model, cons
                 s->cur = s->pcur = cur;
                 if (st != IVS_OK) return st;
             }
+        }
+    }
+    return IVS_OK;
+}
+
+ivs_status ivs_sim_set_bunch_train(ivs_sim* s, const uint32_t* bucket, uint32_t spacing_bins, const float* z,
+                                   uint32_t nmax, float wakescaling) {
+    if (!s) return IVS_ERR_INVALID_ARGUMENT;
+    ivs_ctx* ctx = s->ctx;
+    IVS_REQUIRE(ctx, bucket && z, "ivs_sim_set_bunch_train: null pointer");
+    if (!(s->desc.flags & IVS_SIM_UNFUSED) || !s->has_wake)
+        return ivs_fail(ctx, IVS_ERR_UNSUPPORTED,
+                        "ivs_sim_set_bunch_train: a train of bunches steps through the kernel sequence "
+                        "(create the simulation with IVS_SIM_UNFUSED and a wake impedance)");
+    IVS_REQUIRE(ctx, nmax >= 2 && !(nmax & (nmax - 1)), "ivs_sim_set_bunch_train: nmax must be a power of two");
+    const uint32_t n = s->n, m = s->members;
+    std::vector<double> w((size_t)m * m * 2 * n);
+    const int rc = ivs_train_wake_windows(z, nmax, n, m, bucket, spacing_bins, w.data());
+    IVS_REQUIRE(ctx, rc == 0, "ivs_sim_set_bunch_train: a bunch does not fit the padded profile "
+                              "(bucket * spacing_bins + n > nmax)");
+    IVS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IVS_TRY(settle(s));
+    const bool was = s->train_windows != nullptr;
+    if (!s->train_windows) IVS_TRY(dalloc(ctx, &s->train_windows, w.size()));
+    IVS_TRY(ivs_upload(ctx, s->train_windows, w.data(), w.size() * sizeof(double)));
+    std::vector<float> sc(m, wakescaling);  // one ElectricField::_wakescaling for the whole beam
+    IVS_TRY(ivs_upload(ctx, s->wakescaling, sc.data(), m * sizeof(float)));
+    IVS_TRY(ivs_sync(ctx));
+    if (!was) {  // the step graphs call another wake kernel
+        drop_graphs(s);
+        if (!(s->desc.flags & IVS_SIM_NO_GRAPH)) {
+            IVS_TRY(capture(s, ivs_sim::kGraphSteps, &s->graphK[s->cur]));
+            IVS_TRY(capture(s, 1, &s->graph1[s->cur]));
         }
     }
     return IVS_OK;

@@ -227,14 +227,15 @@ class ProgramOptions:
         return filling, [c for c in filling if c > 0]
 
     def ring_params(self):
+        """the ring parameters; bunch_current = the whole beam's current Ib (src/main.cpp:274), i.e. the one
+        bunch's, or the sum over a filling pattern (a train of bunches: run.py, capi.train_layout)"""
         _, bunches = self.bunch_currents()
-        if len(bunches) != 1:
-            raise OptionError("BunchCurrent names %d bunches: multi-bunch runs (PhaseSpace::nb > 1, "
-                              "src/PS/ElectricField.cpp:236-263) are not supported" % len(bunches))
+        if not bunches:
+            raise OptionError("BunchCurrent names no bunch")
         kw = {field: self.values[name] for name, (_, _, _, field) in OPTIONS.items() if field}
         for k in ("use_csr", "linear_rf", "round_padding"):
             kw[k] = 1 if kw[k] else 0
-        kw["bunch_current"] = bunches[0]
+        kw["bunch_current"] = float(sum(bunches))
         return default_params(**kw)
 
     def unsupported(self):
@@ -243,6 +244,13 @@ class ProgramOptions:
         f = self.values["InitialDistFile"]
         if f and not f.endswith((".h5", ".hdf5")):
             bad.append("InitialDistFile (start distribution from a PNG or text file; result files (.h5) are read)")
+        if len(self.bunch_currents()[1]) > 1:  # a train of bunches (PhaseSpace::nb > 1)
+            if f:
+                bad.append("InitialDistFile with a multi-bunch filling pattern")
+            if self.values["tracking"] not in ("", "/dev/null"):
+                bad.append("tracking (passive particles) with a multi-bunch filling pattern")
+            if self.values["RenormalizeCharge"] > 0:
+                bad.append("RenormalizeCharge > 0 (periodic renormalisation) with a multi-bunch filling pattern")
         return bad
 
     def save_text(self):

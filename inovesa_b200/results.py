@@ -44,35 +44,40 @@ GROUPS = ["/BunchLength", "/BunchPopulation", "/BunchPosition", "/BunchProfile",
 
 class ResultFile:
     def __init__(self, n, nmax, n_particles=0, *, axis_q, axis_p, axis_f, bl, dE, f_scale, Ib, Qb,
-                 t_sync, f_rev, volts=1.0, watt_per_hertz=1.0, watts=1.0, impedance=None, bucket=0):
+                 t_sync, f_rev, volts=1.0, watt_per_hertz=1.0, watts=1.0, impedance=None, bucket=0, nb=1,
+                 impedance_bins=None):
         """sizes and unit factors as the reference's constructor derives them (:151-318):
         axis_q/axis_p = PhaseSpace axes (n floats), axis_f = ElectricField frequency axis,
-        bl/dE = "Meter"/"ElectronVolt" axis scales, t_sync = synchrotron period in s."""
-        self.n, self.nmax, self.np = int(n), int(nmax), int(n_particles)
+        bl/dE = "Meter"/"ElectronVolt" axis scales, t_sync = synchrotron period in s.  nb = PhaseSpace::nb
+        (rows are [time][bunch][...]), bucket = the bunches' bucket numbers (src/main.cpp:258-268);
+        impedance_bins = entries of the impedance table kept (nFreqs / 2; the spaced length for a train)."""
+        self.n, self.nmax, self.np, self.nb = int(n), int(nmax), int(n_particles), int(nb)
+        buckets = np.atleast_1d(np.asarray(bucket, np.uint32))
+        assert buckets.shape == (self.nb,)
         c = 2.99792458e8
         self.fixed = {
             "/Info/AxisValues_z": np.asarray(axis_q, f32),
             "/Info/AxisValues_E": np.asarray(axis_q, f32),  # quirk: written from axis 0 (:168)
             "/Info/AxisValues_f": np.asarray(axis_f, f32)[: self.nmax // 2],
-            "/Info/BucketNumbers": np.asarray([bucket], np.uint32),
+            "/Info/BucketNumbers": buckets,
             "/Info/Inovesa_v": np.asarray([1, 2, -1], np.int32),
         }
         if impedance is not None:
-            z = np.asarray(impedance, f32).reshape(-1, 2)[: self.nmax // 2]
+            z = np.asarray(impedance, f32).reshape(-1, 2)[: (impedance_bins or self.nmax // 2)]
             self.fixed["/Impedance/data/real"] = z[:, 0].copy()
             self.fixed["/Impedance/data/imag"] = z[:, 1].copy()
-        n, h = self.n, self.nmax // 2
+        n, h, nb = self.n, self.nmax // 2, self.nb
         self.rows = {p: [] for p in (
             "/Info/AxisValues_t", "/PhaseSpace/axis0", "/BunchPopulation/data", "/BunchProfile/data",
             "/BunchLength/data", "/BunchPosition/data", "/EnergyProfile/data", "/EnergySpread/data",
             "/EnergyAverage/data", "/Particles/data", "/RFKicks/data", "/WakePotential/data",
             "/CSR/Spectrum/data", "/CSR/Intensity/data", "/PhaseSpace/data")}
         self.row_shape = {
-            "/Info/AxisValues_t": (), "/PhaseSpace/axis0": (), "/BunchPopulation/data": (1,),
-            "/BunchProfile/data": (1, n), "/BunchLength/data": (1,), "/BunchPosition/data": (1,),
-            "/EnergyProfile/data": (1, n), "/EnergySpread/data": (1,), "/EnergyAverage/data": (1,),
-            "/Particles/data": (self.np, 2), "/RFKicks/data": (2,), "/WakePotential/data": (1, n),
-            "/CSR/Spectrum/data": (1, h), "/CSR/Intensity/data": (1,), "/PhaseSpace/data": (1, n, n)}
+            "/Info/AxisValues_t": (), "/PhaseSpace/axis0": (), "/BunchPopulation/data": (nb,),
+            "/BunchProfile/data": (nb, n), "/BunchLength/data": (nb,), "/BunchPosition/data": (nb,),
+            "/EnergyProfile/data": (nb, n), "/EnergySpread/data": (nb,), "/EnergyAverage/data": (nb,),
+            "/Particles/data": (self.np, 2), "/RFKicks/data": (2,), "/WakePotential/data": (nb, n),
+            "/CSR/Spectrum/data": (nb, h), "/CSR/Intensity/data": (nb,), "/PhaseSpace/data": (nb, n, n)}
         self.attrs = {  # unit factors: value in the file * factor = physical unit (:151-318)
             "/Info/AxisValues_z": {"Meter": bl, "Second": bl / c},
             "/Info/AxisValues_E": {"ElectronVolt": dE},
@@ -116,7 +121,7 @@ class ResultFile:
 
     def append_csr(self, spectrum, power):
         """HDF5File::append(ef): the first nmax/2 bins of the spectrum, and the power"""
-        self._put("/CSR/Spectrum/data", np.asarray(spectrum, f32).reshape(-1)[: self.nmax // 2])
+        self._put("/CSR/Spectrum/data", np.asarray(spectrum, f32).reshape(self.nb, -1)[:, : self.nmax // 2])
         self._put("/CSR/Intensity/data", power)
 
     def append_wake(self, wake):
@@ -207,9 +212,10 @@ def unit_factors(derived):
 
 
 def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0, wake_impedance=None,
-                   renormalize=0, progress=None):
-    """main()'s loop with its out-step cadence (src/main.cpp:948-1053) on a `capi.Simulation`
-    with one member: returns the filled ResultFile.  Time axis in synchrotron periods.
+                   renormalize=0, progress=None, buckets=None):
+    """main()'s loop with its out-step cadence (src/main.cpp:948-1053) on a `capi.Simulation` whose members
+    are the bunches of the run (one, or a train set up with set_bunch_train; `buckets` = their bucket
+    numbers): returns the filled ResultFile.  Time axis in synchrotron periods.
     renormalize > 0: the charge is renormalised before every renormalize-th step (:953-955);
     progress(done, steps): called at every out-step."""
     d, n = derived, params.grid_size
@@ -220,27 +226,28 @@ def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0,
     rf = ResultFile(n, nmax, sim.np, axis_q=axis_q, axis_p=axis_p, axis_f=axis_f, bl=d.bl, dE=d.dE,
                     f_scale=2.99792458e8 / d.bl, Ib=d.Ib, Qb=d.Qb, t_sync=1.0 / d.fs, f_rev=d.f_rev,
                     volts=unit_factors(d)[0], watt_per_hertz=unit_factors(d)[1], watts=unit_factors(d)[2],
-                    impedance=wake_impedance)
+                    impedance=wake_impedance, nb=sim.members, bucket=[0] if buckets is None else buckets,
+                    impedance_bins=None if wake_impedance is None else np.asarray(wake_impedance).reshape(-1, 2).shape[0] // 2)
     for name, _ in params._fields_:
         if not name.startswith("reserved"):
             rf.add_parameter(name, getattr(params, name))
     sim.set_radiation()
     done, k = 0, 0
     while True:
-        obs = sim.observe()[0]  # [integral, mean_q, var_q, sigma_q, mean_p, var_p, sigma_p, P_csr]
+        obs = sim.observe()  # per bunch: [integral, mean_q, var_q, sigma_q, mean_p, var_p, sigma_p, P_csr]
         grid, prof, _, parts = sim.download()
         # the CSR spectrum and the wake potential of THIS profile: main() refreshes the wake before
         # the out-step block (src/main.cpp:949-952) and appends updateCSR's spectrum (:1000-1001)
         spectrum, wake = sim.fields()
         t = done / float(d.steps)
-        projy = (grid[0].astype(np.float64) * _simpson(n, d.dq)[:, None]).sum(0).astype(f32)
-        rf.append_time_step(t, prof[0], obs[3], obs[1], projy, obs[6], obs[4], obs[0])
-        rf.append_csr(spectrum[0], obs[7])
-        rf.append_wake(wake[0])
+        projy = (grid.astype(np.float64) * _simpson(n, d.dq)[None, :, None]).sum(1).astype(f32)
+        rf.append_time_step(t, prof, obs[:, 3], obs[:, 1], projy, obs[:, 6], obs[:, 4], obs[:, 0])
+        rf.append_csr(spectrum, obs[:, 7])
+        rf.append_wake(wake)
         if parts is not None:
             rf.append_tracks(parts[0])
         if save_phase_space and k % save_phase_space == 0:
-            rf.append_phase_space(t, grid[0])
+            rf.append_phase_space(t, grid)
         if progress is not None:
             progress(done, steps)
         if done >= steps:
@@ -260,7 +267,7 @@ def run_and_record(sim, params, derived, steps, outstep=100, save_phase_space=0,
             done += nxt
         k += 1
     if not save_phase_space or (k % save_phase_space) != 0:
-        rf.append_phase_space(done / float(d.steps), sim.download()[0][0])  # always at the end (:1084-1086)
+        rf.append_phase_space(done / float(d.steps), sim.download()[0])  # always at the end (:1084-1086)
     return rf
 
 

@@ -54,7 +54,7 @@ def read_start_distribution(path, step):
     row = ps[(ps.shape[0] + step) % ps.shape[0]]
     if row.ndim == 3:
         if row.shape[0] != 1:
-            raise OptionError("%s: %d bunches (multi-bunch runs are not supported)" % (path, row.shape[0]))
+            raise OptionError("%s: %d bunches (a start distribution holds one bunch)" % (path, row.shape[0]))
         row = row[0]
     if row.shape[0] != row.shape[1]:
         raise OptionError("%s: phase space is not square" % path)
@@ -125,14 +125,35 @@ def main(argv=None, out=sys.stdout):
     zfile = opts["Impedance"] or None
     if zfile:
         say('Reading impedance from: "%s"' % zfile)
-    sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts, impedance_file=zfile)
-    if opts["RenormalizeCharge"] >= 0:
-        sim.renormalize()  # the initial renormalisation (src/main.cpp:528-532)
+    filling, bunches = opts.bunch_currents()
+    lay = None
+    if len(bunches) > 1:
+        # a train of bunches (PhaseSpace::nb > 1, src/main.cpp:248-321): the members of the simulation are the
+        # bunches, coupled through the wake potential of the whole padded train (capi.set_bunch_train); the
+        # grids carry the charge fractions (PhaseSpace::normalize with `filling`, src/main.cpp:528-532)
+        lay = capi.train_layout(params, filling)
+        say("Filling pattern: %d bunches in %d buckets, %d bins apart, padded profile of the train %d bins" % (
+            len(bunches), len(filling), lay["spacing_bins"], lay["spaced_bins"]))
+        w = np.full(n, d.dq / 3.0)
+        w[1:-1:2] *= 4.0
+        w[2:-1:2] *= 2.0
+        charge = float((grid.astype(np.float64) * w[:, None] * w[None, :]).sum())  # Simpson, both axes
+        grid = np.stack([grid * f32(fr / charge) for fr in lay["fractions"]]).astype(f32)
+        sim = capi.Simulation(ctx, params, len(bunches), grid=grid, flags=capi.SIM_UNFUSED, impedance_file=zfile)
+    else:
+        sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts, impedance_file=zfile)
+        if opts["RenormalizeCharge"] >= 0:
+            sim.renormalize()  # the initial renormalisation (src/main.cpp:528-532)
     seq = rf_noise(opts, params, d, laststep, seed=1)
     if seq is not None:
         say("Building dynamic, %s RFKickMap..." % ("linear" if params.linear_rf else "nonlinear"))
         sim.set_rf_modulation(seq)
-    zw, nz = capi.wake_impedance(params, d, zfile)
+    if lay is None:
+        zw, nz = capi.wake_impedance(params, d, zfile)
+    else:
+        zw, nz = capi.wake_impedance(params, d, zfile, nfreqs=lay["spaced_bins"])  # src/main.cpp:718
+        if nz:
+            sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], zw, lay["wakescaling"])
     say("Starting the simulation.")
     t0 = time.time()
 
@@ -141,7 +162,8 @@ def main(argv=None, out=sys.stdout):
             say("%8.3f T_s  (%d / %d steps, %.1f s)" % (done / d.steps, done, steps, time.time() - t0))
 
     rf = run_and_record(sim, params, d, laststep, outstep=opts["outstep"], save_phase_space=opts["SavePhaseSpace"],
-                        wake_impedance=zw if nz else None, renormalize=opts["RenormalizeCharge"], progress=progress)
+                        wake_impedance=zw if nz else None, renormalize=opts["RenormalizeCharge"], progress=progress,
+                        buckets=None if lay is None else lay["buckets"])
     dt = time.time() - t0
     if sim.fallback_steps:
         say("%d steps were redone through the kernel sequence (displacement beyond the fused kernel's pad)." % sim.fallback_steps)

@@ -71,6 +71,8 @@ class Oracle:
         L.orc_initial_grid.argtypes = [u32, cf, cf, cf, cf, cd, _fp]
         L.orc_wake_potential.argtypes = [u32, _fp, _fp, u32, cf, _fp, P, P]
         L.orc_csr_power.argtypes = [u32, _fp, _fp, u32, cf, cf, cf, P, _fp]
+        L.orc_train_wake_potential.restype = ci
+        L.orc_train_wake_potential.argtypes = [u32, u32, _fp, _up, u32, _fp, u32, cf, _fp, P]
         L.orc_z_free_space.argtypes = [C.c_size_t, cf, cf, _fp]
         L.orc_z_parallel_plates.argtypes = [C.c_size_t, cf, cf, cd, _fp]
         L.orc_z_resistive_wall.argtypes = [C.c_size_t, cf, cf, cd, cd, cd, cd, _fp]
@@ -190,6 +192,20 @@ class Oracle:
                                     wake, _opt(ff), _opt(pw))
         return (wake, ff, pw) if full else wake
 
+    def train_wake_potential(self, profiles, buckets, spacing_bins, z, wakescaling, full=False):
+        """wake potentials [nb][n] of a train of bunches (profiles [nb][n], bucket numbers, spacing in bins)"""
+        profiles = np.ascontiguousarray(profiles, f32)
+        nb, n = profiles.shape
+        nmax = z.reshape(-1, 2).shape[0]
+        wake = np.zeros((nb, n), f32)
+        pw = np.zeros(nmax, f32)
+        rc = self.lib.orc_train_wake_potential(n, nb, profiles.reshape(-1), np.ascontiguousarray(buckets, np.uint32),
+                                               spacing_bins, np.ascontiguousarray(z, f32).reshape(-1), nmax,
+                                               wakescaling, wake.reshape(-1), _opt(pw))
+        if rc != 0:
+            raise ValueError("a bunch of the train does not fit the padded profile")
+        return (wake, pw) if full else wake
+
     def csr_power(self, profile, z, dq, f_scale, cutoff):
         n, nmax = len(profile), z.reshape(-1, 2).shape[0]
         spec = np.zeros(nmax, f32)
@@ -247,6 +263,7 @@ class Ref:
         L.ref_normalize.argtypes = [u32, cf, cf, cf, cf, _fp, _fp]
         L.ref_wake_potential.argtypes = [u32, cf, cf, cf, cf, _fp, _fp, u32, cd, _fp, P, P, P]
         L.ref_csr_power.argtypes = [u32, cf, cf, cf, cf, cd, _fp, _fp, u32, cf, P, _fp]
+        L.ref_train_wake_potential.argtypes = [u32, u32, cf, cf, cf, cf, _fp, _up, u32, _fp, u32, cd, _fp, P, P]
         L.ref_make_impedance.argtypes = [C.c_size_t, cf, cd, cd, cd, ci, cd, cd, cd, _fp,
                                          C.POINTER(ci)]
         L.ref_airy.argtypes = [cd] + [C.POINTER(cd)] * 4
@@ -346,6 +363,20 @@ class Ref:
             np.ascontiguousarray(z, f32).reshape(-1), nmax, raw_scaling, wake, _opt(ff), _opt(pw),
             _opt(used)))
         return wake, ff, pw, float(used[0])
+
+    def train_wake_potential(self, grids, qmin, qmax, pmin, pmax, buckets, spacing_bins, z, raw_scaling):
+        """ElectricField::wakePotential with PhaseSpace::nb = len(grids): wake [nb][n], padded wake [nmax],
+        scaling actually used"""
+        grids = np.ascontiguousarray(grids, f32)
+        nb, n = grids.shape[0], grids.shape[1]
+        nmax = z.reshape(-1, 2).shape[0]
+        wake = np.zeros((nb, n), f32)
+        pw = np.zeros(nmax, f32)
+        used = np.zeros(1, f32)
+        self._check(self.lib.ref_train_wake_potential(
+            n, nb, qmin, qmax, pmin, pmax, grids.reshape(-1), np.ascontiguousarray(buckets, np.uint32), spacing_bins,
+            np.ascontiguousarray(z, f32).reshape(-1), nmax, raw_scaling, wake.reshape(-1), _opt(pw), _opt(used)))
+        return wake, pw, float(used[0])
 
     def csr_power(self, grid, qmin, qmax, pmin, pmax, bl, z, cutoff):
         n, nmax = grid.shape[0], z.reshape(-1, 2).shape[0]

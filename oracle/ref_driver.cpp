@@ -306,6 +306,32 @@ int ref_wake_potential(uint32_t n, float qmin, float qmax, float pmin, float pma
     });
 }
 
+// wakePotential() of a train of nb bunches (PhaseSpace::nb > 1): grids [nb][n][n] holding the bunches'
+// charge fractions, bucket numbers and the spacing in bins as src/main.cpp:248-321 hands them to the field
+int ref_train_wake_potential(uint32_t n, uint32_t nb, float qmin, float qmax, float pmin, float pmax,
+                             const float* grids, const uint32_t* bucket, uint32_t spacing_bins,
+                             const float* z, uint32_t nmax, double wakescaling_raw, float* wake,
+                             float* padded_wake, float* wakescaling_used) {
+    return guarded([&] {
+        PhaseSpace::resetSize(n, nb);
+        std::vector<integral_t> filling(nb, integral_t(1) / nb);
+        auto g = std::make_shared<PhaseSpace>(qmin, qmax, 1.0, pmin, pmax, 1.0, nullptr, 1, 1, filling, 1, grids);
+        g->updateXProjection();
+        std::vector<impedance_t> zv(nmax);
+        for (uint32_t i = 0; i < nmax; i++) zv[i] = impedance_t(z[2 * i], z[2 * i + 1]);
+        auto imp = std::make_shared<Impedance>(zv, 1.0f, nullptr);
+        std::vector<uint32_t> buckets(bucket, bucket + nb);
+        const double dp = g->getDelta(1);
+        ElectricField f(g, imp, buckets, spacing_bins, nullptr, 1.0, 1.0f, wakescaling_raw * dp,
+                        physcons::c, 1.0, 1.0);
+        const meshaxis_t* w = f.wakePotential();
+        std::copy_n(w, (size_t)nb * n, wake);
+        if (padded_wake) std::copy_n(f.getPaddedWakePotential(), nmax, padded_wake);
+        if (wakescaling_used) *wakescaling_used = f._wakescaling;
+        PhaseSpace::resetSize(n, 1);
+    });
+}
+
 // updateCSR(): spectrum (nmax) and intensity; bl sets the "Meter" scale of axis 0
 int ref_csr_power(uint32_t n, float qmin, float qmax, float pmin, float pmax, double bl,
                   const float* grid, const float* z, uint32_t nmax, float cutoff, float* spectrum,

@@ -732,6 +732,37 @@ void orc_wake_potential(uint32_t n, const float* profile, const float* z, uint32
     free(bp); free(ff); free(wl); free(wp);
 }
 
+/* The same for a TRAIN of nb bunches (src/PS/ElectricField.cpp:186-263 as written, PhaseSpace::nb > 1):
+ * padBunchProfiles() copies the profile of bunch b to _bp_padded + bucket[b] * spacing_bins (:255-263), ONE
+ * transform pair of nmax = impedance->nFreqs() bins couples all bunches (circularly), and bunch b reads its
+ * wake potential back at the same offset (:236-241).  profiles / wake are [nb][n].  Returns 0, or -1 if a
+ * bunch does not fit the padded array (the reference would write past it). */
+int orc_train_wake_potential(uint32_t n, uint32_t nb, const float* profiles, const uint32_t* bucket,
+                             uint32_t spacing_bins, const float* z, uint32_t nmax, float wakescaling,
+                             float* wake, float* padded_wake) {
+    for (uint32_t b = 0; b < nb; b++)
+        if ((uint64_t)bucket[b] * spacing_bins + n > nmax) return -1;
+    float* bp = (float*)calloc(nmax, sizeof(float));
+    float* ff = (float*)calloc(2 * (size_t)nmax, sizeof(float));
+    float* wl = (float*)calloc(2 * (size_t)nmax, sizeof(float));
+    float* wp = (float*)calloc(nmax, sizeof(float));
+    for (uint32_t b = 0; b < nb; b++) /* padBunchProfiles :255-263 (later bunches overwrite overlaps) */
+        memcpy(bp + (size_t)bucket[b] * spacing_bins, profiles + (size_t)b * n, sizeof(float) * n);
+    fft_r2c(bp, nmax, ff);
+    for (uint32_t i = 0; i < nmax / 2; i++) {
+        const float a = z[2 * i], bb = z[2 * i + 1], c = ff[2 * i], d = ff[2 * i + 1];
+        wl[2 * i] = MADD(-bb, d, a * c);
+        wl[2 * i + 1] = MADD(bb, c, a * d);
+    }
+    fft_c2r(wl, nmax, wp);
+    for (uint32_t b = 0; b < nb; b++)
+        for (uint32_t x = 0; x < n; x++)
+            wake[(size_t)b * n + x] = wakescaling * wp[(size_t)bucket[b] * spacing_bins + x];
+    if (padded_wake) memcpy(padded_wake, wp, sizeof(float) * nmax);
+    free(bp); free(ff); free(wl); free(wp);
+    return 0;
+}
+
 /* src/PS/ElectricField.cpp:133-184 with the frequency ruler of the constructor (:28-31) */
 void orc_csr_power(uint32_t n, const float* profile, const float* z, uint32_t nmax, float dq,
                    float f_scale, float cutoff, float* spectrum, float* power) {

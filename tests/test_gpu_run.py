@@ -82,7 +82,7 @@ def test_driver_resumes_from_a_result_file(tmp_path, capi, ctx_fma):
 
 def test_driver_refuses_what_it_cannot_do(tmp_path):
     log = io.StringIO()
-    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3"], out=log) == 1
+    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3", "--tracking", "particles.txt"], out=log) == 1
     assert "multi-bunch" in log.getvalue()
     log = io.StringIO()
     assert run.main(["-c", "/dev/null", "-i", "start.png"], out=log) == 1
@@ -90,3 +90,30 @@ def test_driver_refuses_what_it_cannot_do(tmp_path):
     log = io.StringIO()
     assert run.main(["-c", str(tmp_path / "missing.cfg")], out=log) == 1
     assert "does not exist" in log.getvalue()
+
+
+def test_driver_runs_a_train_of_bunches(tmp_path, capi, ctx_fma):
+    """BunchCurrent with several entries is a filling pattern (src/main.cpp:248-279): the bunches are
+    coupled through the wake potential of the padded train and the result file's rows are [time][bunch][x]"""
+    cfg = tmp_path / "kara.cfg"
+    cfg.write_text(CFG.replace("GridSize = 256", "GridSize = 128").replace("BunchCurrent = 5e-5", ""))
+    out = tmp_path / "train.h5"
+    log = io.StringIO()
+    rc = run.main(["-c", str(cfg), "-o", str(out), "-I", "5e-5", "0", "1e-4"], out=log)
+    text = log.getvalue()
+    assert rc == 0, text
+    assert "2 bunches in 3 buckets" in text and "Finished 250 steps" in text
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from h5reader import read_hdf5
+    data, attrs, links = read_hdf5(str(out))
+    assert data["/BunchProfile/data"].shape == (6, 2, 128) and data["/WakePotential/data"].shape == (6, 2, 128)
+    assert data["/PhaseSpace/data"].shape == (1, 2, 128, 128)
+    assert list(data["/Info/BucketNumbers"]) == [2, 0]
+    pop = data["/BunchPopulation/data"]
+    assert np.allclose(pop[0], [1 / 3, 2 / 3], rtol=1e-5) and np.allclose(pop[-1], [1 / 3, 2 / 3], rtol=1e-3)
+    assert abs(attrs["/BunchProfile/data"]["AmperePerNBL"] - 1.5e-4) < 1e-9
+    # the same run by hand
+    p = kara_params(grid_size=128, steps_per_Ts=1000, gap=-1.0)
+    lay = capi.train_layout(p, [5e-5, 0, 1e-4])
+    assert lay["spaced_bins"] == data["/Impedance/data/real"].shape[0] * 2
+    assert np.abs(data["/WakePotential/data"][-1, 1]).max() > 0

@@ -78,8 +78,11 @@ def test_command_line_wins_over_config_file_and_missing_files():
 def test_refusals():
     o = ProgramOptions().parse(["-I", "1e-3", "0", "2e-3"], read_file=lambda _: None)
     assert o.bunch_currents() == ([1e-3, 0.0, 2e-3], [1e-3, 2e-3])
+    assert abs(o.ring_params().bunch_current - 3e-3) < 1e-9 and o.unsupported() == []  # a train: Ib = the sum
+    o2 = ProgramOptions().parse(["-I", "1e-3", "2e-3", "--tracking", "t.txt", "--RenormalizeCharge", "5"], read_file=lambda _: None)
+    assert len(o2.unsupported()) == 2  # no passive particles, no periodic renormalisation with a train
     with pytest.raises(OptionError):
-        o.ring_params()  # two bunches
+        ProgramOptions().parse(["-I", "0", "0"], read_file=lambda _: None).ring_params()
     o = ProgramOptions().parse(["-Z", "impedance.dat", "-i", "start.png"], read_file=lambda _: None)
     assert len(o.unsupported()) == 1 and o["Impedance"] == "impedance.dat"  # impedance files are read
     assert all(len(v) == 4 for v in OPTIONS.values())

@@ -91,6 +91,26 @@ def test_field_and_impedances_bit_exact(oracle, ref):
     assert np.array_equal(sp, so) and power == po
 
 
+def test_train_wake_potential_bit_exact(oracle, ref, rng):
+    """PhaseSpace::nb > 1: the bunches' profiles share one padded array at bucket * spacing_bins and one
+    transform pair (src/PS/ElectricField.cpp:186-263); three bunches of different charge and shape"""
+    n, nmax = 32, 256
+    g0 = ref.initial_grid(n, -12, 12, -12, 12)
+    grids = np.stack([g0 * f32(0.5), np.roll(g0, 3, axis=0) * f32(0.3), np.roll(g0, -2, axis=0) * f32(0.2)])
+    px = np.stack([ref.reduce(g, -12, 12, -12, 12)[0] for g in grids])
+    z, _ = ref.make_impedance(nmax, 1e12, 47.7, 1e6, -1)
+    for buckets, spacing in (([4, 2, 0], 40), ([2, 1, 0], 32), ([0, 1, 5], 44)):
+        wake, pw, used = ref.train_wake_potential(grids, -12, 12, -12, 12, buckets, spacing, z, 1e-3)
+        ow, opw = oracle.train_wake_potential(px, buckets, spacing, z, used, full=True)
+        assert np.array_equal(opw, pw) and np.array_equal(ow, wake)
+        assert np.abs(wake).max() > 0
+    # one bunch in bucket 0 is the single-bunch field
+    w1 = oracle.train_wake_potential(px[:1], [0], 40, z, f32(1e-3))
+    assert np.array_equal(w1[0], oracle.wake_potential(px[0], z, f32(1e-3)))
+    with pytest.raises(ValueError):
+        oracle.train_wake_potential(px, [6, 2, 0], 40, z, f32(1e-3))
+
+
 def test_airy_against_scipy(oracle, ref):
     from scipy.special import airy
     for x in list(np.logspace(-3, 2, 40)) + [103.0]:
