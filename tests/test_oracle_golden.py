@@ -144,3 +144,15 @@ def test_free_space_wake_is_causal(request):
         assert change[:c].max() < E["causality_limit"]       # but not ahead of it
 
 
+
+
+def test_train_wake_potential_golden(oracle):
+    """ElectricField::wakePotential with PhaseSpace::nb = 3 (src/PS/ElectricField.cpp:186-263): outputs of the
+    reference's own sources (tests/golden/make_train_wake.py), bit for bit"""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_wake.npz"))
+    for k in range(3):
+        wake, padded = oracle.train_wake_potential(g["profiles"], g["case%d_buckets" % k], int(g["case%d_spacing" % k]),
+                                                   g["z"], np.float32(g["case%d_scaling" % k]), full=True)
+        assert np.array_equal(wake, g["case%d_wake" % k]) and np.array_equal(padded, g["case%d_padded" % k])
