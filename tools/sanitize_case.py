@@ -29,3 +29,15 @@ with capi.Context(0, capi.ARITH_FMA) as ctx:
     sim.observe()
     sim.close()
     print("tracking + observe ok")
+    # a train of bunches (multi-bunch filling pattern) on the kernel sequence
+    p = kara_params(grid_size=128, wall_conductivity=5.8e7, collimator=0.008, gap=0.032)
+    lay = capi.train_layout(p, [1e-4, 0, 2e-4], 160)
+    z, _ = capi.wake_impedance(lay["params"], lay["d"], nfreqs=lay["spaced_bins"])
+    g0 = capi.initial_grid(lay["d"], 128)
+    grids = np.stack([g0 * np.float32(fr) for fr in lay["fractions"]])
+    sim = capi.Simulation(ctx, lay["params"], 2, grid=grids, flags=capi.SIM_UNFUSED)
+    sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], z, lay["wakescaling"])
+    sim.step(20)
+    sim.fields(spectrum=False)
+    sim.close()
+    print("train ok")
