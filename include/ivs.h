@@ -320,9 +320,11 @@ ivs_status ivs_sim_set_rf_modulation(ivs_sim* sim, const ivs_rf_model* model, co
  * whole beam (Ib = sum of the bunch currents, already divided by nmax), applied to every bunch -- the
  * grids carry the charge fractions (src/PS/PhaseSpace.cpp:17-66 with `filling`).  The simulation must have
  * been created with IVS_SIM_UNFUSED and a wake impedance (a train steps through the kernel sequence);
- * else IVS_ERR_UNSUPPORTED.  The kick of bunch b uses bunch b's wake potential, as the reference's OpenCL
- * kernel does; its CPU loop reads the offsets of bunches > 0 from the wrong place (src/SM/KickMap.cpp:244-259
- * lacks the factor _ip in the bunch offset), which is not reproduced. */
+ * else IVS_ERR_UNSUPPORTED.  The kick of bunch b uses bunch b's wake potential -- the entry
+ * KickMap::updateSM stores for it (src/SM/KickMap.cpp:348-372: bunch n, row x at (n N + x) _ip + j).  The
+ * reference's CPU loop reads the entries of bunches > 0 back from the wrong place (:244-259 lacks the factor
+ * _ip in the bunch offset) and its OpenCL kernels hold a single bunch; that slip is not reproduced
+ * (DESIGN.md section 10). */
 ivs_status ivs_sim_set_bunch_train(ivs_sim* sim, const uint32_t* bucket, uint32_t spacing_bins, const float* z,
                                    uint32_t nmax, float wakescaling);
 

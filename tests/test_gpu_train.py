@@ -48,7 +48,7 @@ def test_train_wake_potential_matches_oracle(capi, ctx_strict, oracle, rng, n, f
 
 def _oracle_train_steps(oracle, p, lay, z, grids, tables, steps):
     """main()'s loop (src/main.cpp:948-1053) over the bunches of a train with the oracle's maps; the wake kick
-    of bunch b uses bunch b's wake potential (the reference's OpenCL indexing; its CPU loop mis-indexes
+    of bunch b uses bunch b's wake potential (the entry KickMap::updateSM stores for it; the CPU loop mis-indexes
     bunches > 0, src/SM/KickMap.cpp:244-259)"""
     d = lay["d"]
     g = [np.array(x, f32) for x in grids]
