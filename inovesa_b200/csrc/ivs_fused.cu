@@ -1581,6 +1581,8 @@ ivs_status ivs_fused_enqueue_step(ivs_ctx* ctx, ivs_fused_plan* plan, ivs_sim* s
     a.host_flag = s->host_flag;
     a.n = s->n; a.it = s->it; a.hl = plan->halo_lo; a.hr = plan->halo_hi; a.pitch = s->n + 2 * kPad;
     a.has_wake = s->has_wake ? 1 : 0;
+    a.train_nb = s->train_windows ? s->members : 0;
+    a.train_windows = s->train_windows;
     ivs_status st;
     if (plan->stream8) {
         st = ivs_stream8_launch(ctx, plan, s, a);

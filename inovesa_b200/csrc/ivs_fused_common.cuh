@@ -27,6 +27,10 @@ struct fused_args {
     uint32_t n, it, hl, hr, pitch;
     int has_wake;
     int wb;          // which of the two wake buffers wake_out is: status[2 + wb] = ordinal of this step
+    // train of bunches (ivs_sim_set_bunch_train; column-block kernel only): the members are the bunches, coupled
+    // through train_windows[(b * train_nb + c) * 2 n + m + n - 1]; 0: independent members
+    uint32_t train_nb = 0;
+    const double* train_windows = nullptr;
 };
 
 struct stream_args {

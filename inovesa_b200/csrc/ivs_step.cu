@@ -605,10 +605,11 @@ ivs_status ivs_sim_set_bunch_train(ivs_sim* s, const uint32_t* bucket, uint32_t 
     if (!s) return IVS_ERR_INVALID_ARGUMENT;
     ivs_ctx* ctx = s->ctx;
     IVS_REQUIRE(ctx, bucket && z, "ivs_sim_set_bunch_train: null pointer");
-    if (!(s->desc.flags & IVS_SIM_UNFUSED) || !s->has_wake)
+    const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
+    if (!s->has_wake || !(unfused || s->plan.stream8) || s->np)
         return ivs_fail(ctx, IVS_ERR_UNSUPPORTED,
-                        "ivs_sim_set_bunch_train: a train of bunches steps through the kernel sequence "
-                        "(create the simulation with IVS_SIM_UNFUSED and a wake impedance)");
+                        "ivs_sim_set_bunch_train: a train of bunches needs a wake impedance, no tracked particles, and "
+                        "the column-block step kernel (N a multiple of 256 up to 2048) or the kernel sequence (IVS_SIM_UNFUSED)");
     IVS_REQUIRE(ctx, nmax >= 2 && !(nmax & (nmax - 1)), "ivs_sim_set_bunch_train: nmax must be a power of two");
     const uint32_t n = s->n, m = s->members;
     std::vector<double> w((size_t)m * m * 2 * n);
@@ -623,11 +624,20 @@ ivs_status ivs_sim_set_bunch_train(ivs_sim* s, const uint32_t* bucket, uint32_t 
     std::vector<float> sc(m, wakescaling);  // one ElectricField::_wakescaling for the whole beam
     IVS_TRY(ivs_upload(ctx, s->wakescaling, sc.data(), m * sizeof(float)));
     IVS_TRY(ivs_sync(ctx));
-    if (!was) {  // the step graphs call another wake kernel
+    s->plan.resident = false;  // (the persistent kernel keeps its members independent)
+    if (!was) {  // the step graphs call another wake kernel / another instantiation of the step kernel
         drop_graphs(s);
         if (!(s->desc.flags & IVS_SIM_NO_GRAPH)) {
-            IVS_TRY(capture(s, ivs_sim::kGraphSteps, &s->graphK[s->cur]));
-            IVS_TRY(capture(s, 1, &s->graph1[s->cur]));
+            const int cur = s->cur;
+            IVS_TRY(capture(s, ivs_sim::kGraphSteps, &s->graphK[cur]));
+            if (unfused) {
+                IVS_TRY(capture(s, 1, &s->graph1[cur]));
+            } else {
+                s->cur = s->pcur = cur ^ 1;
+                ivs_status st = capture(s, ivs_sim::kGraphSteps, &s->graphK[cur ^ 1]);
+                s->cur = s->pcur = cur;
+                if (st != IVS_OK) return st;
+            }
         }
     }
     return IVS_OK;

@@ -96,7 +96,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool FMA>
+// TRAIN: the members are the bunches of one train (ivs_sim_set_bunch_train): the Toeplitz product of the
+// set-up runs once per source bunch against that pair's window of the wake function.  A separate
+// instantiation, so that the code of the independent-members kernel (and its register allocation) is untouched.
+template <bool FMA, bool TRAIN>
 #ifdef IVS_S8_MAXNREG
 __global__ void __maxnreg__(IVS_S8_MAXNREG) stream8_step_kernel(
 #else
@@ -236,6 +239,34 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(
         }
     }
     __syncthreads();
+    const uint32_t nsrc = TRAIN ? g.train_nb : 1u;  // source bunches of the wake potential
+#pragma unroll 1
+    for (uint32_t src = 0; src < nsrc; src++) {
+    if (TRAIN && g.has_wake) {
+        // the profile of source bunch `src` and the window of the pair (member, src) replace what the
+        // set-up staged (src/PS/ElectricField.cpp:236-263: all bunches of the padded train act on each one)
+        __syncthreads();  // the previous pair's product has read rho and wwin
+        const float* rin = g.rho_in + (size_t)src * n;
+        const double* wf = g.train_windows + ((size_t)member * g.train_nb + src) * 2 * n;
+        // (T = n / 8 threads: 8 profile entries each, requested together; the window in batches of 8)
+        float rr[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) rr[k] = __ldg(rin + tid + k * T);
+        for (uint32_t t0 = tid; t0 < tcount; t0 += 8 * T) {
+            double ww[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) ww[k] = __ldg(wf + min(max(xs + (int)(t0 + k * T), 0), wtop));
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (t0 + k * T < tcount) wwin[wwin_pos(t0 + k * T)] = ww[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t i = tid + k * T;
+            rho[i + (i >> 5)] = (double)rr[k];
+        }
+        __syncthreads();
+    }
     if (g.has_wake) {
         // W[x] = scaling * sum_x' rho[x'] w[x-x']  (src/PS/ElectricField.cpp:186-253 as a Toeplitz
         // product).  Segment s sums x' in [128 s, 128 s + 128); a lane owns 8 consecutive rows and 32
@@ -271,11 +302,15 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(
                 if (sub == 0) {
 #pragma unroll
                     for (int j = 0; j < 8; j++)
-                        if (r0 + j < RIN) partial[(size_t)seg * sa.max_rin + r0 + j] = acc[j];
+                        if (r0 + j < RIN) {
+                            double* pp = partial + (size_t)seg * sa.max_rin + r0 + j;
+                            *pp = (TRAIN && src) ? *pp + acc[j] : acc[j];  // (the lane that wrote it adds to it)
+                        }
                 }
             }
         }
     }
+    }  // source bunches
     __syncthreads();
     {
         const float scal = g.has_wake ? g.wakescaling[member] : 0.0f;
@@ -683,7 +718,8 @@ bool ivs_stream8_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan, const int*
     const uint32_t H = plan->halo_lo + plan->halo_hi;
     const uint32_t threads = n / 8;
     const bool fma = ctx->arith == IVS_ARITH_FMA;
-    const void* kfn = fma ? (const void*)stream8_step_kernel<true> : (const void*)stream8_step_kernel<false>;
+    const void* kfn = fma ? (const void*)stream8_step_kernel<true, false> : (const void*)stream8_step_kernel<false, false>;
+    const void* kfn_train = fma ? (const void*)stream8_step_kernel<true, true> : (const void*)stream8_step_kernel<false, true>;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, kfn) != cudaSuccess) return false;
     const uint32_t regs_thread = (std::max(fa.numRegs, 32) + 7) & ~7;
@@ -713,6 +749,7 @@ bool ivs_stream8_plan(ivs_ctx* ctx, ivs_sim* s, ivs_fused_plan* plan, const int*
     }
     if (!bestP) return false;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem) != cudaSuccess) return false;
+    if (cudaFuncSetAttribute(kfn_train, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem) != cudaSuccess) return false;
     plan->stream8 = true;
     plan->strip = ivs_div_up(n, bestP);
     plan->max_strip = plan->strip;
@@ -731,8 +768,14 @@ ivs_status ivs_stream8_launch(ivs_ctx* ctx, const ivs_fused_plan* plan, const iv
     sa.strip = plan->strip; sa.kslots = plan->kslots;
     sa.max_strip = plan->max_strip; sa.max_rin = plan->max_rin; sa.wwin_len = plan->wwin_len;
     const dim3 sgrid(ivs_div_up(s->n, plan->strip), s->members);
-    if (ctx->arith == IVS_ARITH_FMA) stream8_step_kernel<true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
-    else stream8_step_kernel<false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+    if (sa.f.train_nb) {
+        if (ctx->arith == IVS_ARITH_FMA) stream8_step_kernel<true, true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+        else stream8_step_kernel<false, true><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+    } else if (ctx->arith == IVS_ARITH_FMA) {
+        stream8_step_kernel<true, false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+    } else {
+        stream8_step_kernel<false, false><<<sgrid, plan->threads, plan->smem, ctx->stream>>>(sa);
+    }
     IVS_LAUNCHED(ctx);
     return IVS_OK;
 }

@@ -139,7 +139,9 @@ def main(argv=None, out=sys.stdout):
         w[2:-1:2] *= 2.0
         charge = float((grid.astype(np.float64) * w[:, None] * w[None, :]).sum())  # Simpson, both axes
         grid = np.stack([grid * f32(fr / charge) for fr in lay["fractions"]]).astype(f32)
-        sim = capi.Simulation(ctx, params, len(bunches), grid=grid, flags=capi.SIM_UNFUSED, impedance_file=zfile)
+        # (the column-block step kernel takes a train at N = 256, 512, ... 2048; other sizes step through the kernel sequence)
+        train_flags = 0 if (n % 256 == 0 and n <= 2048) else capi.SIM_UNFUSED
+        sim = capi.Simulation(ctx, params, len(bunches), grid=grid, flags=train_flags, impedance_file=zfile)
     else:
         sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts, impedance_file=zfile)
         if opts["RenormalizeCharge"] >= 0:
@@ -153,7 +155,14 @@ def main(argv=None, out=sys.stdout):
     else:
         zw, nz = capi.wake_impedance(params, d, zfile, nfreqs=lay["spaced_bins"])  # src/main.cpp:718
         if nz:
-            sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], zw, lay["wakescaling"])
+            try:
+                sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], zw, lay["wakescaling"])
+            except capi.IvsError as e:
+                if e.code != capi.ERR_UNSUPPORTED or train_flags == capi.SIM_UNFUSED:
+                    raise
+                sim.close()  # no column-block plan for these maps: the kernel sequence takes any
+                sim = capi.Simulation(ctx, params, len(bunches), grid=grid, flags=capi.SIM_UNFUSED, impedance_file=zfile)
+                sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], zw, lay["wakescaling"])
     say("Starting the simulation.")
     t0 = time.time()
 

@@ -87,6 +87,35 @@ def test_train_simulation_matches_the_oracle(capi, ctx_strict, ctx_fma, oracle, 
     assert rel_l1(gi[nb - 1], want[nb - 1]) > 1e-4
 
 
+@pytest.mark.parametrize("mode", ["strict", "fma"])
+@pytest.mark.parametrize("n, filling", [(256, [3e-4, 0, 1e-4, 2e-4]), (512, [1e-4, 2e-4])])
+def test_train_through_the_column_block_kernel(capi, ctx_strict, ctx_fma, oracle, oracle_fma, mode, n, filling):
+    """the fused step of a train: the column-block kernel's set-up forms the Toeplitz product once per source
+    bunch (stream8_step_kernel<., TRAIN>); against the oracle's maps and against the kernel sequence"""
+    ctx, orc = (ctx_strict, oracle) if mode == "strict" else (ctx_fma, oracle_fma)
+    steps = 40
+    p, lay, z = _train(capi, n, filling, steps_per_Ts=1000)
+    d, nb = lay["d"], len(lay["buckets"])
+    g0 = capi.initial_grid(d, n, p.zoom)
+    grids = np.stack([np.roll(g0, 3 * b, axis=0) * f32(fr) for b, fr in enumerate(lay["fractions"])]).astype(f32)
+    out = {}
+    for name, flags in (("fused", 0), ("fused, one launch per step", capi.SIM_NO_GRAPH), ("sequence", capi.SIM_UNFUSED)):
+        sim = capi.Simulation(ctx, lay["params"], nb, grid=grids, flags=flags)
+        sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], z, lay["wakescaling"])
+        sim.step(steps)
+        out[name] = sim.download()
+        assert sim.fallback_steps == 0
+        tables = sim.tables
+        sim.close()
+    want = _oracle_train_steps(orc, p, lay, z, grids, tables, steps)
+    for b in range(nb):
+        assert rel_l1(out["fused"][0][b], want[b]) < 1e-5, b
+        assert rel_l1(out["fused"][0][b], out["sequence"][0][b]) < 2e-6, b
+    assert np.array_equal(out["fused"][0], out["fused, one launch per step"][0])
+    wf, ws = out["fused"][2], out["sequence"][2]  # the wake potentials applied by the last step
+    assert np.abs(wf - ws).max() < 1e-5 * np.abs(ws).max()  # (of states that differ by ~1e-6 after 40 steps)
+
+
 def test_train_of_one_bunch_is_the_single_bunch_run(capi, ctx_strict):
     """one bunch in bucket 0 with the single-bunch impedance table (same length, same scaling): the train's
     Toeplitz product and the single-bunch transform pair give the same run to the rounding of the fp32

@@ -22,8 +22,9 @@ with capi.Context(0, capi.ARITH_FMA) as ctx:
         g0 = capi.initial_grid(d, n, p.zoom)
         grids = np.stack([g0 * f32(fr) for fr in lay["fractions"]]).astype(f32)
         res = {}
-        for name, train in (("independent bunches", False), ("train", True)):
-            sim = capi.Simulation(ctx, lay["params"], nb, grid=grids, flags=capi.SIM_UNFUSED)
+        for name, train, fl in (("independent bunches", False, capi.SIM_UNFUSED), ("train", True, capi.SIM_UNFUSED),
+                                ("fused independent", False, capi.SIM_NO_PERSISTENT), ("fused train", True, 0)):
+            sim = capi.Simulation(ctx, lay["params"], nb, grid=grids, flags=fl)
             if train:
                 sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], z, lay["wakescaling"])
             sim.step(32); ctx.sync()
@@ -32,4 +33,5 @@ with capi.Context(0, capi.ARITH_FMA) as ctx:
             res[name] = (time.perf_counter() - t0) / steps * 1e6
             sim.close()
         print("n=%-5d %2d bunches: kernel sequence %.1f us per step with independent wakes (one FFT per bunch), "
-              "%.1f us as a train (Toeplitz products, %d x %d windows)" % (n, nb, res["independent bunches"], res["train"], nb, nb))
+              "%.1f us as a train (Toeplitz products, %d x %d windows); column-block kernel: %.1f us independent, %.1f us as a train"
+              % (n, nb, res["independent bunches"], res["train"], nb, nb, res["fused independent"], res["fused train"]))
