@@ -42,28 +42,34 @@ kick_y_kernel(const float* __restrict__ in, float* __restrict__ out, uint32_t n,
 }
 
 // ---------------------------------------------------------------- KickMap, Axis::x
-// src/SM/KickMap.cpp:221-242.  Thread = column y (coalesced along y), CTA = 32 columns x a
-// strip of rows; the per-column taps are computed once per thread and reused down the strip.
-constexpr int kXStrip = 64;
+// src/SM/KickMap.cpp:221-242.  Thread = column y (coalesced along y), CTA = 128 columns x a
+// strip of rows; the per-column taps are computed once per thread and reused down the strip, and the
+// four source rows of consecutive output rows overlap in three: they slide through registers, one load
+// per output row (rows outside the grid are skipped taps, as in the reference's loop).
 template <bool FMA>
 __global__ void __launch_bounds__(kThreads)
 kick_x_kernel(const float* __restrict__ in_all, float* __restrict__ out_all, uint32_t n,
-              const float* __restrict__ offset, uint32_t offset_stride, uint32_t it) {
+              const float* __restrict__ offset, uint32_t offset_stride, uint32_t it, uint32_t strip) {
     const uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= n) return;
     const float* in = in_all + (size_t)blockIdx.z * n * n;
     float* out = out_all + (size_t)blockIdx.z * n * n;
     const ivs_taps t = ivs_kick_taps(offset[blockIdx.z * offset_stride + y], n, it);
-    const uint32_t x0 = blockIdx.y * kXStrip;
-    const uint32_t x1 = min(x0 + kXStrip, n);
-    for (uint32_t x = x0; x < x1; x++) {
-        const int p = (int)x + t.first;
+    const uint32_t x0 = blockIdx.y * strip;
+    const uint32_t x1 = min(x0 + strip, n);
+    auto row = [&](int p) { return (uint32_t)p < n ? __ldg(in + (size_t)p * n + y) : 0.0f; };
+    int p = (int)x0 + t.first;
+    float r0 = row(p), r1 = row(p + 1), r2 = row(p + 2), r3;
+#pragma unroll 4
+    for (uint32_t x = x0; x < x1; x++, p++) {
+        r3 = row(p + 3);
         float v = 0.0f;
-        if ((uint32_t)(p) < n) v = madd<FMA>(in[(size_t)(p)*n + y], t.w[0], v);
-        if ((uint32_t)(p + 1) < n) v = madd<FMA>(in[(size_t)(p + 1) * n + y], t.w[1], v);
-        if ((uint32_t)(p + 2) < n) v = madd<FMA>(in[(size_t)(p + 2) * n + y], t.w[2], v);
-        if ((uint32_t)(p + 3) < n) v = madd<FMA>(in[(size_t)(p + 3) * n + y], t.w[3], v);
+        if ((uint32_t)(p) < n) v = madd<FMA>(r0, t.w[0], v);
+        if ((uint32_t)(p + 1) < n) v = madd<FMA>(r1, t.w[1], v);
+        if ((uint32_t)(p + 2) < n) v = madd<FMA>(r2, t.w[2], v);
+        if ((uint32_t)(p + 3) < n) v = madd<FMA>(r3, t.w[3], v);
         out[(size_t)x * n + y] = v;
+        r0 = r1; r1 = r2; r2 = r3;
     }
 }
 
@@ -358,9 +364,12 @@ ivs_status ivs_kick_x_batched(ivs_ctx* ctx, const float* in, float* out, uint32_
                               uint32_t members, const float* offset, uint32_t offset_stride,
                               uint32_t it) {
     const uint32_t bx = 128;
+    // rows per CTA: long strips amortise the three extra source rows, short ones fill the machine at small N
+    uint32_t strip = 64;
+    while (strip > 8 && (uint64_t)ivs_div_up(n, bx) * ivs_div_up(n, strip) * members < 2u * (uint32_t)ctx->sm_count) strip /= 2;
     return launch(ctx, kick_x_kernel<true>, kick_x_kernel<false>,
-                  dim3(ivs_div_up(n, bx), ivs_div_up(n, kXStrip), members), dim3(bx), 0, in, out, n,
-                  offset, offset_stride, it);
+                  dim3(ivs_div_up(n, bx), ivs_div_up(n, strip), members), dim3(bx), 0, in, out, n,
+                  offset, offset_stride, it, strip);
 }
 ivs_status ivs_fokker_planck_batched(ivs_ctx* ctx, const float* in, float* out, uint32_t n,
                                      uint32_t members, const float* w5) {
