@@ -20,7 +20,7 @@ for k, dst in (("stream8", "r2_ncu_stream8_step_top_stalls.txt"), ("resident", "
         subprocess.check_call([sys.executable, os.path.join(R, "tools", "ncu_src.py"), "25"], stdin=fi, stdout=fo)
 out = []
 titles = {"stream8": "stream8_step_kernel, one launch on the benchmark batch (26 x 2048^2, 442 CTAs x 256 threads)",
-          "track": "track_step_kernel, one launch (26 x 1e5 particles)",
+          "track": "track_step_staged_kernel, one launch (26 x 1e5 particles, 442 blocks x 512 threads)",
           "resident": "resident_run_kernel, one launch = 2000 steps of one 256^2 run (128 CTAs x 512 threads, cooperative)"}
 names = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
          "lts__t_sectors_srcunit_tex_op_write.sum", "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
