@@ -116,6 +116,27 @@ def test_train_through_the_column_block_kernel(capi, ctx_strict, ctx_fma, oracle
     assert np.abs(wf - ws).max() < 1e-5 * np.abs(ws).max()  # (of states that differ by ~1e-6 after 40 steps)
 
 
+def test_train_recovers_from_displacements_beyond_the_pad(capi, ctx_strict):
+    """a wake kick beyond the fused kernels' staged range is redone through the kernel sequence (DESIGN.md
+    section 6) -- with the train's wake potential, not the single bunch's"""
+    n, steps = 256, 24
+    p, lay, z = _train(capi, n, [2e-2, 2e-2], steps_per_Ts=1000)
+    d = lay["d"]
+    g0 = capi.initial_grid(d, n, p.zoom)
+    grids = np.stack([g0 * f32(fr) for fr in lay["fractions"]]).astype(f32)
+    out = {}
+    for name, flags in (("fused", 0), ("sequence", capi.SIM_UNFUSED)):
+        sim = capi.Simulation(ctx_strict, lay["params"], 2, grid=grids, flags=flags)
+        sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], z, lay["wakescaling"])
+        sim.step(steps)
+        out[name] = sim.download()[0]
+        if name == "fused":
+            assert sim.fallback_steps > 0
+        sim.close()
+    for b in range(2):
+        assert rel_l1(out["fused"][b], out["sequence"][b]) < 1e-5, b
+
+
 def test_train_of_one_bunch_is_the_single_bunch_run(capi, ctx_strict):
     """one bunch in bucket 0 with the single-bunch impedance table (same length, same scaling): the train's
     Toeplitz product and the single-bunch transform pair give the same run to the rounding of the fp32
