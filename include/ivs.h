@@ -320,8 +320,8 @@ ivs_status ivs_sim_set_rf_modulation(ivs_sim* sim, const ivs_rf_model* model, co
  * whole beam (Ib = sum of the bunch currents, already divided by nmax), applied to every bunch -- the
  * grids carry the charge fractions (src/PS/PhaseSpace.cpp:17-66 with `filling`).  A train steps through the
  * column-block step kernel (N a multiple of 256 up to 2048: its set-up forms the Toeplitz product once per
- * source bunch) or, with IVS_SIM_UNFUSED, through the kernel sequence; it needs a wake impedance and has no
- * tracked particles;
+ * source bunch; no tracked particles) or, with IVS_SIM_UNFUSED, through the kernel sequence (tracked particles
+ * of member b move in bunch b's fields); it needs a wake impedance;
  * else IVS_ERR_UNSUPPORTED.  The kick of bunch b uses bunch b's wake potential -- the entry
  * KickMap::updateSM stores for it (src/SM/KickMap.cpp:348-372: bunch n, row x at (n N + x) _ip + j).  The
  * reference's CPU loop reads the entries of bunches > 0 back from the wrong place (:244-259 lacks the factor

@@ -140,8 +140,10 @@ def main(argv=None, out=sys.stdout):
         charge = float((grid.astype(np.float64) * w[:, None] * w[None, :]).sum())  # Simpson, both axes
         grid = np.stack([grid * f32(fr / charge) for fr in lay["fractions"]]).astype(f32)
         # (the column-block step kernel takes a train at N = 256, 512, ... 2048; other sizes step through the kernel sequence)
-        train_flags = 0 if (n % 256 == 0 and n <= 2048) else capi.SIM_UNFUSED
-        sim = capi.Simulation(ctx, params, len(bunches), grid=grid, flags=train_flags, impedance_file=zfile)
+        # (tracked particles: the kernel sequence; they move in the fields of the first bunch, as the reference's
+        # applyTo reads the offsets of bunch 0, src/SM/KickMap.cpp:280-303 -- the result file keeps member 0's)
+        train_flags = 0 if (n % 256 == 0 and n <= 2048 and parts is None) else capi.SIM_UNFUSED
+        sim = capi.Simulation(ctx, params, len(bunches), grid=grid, particles=parts, flags=train_flags, impedance_file=zfile)
     else:
         sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts, impedance_file=zfile)
         if opts["RenormalizeCharge"] >= 0:
@@ -161,7 +163,7 @@ def main(argv=None, out=sys.stdout):
                 if e.code != capi.ERR_UNSUPPORTED or train_flags == capi.SIM_UNFUSED:
                     raise
                 sim.close()  # no column-block plan for these maps: the kernel sequence takes any
-                sim = capi.Simulation(ctx, params, len(bunches), grid=grid, flags=capi.SIM_UNFUSED, impedance_file=zfile)
+                sim = capi.Simulation(ctx, params, len(bunches), grid=grid, particles=parts, flags=capi.SIM_UNFUSED, impedance_file=zfile)
                 sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], zw, lay["wakescaling"])
     say("Starting the simulation.")
     t0 = time.time()

@@ -82,7 +82,7 @@ def test_driver_resumes_from_a_result_file(tmp_path, capi, ctx_fma):
 
 def test_driver_refuses_what_it_cannot_do(tmp_path):
     log = io.StringIO()
-    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3", "--tracking", "particles.txt"], out=log) == 1
+    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3", "--RenormalizeCharge", "10"], out=log) == 1
     assert "multi-bunch" in log.getvalue()
     log = io.StringIO()
     assert run.main(["-c", "/dev/null", "-i", "start.png"], out=log) == 1

@@ -137,6 +137,41 @@ def test_train_recovers_from_displacements_beyond_the_pad(capi, ctx_strict):
         assert rel_l1(out["fused"][b], out["sequence"][b]) < 1e-5, b
 
 
+def test_train_with_tracked_particles_on_the_kernel_sequence(capi, ctx_strict, oracle, rng):
+    """passive particles of member b move in bunch b's fields (wake kick from the train's wake potential of
+    that bunch, then RF kick, drift, Fokker-Planck applyTo): against the oracle's applyTo functions"""
+    n, steps = 128, 15
+    p, lay, z = _train(capi, n, [3e-4, 1e-4], steps_per_Ts=500)
+    p.fp_track = lay["params"].fp_track = 1
+    d = lay["d"]
+    g0 = capi.initial_grid(d, n, p.zoom)
+    grids = np.stack([g0 * f32(fr) for fr in lay["fractions"]]).astype(f32)
+    parts = (rng.random((400, 2)) * (n - 40) + 20).astype(f32)
+    sim = capi.Simulation(ctx_strict, lay["params"], 2, grid=grids, particles=parts, flags=capi.SIM_UNFUSED)
+    sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], z, lay["wakescaling"])
+    sim.step(steps)
+    got = sim.download()[3]
+    tables = sim.tables
+    sim.close()
+    g = [grids[0].copy(), grids[1].copy()]
+    pt = [parts.copy(), parts.copy()]
+    for _ in range(steps):
+        prof = np.stack([oracle.reduce(x, d.qmin, d.qmax, d.pmin, d.pmax)[0] for x in g])
+        wake = oracle.train_wake_potential(prof, lay["buckets"], lay["spacing_bins"], z, f32(lay["wakescaling"]))
+        for b in range(2):
+            t = oracle.kick_apply(g[b], wake[b], p.interpolation, 1)
+            pt[b] = oracle.kick_track(n, 1, wake[b], pt[b])
+            t = oracle.kick_apply(t, tables["rf"], p.interpolation, 1)
+            pt[b] = oracle.kick_track(n, 1, tables["rf"], pt[b])
+            t3 = oracle.kick_apply(t, tables["drift"], p.interpolation, 0)
+            pt[b] = oracle.kick_track(n, 0, tables["drift"], pt[b])
+            g[b] = oracle.fp_apply(t3, d.pmin, d.pmax, d.e1, p.fp_type, p.derivation)
+            pt[b] = oracle.fp_track(t3, d.pmin, d.pmax, d.e1, p.fp_type, p.derivation, 1, pt[b])
+    for b in range(2):
+        assert np.abs(got[b] - pt[b]).max() < 1e-3, b
+    assert np.abs(got[0] - got[1]).max() > 1e-3  # the two bunches' particles see different wakes
+
+
 def test_train_of_one_bunch_is_the_single_bunch_run(capi, ctx_strict):
     """one bunch in bucket 0 with the single-bunch impedance table (same length, same scaling): the train's
     Toeplitz product and the single-bunch transform pair give the same run to the rounding of the fp32
