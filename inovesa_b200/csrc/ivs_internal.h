@@ -27,7 +27,7 @@ ivs_status ivs_project_y_batched(ivs_ctx* ctx, const float* grid, uint32_t n, ui
 ivs_status ivs_integrate_batched(ivs_ctx* ctx, const float* proj, uint32_t n, uint32_t members,
                                  const float* ws, float* integral);
 ivs_status ivs_normalize_batched(ivs_ctx* ctx, float* grid, uint32_t n, uint32_t members,
-                                 float filling_set, const float* integral);
+                                 float filling_set, const float* integral, const float* filling_sets = nullptr);
 ivs_status ivs_moments_batched(ivs_ctx* ctx, const float* proj, uint32_t n, uint32_t members,
                                float amin, float delta, const float* integral, float* out3);
 // out-step observables formed by the field kernel in CSR mode: obs[member*8 + {integral, mean_q,

@@ -95,8 +95,9 @@ integrate_kernel(const float* __restrict__ proj, uint32_t n, const float* __rest
 // reference's `_data[n][x][y] *= _filling_set[n]/_filling[n]`)
 __global__ void __launch_bounds__(256)
 normalize_kernel(float* __restrict__ grid, size_t cells_per_member, float filling_set,
-                 const float* __restrict__ integral) {
-    const float s = __fdiv_rn(filling_set, integral[blockIdx.y]);
+                 const float* __restrict__ integral, const float* __restrict__ filling_sets) {
+    // filling_sets: one target per member (the bunches of a train carry their charge fractions), else filling_set
+    const float s = __fdiv_rn(filling_sets ? filling_sets[blockIdx.y] : filling_set, integral[blockIdx.y]);
     float* g = grid + (size_t)blockIdx.y * cells_per_member;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells_per_member;
          i += (size_t)gridDim.x * blockDim.x) {
@@ -159,10 +160,10 @@ ivs_status ivs_integrate_batched(ivs_ctx* ctx, const float* proj, uint32_t n, ui
     return IVS_OK;
 }
 ivs_status ivs_normalize_batched(ivs_ctx* ctx, float* grid, uint32_t n, uint32_t members,
-                                 float filling_set, const float* integral) {
+                                 float filling_set, const float* integral, const float* filling_sets) {
     const size_t cells = (size_t)n * n;
     const uint32_t bx = (uint32_t)((cells + 255) / 256 < 1184 ? (cells + 255) / 256 : 1184);
-    normalize_kernel<<<dim3(bx, members), 256, 0, ctx->stream>>>(grid, cells, filling_set, integral);
+    normalize_kernel<<<dim3(bx, members), 256, 0, ctx->stream>>>(grid, cells, filling_set, integral, filling_sets);
     IVS_LAUNCHED(ctx);
     return IVS_OK;
 }
@@ -200,7 +201,7 @@ ivs_status ivs_normalize(ivs_ctx* ctx, void* d_grid, uint32_t n, float filling_s
                          const void* d_integral) {
     if (!ctx) return IVS_ERR_INVALID_ARGUMENT;
     IVS_REQUIRE(ctx, d_grid && d_integral && n >= 2, "ivs_normalize: null pointer or n < 2");
-    return ivs_normalize_batched(ctx, (float*)d_grid, n, 1, filling_set, (const float*)d_integral);
+    return ivs_normalize_batched(ctx, (float*)d_grid, n, 1, filling_set, (const float*)d_integral, nullptr);
 }
 
 ivs_status ivs_moments(ivs_ctx* ctx, const void* d_proj, uint32_t n, float amin, float delta,

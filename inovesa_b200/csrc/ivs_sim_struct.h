@@ -54,6 +54,7 @@ struct ivs_sim {
     uint64_t rf_step0 = 0;
     // train of bunches (ivs_sim_set_bunch_train): the members are coupled through these wake-function windows
     double* train_windows = nullptr;  // [members][members][2 n]
+    float* train_filling = nullptr;   // [members] the bunches' charge fractions (their integrals when the train was set)
     float f_scale = 0, cutoff = 0;
     uint64_t steps_done = 0;
     ivs_fused_plan plan{};

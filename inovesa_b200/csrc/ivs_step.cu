@@ -278,6 +278,7 @@ ivs_status ivs_sim_destroy(ivs_sim* s) {
     for (int b = 0; b < 2; b++) if (s->ev_track[b]) cudaEventDestroy(s->ev_track[b]);
     if (s->wakebuf[1] && s->wakebuf[1] != s->wake) cudaFree(s->wakebuf[1]);
     if (s->train_windows) cudaFree(s->train_windows);
+    if (s->train_filling) cudaFree(s->train_filling);
     float* bufs[] = {s->grid[0], s->grid[1], s->grid[2], s->profile[0], s->profile[1], s->wake, s->rf,
                      s->drift, s->fpw, s->ws, s->impedance, s->rad_impedance, s->wakescaling,
                      (float*)s->wakefunction, s->particles, s->projy, s->obs, s->integral, s->moments, s->power,
@@ -539,7 +540,9 @@ ivs_status ivs_sim_renormalize(ivs_sim* s) {
     ivs_ctx* ctx = s->ctx;
     IVS_TRY(settle(s));
     IVS_TRY(ivs_integrate_batched(ctx, s->profile[s->pcur], s->n, s->members, s->ws, s->integral));
-    return ivs_normalize_batched(ctx, s->grid[s->cur], s->n, s->members, 1.0f, s->integral);
+    // (a train: every bunch back to the charge fraction it carried when the train was set, PhaseSpace::normalize
+    // with `filling`, src/PS/PhaseSpace.cpp:342-362)
+    return ivs_normalize_batched(ctx, s->grid[s->cur], s->n, s->members, 1.0f, s->integral, s->train_filling);
 }
 
 ivs_status ivs_sim_set_rf_offset(ivs_sim* s, const float* rf_offset) {
@@ -621,6 +624,10 @@ ivs_status ivs_sim_set_bunch_train(ivs_sim* s, const uint32_t* bucket, uint32_t 
     const bool was = s->train_windows != nullptr;
     if (!s->train_windows) IVS_TRY(dalloc(ctx, &s->train_windows, w.size()));
     IVS_TRY(ivs_upload(ctx, s->train_windows, w.data(), w.size() * sizeof(double)));
+    // the charge fractions the grids carry now are what ivs_sim_renormalize restores
+    if (!s->train_filling) IVS_TRY(dalloc(ctx, &s->train_filling, m));
+    IVS_TRY(ivs_integrate_batched(ctx, s->profile[s->pcur], n, m, s->ws, s->integral));
+    IVS_CUDA(ctx, cudaMemcpyAsync(s->train_filling, s->integral, m * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     std::vector<float> sc(m, wakescaling);  // one ElectricField::_wakescaling for the whole beam
     IVS_TRY(ivs_upload(ctx, s->wakescaling, sc.data(), m * sizeof(float)));
     IVS_TRY(ivs_sync(ctx));

@@ -247,8 +247,6 @@ class ProgramOptions:
         if len(self.bunch_currents()[1]) > 1:  # a train of bunches (PhaseSpace::nb > 1)
             if f:
                 bad.append("InitialDistFile with a multi-bunch filling pattern")
-            if self.values["RenormalizeCharge"] > 0:
-                bad.append("RenormalizeCharge > 0 (periodic renormalisation) with a multi-bunch filling pattern")
         return bad
 
     def save_text(self):

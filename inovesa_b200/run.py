@@ -165,6 +165,8 @@ def main(argv=None, out=sys.stdout):
                 sim.close()  # no column-block plan for these maps: the kernel sequence takes any
                 sim = capi.Simulation(ctx, params, len(bunches), grid=grid, particles=parts, flags=capi.SIM_UNFUSED, impedance_file=zfile)
                 sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], zw, lay["wakescaling"])
+            if opts["RenormalizeCharge"] >= 0:
+                sim.renormalize()  # every bunch to its charge fraction (src/main.cpp:528-532)
     say("Starting the simulation.")
     t0 = time.time()
 

@@ -82,7 +82,7 @@ def test_driver_resumes_from_a_result_file(tmp_path, capi, ctx_fma):
 
 def test_driver_refuses_what_it_cannot_do(tmp_path):
     log = io.StringIO()
-    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3", "--RenormalizeCharge", "10"], out=log) == 1
+    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3", "-i", "start.h5"], out=log) == 1
     assert "multi-bunch" in log.getvalue()
     log = io.StringIO()
     assert run.main(["-c", "/dev/null", "-i", "start.png"], out=log) == 1
@@ -99,7 +99,7 @@ def test_driver_runs_a_train_of_bunches(tmp_path, capi, ctx_fma):
     cfg.write_text(CFG.replace("GridSize = 256", "GridSize = 128").replace("BunchCurrent = 5e-5", ""))
     out = tmp_path / "train.h5"
     log = io.StringIO()
-    rc = run.main(["-c", str(cfg), "-o", str(out), "-I", "5e-5", "0", "1e-4"], out=log)
+    rc = run.main(["-c", str(cfg), "-o", str(out), "-I", "5e-5", "0", "1e-4", "--RenormalizeCharge", "40"], out=log)
     text = log.getvalue()
     assert rc == 0, text
     assert "2 bunches in 3 buckets" in text and "Finished 250 steps" in text
@@ -110,7 +110,7 @@ def test_driver_runs_a_train_of_bunches(tmp_path, capi, ctx_fma):
     assert data["/PhaseSpace/data"].shape == (1, 2, 128, 128)
     assert list(data["/Info/BucketNumbers"]) == [2, 0]
     pop = data["/BunchPopulation/data"]
-    assert np.allclose(pop[0], [1 / 3, 2 / 3], rtol=1e-5) and np.allclose(pop[-1], [1 / 3, 2 / 3], rtol=1e-3)
+    assert np.allclose(pop[0], [1 / 3, 2 / 3], rtol=1e-5) and np.allclose(pop[-1], [1 / 3, 2 / 3], rtol=1e-4)
     assert abs(attrs["/BunchProfile/data"]["AmperePerNBL"] - 1.5e-4) < 1e-9
     # the same run by hand
     p = kara_params(grid_size=128, steps_per_Ts=1000, gap=-1.0)

@@ -172,6 +172,26 @@ def test_train_with_tracked_particles_on_the_kernel_sequence(capi, ctx_strict, o
     assert np.abs(got[0] - got[1]).max() > 1e-3  # the two bunches' particles see different wakes
 
 
+def test_train_renormalisation_restores_the_charge_fractions(capi, ctx_fma):
+    """PhaseSpace::normalize with `filling` (src/PS/PhaseSpace.cpp:342-362): every bunch back to its fraction"""
+    n = 256
+    p, lay, z = _train(capi, n, [1e-4, 0, 3e-4], steps_per_Ts=1000)
+    d = lay["d"]
+    g0 = capi.initial_grid(d, n, p.zoom)
+    grids = np.stack([g0 * f32(fr) for fr in lay["fractions"]]).astype(f32)
+    sim = capi.Simulation(ctx_fma, lay["params"], 2, grid=grids)
+    sim.set_bunch_train(lay["buckets"], lay["spacing_bins"], z, lay["wakescaling"])
+    before = sim.observe()[:, 0]
+    assert np.allclose(before, lay["fractions"], rtol=1e-4)
+    sim.upload_grid(grids * f32(1.01))  # (charge drifts away ...)
+    sim.step(2)
+    assert not np.allclose(sim.observe()[:, 0], before, rtol=1e-3)
+    sim.renormalize()  # (... and is restored: the grid is rescaled, its projection follows with the next step)
+    sim.step(1)
+    assert np.allclose(sim.observe()[:, 0], before, rtol=2e-5)
+    sim.close()
+
+
 def test_train_of_one_bunch_is_the_single_bunch_run(capi, ctx_strict):
     """one bunch in bucket 0 with the single-bunch impedance table (same length, same scaling): the train's
     Toeplitz product and the single-bunch transform pair give the same run to the rounding of the fp32

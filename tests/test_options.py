@@ -80,7 +80,7 @@ def test_refusals():
     assert o.bunch_currents() == ([1e-3, 0.0, 2e-3], [1e-3, 2e-3])
     assert abs(o.ring_params().bunch_current - 3e-3) < 1e-9 and o.unsupported() == []  # a train: Ib = the sum
     o2 = ProgramOptions().parse(["-I", "1e-3", "2e-3", "--tracking", "t.txt", "--RenormalizeCharge", "5"], read_file=lambda _: None)
-    assert len(o2.unsupported()) == 1  # no periodic renormalisation with a train (passive particles are fine)
+    assert o2.unsupported() == []  # passive particles and periodic renormalisation work with a train
     with pytest.raises(OptionError):
         ProgramOptions().parse(["-I", "0", "0"], read_file=lambda _: None).ring_params()
     o = ProgramOptions().parse(["-Z", "impedance.dat", "-i", "start.png"], read_file=lambda _: None)
