@@ -244,9 +244,6 @@ class ProgramOptions:
         f = self.values["InitialDistFile"]
         if f and not f.endswith((".h5", ".hdf5")):
             bad.append("InitialDistFile (start distribution from a PNG or text file; result files (.h5) are read)")
-        if len(self.bunch_currents()[1]) > 1:  # a train of bunches (PhaseSpace::nb > 1)
-            if f:
-                bad.append("InitialDistFile with a multi-bunch filling pattern")
         return bad
 
     def save_text(self):

@@ -39,7 +39,7 @@ def read_tracking_file(path, d, n):
     return np.asarray(pts, f32).reshape(-1, 2)
 
 
-def read_start_distribution(path, step):
+def read_start_distribution(path, step, nbunches=1):
     """makePSFromHDF5 / HDF5File::readPhaseSpace (src/IO/HDF5File.cpp:425-480): row (rows + step) % rows of
     /PhaseSpace/data of an earlier result file; the grid size is the file's"""
     try:
@@ -52,13 +52,14 @@ def read_start_distribution(path, step):
     if ps.ndim not in (3, 4) or ps.shape[0] == 0:
         raise OptionError("%s: /PhaseSpace/data holds no phase space" % path)
     row = ps[(ps.shape[0] + step) % ps.shape[0]]
-    if row.ndim == 3:
-        if row.shape[0] != 1:
-            raise OptionError("%s: %d bunches (a start distribution holds one bunch)" % (path, row.shape[0]))
-        row = row[0]
-    if row.shape[0] != row.shape[1]:
+    if row.ndim == 2:
+        row = row[None]
+    if row.shape[0] != nbunches:
+        raise OptionError("%s: %d bunches in the file, %d in the filling pattern" % (path, row.shape[0], nbunches))
+    if row.shape[1] != row.shape[2]:
         raise OptionError("%s: phase space is not square" % path)
-    return np.ascontiguousarray(row, f32)
+    row = np.ascontiguousarray(row, f32)
+    return row[0] if nbunches == 1 else row  # a train: [bunch][x][y], every bunch carrying its charge fraction
 
 
 def rf_noise(opts, params, d, laststep, seed):
@@ -95,11 +96,11 @@ def main(argv=None, out=sys.stdout):
     if opts["InitialDistFile"]:  # (.h5 / .hdf5: checked by ProgramOptions.unsupported)
         say('Reading in initial distribution from: "%s"' % opts["InitialDistFile"])
         try:
-            grid = read_start_distribution(opts["InitialDistFile"], opts["InitialDistStep"])
+            grid = read_start_distribution(opts["InitialDistFile"], opts["InitialDistStep"], len(opts.bunch_currents()[1]))
         except (OptionError, OSError, KeyError, ValueError) as e:
             say("Error reading %s: %s" % (opts["InitialDistFile"], e))
             return 0  # (EXIT_SUCCESS, src/main.cpp:509-512)
-        params.grid_size = grid.shape[0]
+        params.grid_size = grid.shape[-1]
     d = capi.derive(params)
     laststep = int(np.floor(d.steps * opts["rotations"] + 0.5)) if opts["rotations"] > 0 else 0
     ofname = opts["output"]
@@ -134,11 +135,12 @@ def main(argv=None, out=sys.stdout):
         lay = capi.train_layout(params, filling)
         say("Filling pattern: %d bunches in %d buckets, %d bins apart, padded profile of the train %d bins" % (
             len(bunches), len(filling), lay["spacing_bins"], lay["spaced_bins"]))
-        w = np.full(n, d.dq / 3.0)
-        w[1:-1:2] *= 4.0
-        w[2:-1:2] *= 2.0
-        charge = float((grid.astype(np.float64) * w[:, None] * w[None, :]).sum())  # Simpson, both axes
-        grid = np.stack([grid * f32(fr / charge) for fr in lay["fractions"]]).astype(f32)
+        if grid.ndim == 2:  # (a start distribution read from a result file already holds the bunches)
+            w = np.full(n, d.dq / 3.0)
+            w[1:-1:2] *= 4.0
+            w[2:-1:2] *= 2.0
+            charge = float((grid.astype(np.float64) * w[:, None] * w[None, :]).sum())  # Simpson, both axes
+            grid = np.stack([grid * f32(fr / charge) for fr in lay["fractions"]]).astype(f32)
         # (the column-block step kernel takes a train at N = 256, 512, ... 2048; other sizes step through the kernel sequence)
         # (tracked particles: the kernel sequence; they move in the fields of the first bunch, as the reference's
         # applyTo reads the offsets of bunch 0, src/SM/KickMap.cpp:280-303 -- the result file keeps member 0's)

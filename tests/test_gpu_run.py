@@ -82,9 +82,6 @@ def test_driver_resumes_from_a_result_file(tmp_path, capi, ctx_fma):
 
 def test_driver_refuses_what_it_cannot_do(tmp_path):
     log = io.StringIO()
-    assert run.main(["-c", "/dev/null", "-I", "1e-3", "1e-3", "-i", "start.h5"], out=log) == 1
-    assert "multi-bunch" in log.getvalue()
-    log = io.StringIO()
     assert run.main(["-c", "/dev/null", "-i", "start.png"], out=log) == 1
     assert "InitialDistFile" in log.getvalue()
     log = io.StringIO()
@@ -117,3 +114,24 @@ def test_driver_runs_a_train_of_bunches(tmp_path, capi, ctx_fma):
     lay = capi.train_layout(p, [5e-5, 0, 1e-4])
     assert lay["spaced_bins"] == data["/Impedance/data/real"].shape[0] * 2
     assert np.abs(data["/WakePotential/data"][-1, 1]).max() > 0
+
+
+def test_driver_resumes_a_train(tmp_path, capi, ctx_fma):
+    """-i result.h5 with a filling pattern: the file's [bunch][x][y] row is the start distribution of the train;
+    100 + 100 steps equal 200 in one go bit for bit"""
+    cfg = tmp_path / "kara.cfg"
+    cfg.write_text(CFG.replace("rotations = 0.25", "rotations = 0.1").replace("BunchCurrent = 5e-5", ""))
+    a, b, c = (str(tmp_path / n) for n in ("a.h5", "b.h5", "c.h5"))
+    fill = ["-I", "5e-5", "1e-4", "--RenormalizeCharge", "-1"]
+    log = io.StringIO()
+    assert run.main(["-c", str(cfg), "-o", a] + fill, out=log) == 0, log.getvalue()
+    assert run.main(["-c", str(cfg), "-o", b, "-i", a] + fill, out=log) == 0, log.getvalue()
+    assert run.main(["-c", str(cfg), "-o", c, "-T", "0.2"] + fill, out=log) == 0, log.getvalue()
+    from inovesa_b200.h5native import read_dataset
+    end_b = read_dataset(b, "/PhaseSpace/data")[-1]
+    end_c = read_dataset(c, "/PhaseSpace/data")[-1]
+    assert end_b.shape == (2, 256, 256) and np.array_equal(end_b, end_c)
+    log = io.StringIO()  # one bunch in the file, two in the pattern
+    single = str(tmp_path / "single.h5")
+    assert run.main(["-c", str(cfg), "-o", single, "-I", "5e-5"], out=log) == 0
+    assert run.main(["-c", str(cfg), "-i", single] + fill, out=log) == 0 and "2 in the filling pattern" in log.getvalue()
