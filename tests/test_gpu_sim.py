@@ -195,11 +195,12 @@ def test_tracking_with_staged_tables_equals_tracking_with_gathers(capi, ctx_stri
     p = kara_params(grid_size=256)
     p.fp_track = 1
     parts = (rng.random((6001, 2)) * 200 + 28).astype(f32)
-    for members in (1, 3):
-        (_, _, _, even), = _states(capi, ctx_strict, p, 0, [37], particles=parts[:6000], members=members)
-        (_, _, _, odd), = _states(capi, ctx_strict, p, 0, [37], particles=parts, members=members)
-        assert even.shape[-2] == 6000 and odd.shape[-2] == 6001
-        assert np.array_equal(even, odd[..., :6000, :])
+    # (one chunk per member when there are more members than resident blocks; a launch of a single pair)
+    for members, k, steps in ((1, 6000, 37), (3, 6000, 37), (700, 64, 5), (2, 2, 20)):
+        (_, _, _, even), = _states(capi, ctx_strict, p, 0, [steps], particles=parts[:k], members=members)
+        (_, _, _, odd), = _states(capi, ctx_strict, p, 0, [steps], particles=parts[:k + 1], members=members)
+        assert even.shape[-2] == k and odd.shape[-2] == k + 1
+        assert np.array_equal(even, odd[..., :k, :])
 
 
 def test_stochastic_tracking_is_reproducible_and_graph_safe(capi, ctx_fma, rng):
