@@ -285,6 +285,26 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(
                     wv[j] = wwin[wwin_pos(t0 + j)];
                     acc[j] = 0.0;
                 }
+#ifdef IVS_S8_WAKE_F32
+                // TIMING PROBE ONLY (not the reference's numbers to the last bit): the 32-term inner sums in fp32,
+                // i.e. with the accuracy of the reference's own fp32 transforms; the outer sums stay in double
+                {
+                    float wf[8], af[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { wf[j] = (float)wv[j]; af[j] = 0.0f; }
+#pragma unroll 8
+                    for (uint32_t k = 0; k < 32; k++) {
+                        const float rh = (float)rp[k];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) af[j] = __fmaf_rn(rh, wf[j], af[j]);
+#pragma unroll
+                        for (int j = 7; j > 0; j--) wf[j] = wf[j - 1];
+                        wf[0] = (float)wwin[wwin_pos(max((int)(t0 - k) - 1, 0))];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[j] = (double)af[j];
+                }
+#else
 #pragma unroll 8
                 for (uint32_t k = 0; k < 32; k++) {
                     const double rh = rp[k];
@@ -294,6 +314,7 @@ __global__ void __launch_bounds__(256, 1) stream8_step_kernel(
                     for (int j = 7; j > 0; j--) wv[j] = wv[j - 1];
                     wv[0] = wwin[wwin_pos(max((int)(t0 - k) - 1, 0))];
                 }
+#endif
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
