@@ -198,7 +198,9 @@ constexpr int kRotGY = 4;  // row groups of a CTA: thread (c, g) forms the rows 
 
 __device__ __forceinline__ uint32_t rot_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool FMA>
+// CLAMP: the clamp of the cubic map (src/SM/RotationMap.cpp:161-171) as a template parameter, so that the
+// unclamped map does not pay for the min / max of the four inner source cells
+template <bool FMA, bool CLAMP>
 __global__ void __launch_bounds__(kRotTY * kRotGY)
 rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_params p, uint32_t cap_rows,
                    uint32_t pitch) {
@@ -291,13 +293,13 @@ rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_pa
                 for (int j1 = 0; j1 < 4; j1++) {
                     const float src = t0[(size_t)i1 * pitch + j1];
                     v = madd<FMA>(src, IVS_MUL(icq[i1], icp[j1]), v);
-                    if (p.clamp && i1 >= 1 && i1 <= 2 && j1 >= 1 && j1 <= 2) {
+                    if (CLAMP && i1 >= 1 && i1 <= 2 && j1 >= 1 && j1 <= 2) {
                         ceil = (ceil < src) ? src : ceil;  // std::max(ceil, src)
                         flor = (src < flor) ? src : flor;  // std::min(flor, src)
                     }
                 }
             }
-            if (p.clamp) {
+            if (CLAMP) {
                 const float m = (v < ceil) ? v : ceil;  // std::min(ceil, v)
                 v = (m < flor) ? flor : m;              // std::max(m, flor)
             }
@@ -315,17 +317,17 @@ rotate_tile_kernel(const float* __restrict__ in, float* __restrict__ out, rot_pa
                     if (ok) src = staged ? tile[(size_t)((int)i0 - r0) * pitch + ((int)j0 - c0)] : in[(size_t)i0 * n + j0];
                     const float w = ok ? IVS_MUL(icq[i1], icp[j1]) : 0.0f;
                     v = madd<FMA>(src, w, v);
-                    if (p.clamp && i1 >= 1 && i1 <= 2 && j1 >= 1 && j1 <= 2) {
+                    if (CLAMP && i1 >= 1 && i1 <= 2 && j1 >= 1 && j1 <= 2) {
                         ceil = (ceil < src) ? src : ceil;  // std::max(ceil, src)
                         flor = (src < flor) ? src : flor;  // std::min(flor, src)
                     }
                 }
             }
-            if (p.clamp) {
+            if (CLAMP) {
                 const float m = (v < ceil) ? v : ceil;  // std::min(ceil, v)
                 v = (m < flor) ? flor : m;              // std::max(m, flor)
             }
-        } else if (p.clamp) {
+        } else if (CLAMP) {
             // all 16 taps are {0,0}: value 0 clamped to [in[0], in[0]] (:161-171)
             float ceil = 1.17549435e-38f, flor = 3.402823466e+38f;
             ceil = (ceil < in0) ? in0 : ceil;
@@ -460,13 +462,18 @@ ivs_status ivs_rotate(ivs_ctx* ctx, const void* d_in, void* d_out, uint32_t n, f
     // once per context: the attribute belongs to the kernel (two API calls of 15 us each otherwise)
     const bool opted_in = (ctx->optin & 1u) != 0;
     if (smem > 40 * 1024 && !opted_in) {
-        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
-        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
+        IVS_CUDA(ctx, cudaFuncSetAttribute(rotate_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvsMaxOptinSmem));
         ctx->optin |= 1u;
     }
-    return launch(ctx, rotate_tile_kernel<true>, rotate_tile_kernel<false>,
-                  dim3(ivs_div_up(n, kRotTY), ivs_div_up(n, kRotTX)), dim3(kRotTY, kRotGY), smem, (const float*)d_in,
-                  (float*)d_out, p, cap_rows, pitch);
+    const dim3 grid(ivs_div_up(n, kRotTY), ivs_div_up(n, kRotTX)), block(kRotTY, kRotGY);
+    if (clamp)
+        return launch(ctx, rotate_tile_kernel<true, true>, rotate_tile_kernel<false, true>, grid, block, smem,
+                      (const float*)d_in, (float*)d_out, p, cap_rows, pitch);
+    return launch(ctx, rotate_tile_kernel<true, false>, rotate_tile_kernel<false, false>, grid, block, smem,
+                  (const float*)d_in, (float*)d_out, p, cap_rows, pitch);
 }
 
 }  // extern "C"
