@@ -320,8 +320,8 @@ ivs_status ivs_sim_set_rf_modulation(ivs_sim* sim, const ivs_rf_model* model, co
  * whole beam (Ib = sum of the bunch currents, already divided by nmax), applied to every bunch -- the
  * grids carry the charge fractions (src/PS/PhaseSpace.cpp:17-66 with `filling`).  A train steps through the
  * column-block step kernel (N a multiple of 256 up to 2048: its set-up forms the Toeplitz product once per
- * source bunch; no tracked particles) or, with IVS_SIM_UNFUSED, through the kernel sequence (tracked particles
- * of member b move in bunch b's fields); it needs a wake impedance.  ivs_sim_renormalize restores the charge
+ * source bunch) or, with IVS_SIM_UNFUSED, through the kernel sequence; tracked particles of member b move in
+ * bunch b's fields; it needs a wake impedance.  ivs_sim_renormalize restores the charge
  * fraction every bunch carries at this call (PhaseSpace::normalize with `filling`, src/PS/PhaseSpace.cpp:342-362);
  * else IVS_ERR_UNSUPPORTED.  The kick of bunch b uses bunch b's wake potential -- the entry
  * KickMap::updateSM stores for it (src/SM/KickMap.cpp:348-372: bunch n, row x at (n N + x) _ip + j).  The

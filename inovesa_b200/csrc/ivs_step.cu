@@ -609,10 +609,10 @@ ivs_status ivs_sim_set_bunch_train(ivs_sim* s, const uint32_t* bucket, uint32_t 
     ivs_ctx* ctx = s->ctx;
     IVS_REQUIRE(ctx, bucket && z, "ivs_sim_set_bunch_train: null pointer");
     const bool unfused = (s->desc.flags & IVS_SIM_UNFUSED) != 0;
-    if (!s->has_wake || !(unfused || (s->plan.stream8 && !s->np)))
+    if (!s->has_wake || !(unfused || s->plan.stream8))
         return ivs_fail(ctx, IVS_ERR_UNSUPPORTED,
                         "ivs_sim_set_bunch_train: a train of bunches needs a wake impedance and either the column-block step "
-                        "kernel (N a multiple of 256 up to 2048, no tracked particles) or the kernel sequence (IVS_SIM_UNFUSED)");
+                        "kernel (N a multiple of 256 up to 2048) or the kernel sequence (IVS_SIM_UNFUSED)");
     IVS_REQUIRE(ctx, nmax >= 2 && !(nmax & (nmax - 1)), "ivs_sim_set_bunch_train: nmax must be a power of two");
     const uint32_t n = s->n, m = s->members;
     std::vector<double> w((size_t)m * m * 2 * n);

@@ -142,9 +142,9 @@ def main(argv=None, out=sys.stdout):
             charge = float((grid.astype(np.float64) * w[:, None] * w[None, :]).sum())  # Simpson, both axes
             grid = np.stack([grid * f32(fr / charge) for fr in lay["fractions"]]).astype(f32)
         # (the column-block step kernel takes a train at N = 256, 512, ... 2048; other sizes step through the kernel sequence)
-        # (tracked particles: the kernel sequence; they move in the fields of the first bunch, as the reference's
-        # applyTo reads the offsets of bunch 0, src/SM/KickMap.cpp:280-303 -- the result file keeps member 0's)
-        train_flags = 0 if (n % 256 == 0 and n <= 2048 and parts is None) else capi.SIM_UNFUSED
+        # (tracked particles move in the fields of the first bunch, as the reference's applyTo reads the offsets of
+        # bunch 0, src/SM/KickMap.cpp:280-303: the result file keeps member 0's)
+        train_flags = 0 if (n % 256 == 0 and n <= 2048) else capi.SIM_UNFUSED
         sim = capi.Simulation(ctx, params, len(bunches), grid=grid, particles=parts, flags=train_flags, impedance_file=zfile)
     else:
         sim = capi.Simulation(ctx, params, 1, grid=grid, particles=parts, impedance_file=zfile)

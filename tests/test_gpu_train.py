@@ -137,7 +137,7 @@ def test_train_recovers_from_displacements_beyond_the_pad(capi, ctx_strict):
         assert rel_l1(out["fused"][b], out["sequence"][b]) < 1e-5, b
 
 
-def test_train_with_tracked_particles_on_the_kernel_sequence(capi, ctx_strict, oracle, rng):
+def test_train_with_tracked_particles(capi, ctx_strict, oracle, rng):
     """passive particles of member b move in bunch b's fields (wake kick from the train's wake potential of
     that bunch, then RF kick, drift, Fokker-Planck applyTo): against the oracle's applyTo functions"""
     n, steps = 128, 15
@@ -170,6 +170,23 @@ def test_train_with_tracked_particles_on_the_kernel_sequence(capi, ctx_strict, o
     for b in range(2):
         assert np.abs(got[b] - pt[b]).max() < 1e-3, b
     assert np.abs(got[0] - got[1]).max() > 1e-3  # the two bunches' particles see different wakes
+    # the same through the column-block kernel (its tracking kernel reads the train's wake potential from the
+    # step kernel's wake buffer), side-stream and in-line tracking
+    n2 = 256
+    p2, lay2, z2 = _train(capi, n2, [3e-4, 1e-4], steps_per_Ts=1000)
+    p2.fp_track = lay2["params"].fp_track = 1
+    g2 = capi.initial_grid(lay2["d"], n2, p2.zoom)
+    grids2 = np.stack([g2 * f32(fr) for fr in lay2["fractions"]]).astype(f32)
+    parts2 = (rng.random((1000, 2)) * (n2 - 80) + 40).astype(f32)
+    res = {}
+    for name, flags in (("fused", 0), ("fused, in line", capi.SIM_TRACK_INLINE), ("sequence", capi.SIM_UNFUSED)):
+        sim = capi.Simulation(ctx_strict, lay2["params"], 2, grid=grids2, particles=parts2, flags=flags)
+        sim.set_bunch_train(lay2["buckets"], lay2["spacing_bins"], z2, lay2["wakescaling"])
+        sim.step(35)
+        res[name] = sim.download()[3]
+        sim.close()
+    assert np.abs(res["fused"] - res["sequence"]).max() < 1e-3
+    assert np.array_equal(res["fused"], res["fused, in line"])
 
 
 def test_train_renormalisation_restores_the_charge_fractions(capi, ctx_fma):
