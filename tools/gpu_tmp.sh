@@ -1,22 +1,14 @@
-# ncu --set full of the kernels beside the fused step: field kernel (nmax 2048), unfused maps at 2048^2, train wake kernel
-ncu --set full --clock-control none -k regex:"field_kernel|kick_y|kick_x|fokker_planck|project_x" -s 0 -c 400 -f -o gpurun_out/r2_side python tools/kernel_times.py 2 > gpurun_out/side.log 2>&1
-ncu -i gpurun_out/r2_side.ncu-rep --page raw --csv > gpurun_out/r2_side_raw.csv 2>&1
+# device times of the train kernels (cold, serialised): the Toeplitz kernel of the kernel sequence and the TRAIN
+# instantiation of the column-block kernel, last launches of tools/train_times.py 40
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum --clock-control none -k regex:"train_wake_kernel|stream8_step_kernel" --csv --log-file gpurun_out/r2_train_launches.csv python tools/train_times.py 40 > gpurun_out/train_ncu.log 2>&1
 python - <<'PY'
 import csv
-rows = list(csv.reader(open("gpurun_out/r2_side_raw.csv")))
-hdr = next(r for r in rows if r and r[0] == "ID")
-i0 = rows.index(hdr)
-col = {h: i for i, h in enumerate(hdr)}
-want = ["Kernel Name", "launch__grid_size", "launch__block_size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread"]
-print("units:", [rows[i0 + 1][col[w]] for w in want if w in col])
-seen = {}
-for r in rows[i0 + 2:]:
-    if len(r) < len(hdr):
-        continue
-    key = (r[col["Kernel Name"]][:60], r[col["launch__grid_size"]])
-    seen[key] = [r[col[w]] for w in want if w in col]   # the last launch of each (kernel, grid) pair
-for k, v in seen.items():
-    print(" | ".join(v))
+rows = [r for r in csv.reader(open("gpurun_out/r2_train_launches.csv")) if len(r) > 10]
+hdr = rows[0]; col = {h: i for i, h in enumerate(hdr)}
+last = {}
+for r in rows[1:]:
+    key = (r[col["Kernel Name"]][:70], r[col["Grid Size"]], r[col["Block Size"]], r[col["Metric Name"]])
+    last[key] = r[col["Metric Value"]] + " " + r[col["Metric Unit"]]
+for k in sorted(last):
+    print(" | ".join(k), "=", last[k])
 PY
